@@ -1,0 +1,21 @@
+"""CPU oracle for the DynamiCrafter denoising hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``dynamicrafter_b200/`` may import this
+package; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs do, and only as the checker / the
+reported CPU baseline.
+
+The oracle is a *functional restatement* (plain torch fp32 on CPU, no nn.Module,
+weights read straight out of a ``state_dict``) of the reference algorithm:
+
+* ``unet_oracle.unet_forward``      <- lvdm/modules/networks/openaimodel3d.py:548-603
+* ``vae_oracle.decode``             <- lvdm/models/autoencoder.py:104-107,
+                                       lvdm/modules/networks/ae_modules.py:539-578
+* ``ddim_oracle.DDIMOracle.sample`` <- lvdm/models/samplers/ddim.py:24-279
+
+Parity pin: the reference ships no tests or golden vectors, so
+the oracle is pinned against outputs of the reference itself, imported in the
+build container from /root/reference by ``oracle/make_golden.py`` and committed
+as small fixtures under ``tests/golden/``.  ``tests/test_oracle_golden.py``
+re-checks the oracle against those fixtures on every run (CPU).
+"""

@@ -1,0 +1,130 @@
+"""Pin the CPU oracle against outputs of the unmodified reference (tests/golden, made by
+oracle/make_golden.py in the build container).  CPU-only; runs everywhere."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+from dynamicrafter_b200.synth import synth_state_dict, synth_input
+from oracle import unet_oracle, vae_oracle, ddim_oracle
+
+TOL = 2e-5   # fp32 eager vs fp32 functional restatement: only summation-order noise
+
+
+def _unet_case(name):
+    g = load_golden(name)
+    cfg, b, h, w, seed = g["cfg"], g["b"], g["h"], g["w"], g["seed"]
+    sd = synth_state_dict(g["shapes"], seed)
+    T = cfg["temporal_length"]
+    x = synth_input("x", (b, cfg["in_channels"], T, h, w), seed)
+    ctx = synth_input("context", (b, 77 + 16 * T, cfg["context_dim"]), seed)
+    ts = torch.tensor([g["t_val"] - 7 * i for i in range(b)], dtype=torch.long)
+    fs = torch.tensor([cfg["default_fs"] + 2 * i for i in range(b)], dtype=torch.long) if g["with_fs"] else None
+    assert abs(float(x.double().sum()) - g["x_sum"]) < 1e-6
+    assert abs(float(ctx.double().sum()) - g["ctx_sum"]) < 1e-6
+    return g, cfg, sd, x, ts, ctx, fs
+
+
+@pytest.mark.parametrize("name", ["unet_tiny512.pt", "unet_tiny512_b2.pt", "unet_tiny256.pt"])
+def test_unet_oracle_matches_reference(name):
+    g, cfg, sd, x, ts, ctx, fs = _unet_case(name)
+    y = unet_oracle.unet_forward(sd, cfg, x, ts, ctx, fs)
+    assert y.shape == g["y"].shape
+    assert rel_l2(y, g["y"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["unet_tiny512.pt", "unet_tiny256.pt"])
+def test_module_oracles_match_reference(name):
+    g, cfg, sd, *_ = _unet_case(name)
+    b, h, w, seed, T = g["b"], g["h"], g["w"], g["seed"], cfg["temporal_length"]
+    mc = cfg["model_channels"]
+    emb = synth_input("emb", (b * T, 4 * mc), seed)
+    hx = synth_input("h", (b * T, mc, h, w), seed)
+    ctxf = synth_input("ctx_frames", (b * T, 77 + 16, cfg["context_dim"]), seed)
+    learn = bool(cfg.get("image_cross_attention_scale_learnable", False))
+    r = unet_oracle.res_block(sd, "input_blocks.1.0", hx, emb, b)
+    s = unet_oracle.spatial_transformer(sd, "input_blocks.1.1", hx, ctxf, mc // 64, 64, learn)
+    h5 = hx.reshape(b, T, mc, h, w).permute(0, 2, 1, 3, 4)
+    tt = unet_oracle.temporal_transformer(sd, "input_blocks.1.2", h5, mc // 64, 64)
+    assert rel_l2(r[:, ::4], g["res"]) < TOL
+    assert rel_l2(s[:, ::4], g["st"]) < TOL
+    assert rel_l2(tt[:, ::4], g["tt"]) < TOL
+
+
+def test_vae_oracle_matches_reference():
+    g = load_golden("vae_tiny.pt")
+    sd = synth_state_dict(g["shapes"], g["seed"])
+    z = synth_input("z", g["zshape"], g["seed"])
+    y = vae_oracle.decode(sd, g["dd"], z)
+    assert rel_l2(y, g["y"]) < TOL
+
+
+SCHED = {
+    "c1": dict(kw=dict(parameterization="eps"), S=10, spacing="uniform", eta=1.0),
+    "c2": dict(kw=dict(parameterization="v", rescale_betas_zero_snr=True, use_dynamic_rescale=True,
+                       base_scale=0.7), S=50, spacing="uniform_trailing", eta=1.0),
+    "c2_eta0": dict(kw=dict(parameterization="v", rescale_betas_zero_snr=True, use_dynamic_rescale=True,
+                            base_scale=0.7), S=50, spacing="uniform_trailing", eta=0.0),
+}
+
+
+@pytest.mark.parametrize("tag", list(SCHED))
+def test_schedule_tables_bit_exact(tag):
+    g = load_golden("ddim.pt")["tables_" + tag]
+    c = SCHED[tag]
+    tab = ddim_oracle.DiffusionTables(**c["kw"])
+    dt = ddim_oracle.ddim_tables(tab, c["S"], c["spacing"], c["eta"])
+    assert np.array_equal(np.asarray(dt["timesteps"]), g["timesteps"].numpy())
+    for k in ("alphas", "alphas_prev", "sigmas", "sqrt_one_minus_alphas"):
+        got = torch.as_tensor(dt[k])
+        assert got.dtype == g[k].dtype, (k, got.dtype, g[k].dtype)
+        assert torch.equal(got, g[k]), k
+    for k in ("alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod"):
+        assert torch.equal(getattr(tab, k), g[k]), k
+    if "scale" in g:
+        assert torch.equal(dt["scale"], g["scale"]) and torch.equal(dt["scale_prev"], g["scale_prev"])
+        assert torch.equal(tab.scale_arr, g["scale_arr"])
+
+
+@pytest.mark.parametrize("tag,eta", [("mock_c2", 0.0), ("mock_c2", 1.0), ("mock_c1", 0.0), ("mock_c1", 1.0)])
+def test_sampler_with_mock_denoiser(tag, eta):
+    g = load_golden("ddim.pt")[f"{tag}_eta{int(eta)}"]
+    c = SCHED["c2" if tag.endswith("c2") else "c1"]
+    tab = ddim_oracle.DiffusionTables(**c["kw"])
+    gr = 0.7 if tag.endswith("c2") else 0.0
+    torch.manual_seed(0)
+    samples, inter = ddim_oracle.sample(
+        tab, lambda x, t, cnd: torch.tanh(0.3 * x + cnd), c["S"], (2, 4, 16, 8, 8),
+        torch.tensor([0.1]), uncond=torch.tensor([-0.1]), ucg_scale=7.5, eta=eta,
+        timestep_spacing=c["spacing"], guidance_rescale=gr)
+    assert len(inter["x_inter"]) == g["n_inter"]
+    assert torch.equal(samples, g["samples"])          # same torch ops, same RNG stream: bit-exact
+    assert torch.equal(inter["pred_x0"][-1], g["last_pred_x0"])
+
+
+@pytest.mark.parametrize("tag", ["e2e_c2", "e2e_c1"])
+def test_end_to_end_oracle(tag):
+    g = load_golden("ddim.pt")[tag]
+    c = SCHED["c2" if tag.endswith("c2") else "c1"]
+    tab = ddim_oracle.DiffusionTables(**c["kw"])
+    ucfg, seed = g["ucfg"], g["seed"]
+    usd = synth_state_dict(g["unet_shapes"], seed)
+    vsd = synth_state_dict(g["vae_shapes"], seed)
+    B, T, h, w = 1, 16, 8, 8
+    cond = synth_input("cond", (B, 77 + 16 * T, 1024), seed)
+    uncond = synth_input("uncond", (B, 77 + 16 * T, 1024), seed)
+    concat = synth_input("concat", (B, 4, T, h, w), seed)
+    x_T = synth_input("x_T", (B, 4, T, h, w), seed)
+    fs = torch.tensor([ucfg["default_fs"]] * B, dtype=torch.long)
+
+    def apply_model(x, t, ctx):          # ddpm3d.py:723-733 + 1254-1258 (hybrid conditioning)
+        return unet_oracle.unet_forward(usd, ucfg, torch.cat([x, concat], 1), t, ctx, fs)
+
+    torch.manual_seed(123)
+    samples, _ = ddim_oracle.sample(tab, apply_model, g["S"], (B, 4, T, h, w), cond, uncond=uncond,
+                                    ucg_scale=7.5, eta=1.0, timestep_spacing=g["spacing"],
+                                    guidance_rescale=g["gr"], x_T=x_T)
+    assert rel_l2(samples, g["samples"]) < 1e-4
+    from oracle.make_golden import TINY_VAE
+    video = vae_oracle.decode_first_stage(vsd, TINY_VAE, g["samples"])
+    assert rel_l2(video, g["video"]) < TOL
