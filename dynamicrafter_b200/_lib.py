@@ -1,0 +1,67 @@
+"""ctypes binding of libdcb200.so (include/dcb200.h).  No fallbacks: a missing library is an error."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdcb200.so")
+
+MAX_TAPS = 9
+c_int = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_vp = ctypes.c_void_p
+c_f = ctypes.c_float
+
+
+class DcbError(RuntimeError):
+    pass
+
+
+class TapGemmArgs(ctypes.Structure):
+    _fields_ = [
+        ("a", c_vp), ("a_s1", c_i64), ("a_s2", c_i64), ("a_s3", c_i64),
+        ("C", c_int), ("D1", c_int), ("D2", c_int), ("D3", c_int),
+        ("A1", c_int), ("A2", c_int), ("A3", c_int),
+        ("b1", c_int), ("b2", c_int), ("b3", c_int),
+        ("ntaps", c_int), ("taps", (c_int * 3) * MAX_TAPS),
+        ("w", c_vp), ("N", c_int), ("block_n", c_int),
+        ("bias", c_vp), ("group_bias", c_vp), ("rows_per_group", c_int), ("ld_group_bias", c_int),
+        ("residual", c_vp), ("ld_residual", c_int), ("geglu", c_int),
+        ("out_f32", c_vp), ("out_bf16", c_vp), ("ld_out", c_int), ("out_scale", c_f),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the CDLL.  Raises if the extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DcbError(
+                f"{LIB_PATH} is missing: run `python -m dynamicrafter_b200.build` "
+                "(there is no CPU or PyTorch fallback for the dcb200 kernels)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.dcb_last_error.restype = ctypes.c_char_p
+        for name in EXPORTS:
+            fn = getattr(_lib, name)       # AttributeError if the symbol is absent
+            if name != "dcb_last_error":
+                fn.restype = ctypes.c_int
+    return _lib
+
+
+# every symbol include/dcb200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "dcb_last_error", "dcb_abi_version", "dcb_check_device", "dcb_tap_gemm",
+]
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().dcb_last_error().decode(errors="replace")
+        raise DcbError(f"{what} failed ({rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())

@@ -1,0 +1,47 @@
+// Error reporting and device checks of the C ABI.
+#include <cstdarg>
+#include <cstdio>
+
+#include "dcb_internal.h"
+
+namespace dcb {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return DCB_OK;
+}
+
+}  // namespace dcb
+
+extern "C" const char* dcb_last_error(void) { return dcb::g_err; }
+extern "C" int dcb_abi_version(void) { return 1; }
+
+extern "C" int dcb_check_device(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+        return dcb::set_error(DCB_ERR_CUDA, "no CUDA device");
+    if (major != 10) return dcb::set_error(DCB_ERR_DEVICE, "dcb200 needs an sm_100 device, found sm_%d0", major);
+    return DCB_OK;
+}

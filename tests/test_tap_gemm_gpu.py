@@ -1,0 +1,110 @@
+"""tcgen05 implicit-GEMM kernel vs a plain torch fp32 computation on the same bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+def _close(got, ref, tol=2e-3):
+    err = (got.float() - ref).abs().max().item()
+    den = ref.abs().max().item() + 1e-6
+    assert err / den < tol, (err, den)
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+@pytest.mark.parametrize("M,K,N", [(300, 320, 320), (128, 64, 128), (1000, 1280, 512), (77, 1024, 640), (4096, 320, 960)])
+def test_linear_bias_residual(M, K, N):
+    from dynamicrafter_b200 import ops
+    a, w = _mk((M, K), 1), _mk((N, K), 2, K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    ref = a.float() @ w.float().t() + bias + res
+    out = ops.linear(a, w, bias=bias, residual=res, f32=True, bf16=False)
+    torch.cuda.synchronize()
+    _close(out, ref, 1e-4)
+    ob = ops.linear(a, w, bias=bias, residual=res, f32=False, bf16=True)
+    _close(ob, ref, 1e-2)
+
+
+def test_linear_strided_a_and_small_n():
+    from dynamicrafter_b200 import ops
+    big = _mk((500, 3 * 128), 3)
+    a = big[:, 128:256]
+    w = _mk((4, 128), 4, 0.1)
+    ref = a.float() @ w.float().t()
+    out = ops.linear(a, w, f32=True, bf16=False)
+    _close(out, ref, 1e-4)
+
+
+@pytest.mark.parametrize("K,inner,bn", [(128, 320, 160), (64, 256, 128)])
+def test_geglu(K, inner, bn):
+    from dynamicrafter_b200 import ops
+    M = 200
+    a, w = _mk((M, K), 5), _mk((2 * inner, K), 6, K ** -0.5)
+    bias = torch.randn(2 * inner, device="cuda") * 0.1
+    h = a.float() @ w.float().t() + bias
+    ref = h[:, :inner] * F.gelu(h[:, inner:])
+    half = bn // 2
+    idx = torch.cat([torch.cat([torch.arange(j * half, (j + 1) * half), inner + torch.arange(j * half, (j + 1) * half)])
+                     for j in range(inner // half)]).cuda()
+    out = ops.linear(a, w[idx].contiguous(), bias=bias[idx].contiguous(), geglu=True, f32=True, bf16=False, block_n=bn)
+    _close(out, ref, 1e-4)
+
+
+@pytest.mark.parametrize("nf,H,W,C,N", [(3, 10, 16, 64, 128), (2, 5, 8, 128, 320), (1, 40, 64, 64, 160), (4, 3, 2, 64, 64)])
+def test_conv3x3(nf, H, W, C, N):
+    from dynamicrafter_b200 import ops
+    x = _mk((nf, H, W, C), 7)
+    wt = _mk((N, C, 3, 3), 8, (9 * C) ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    gb = torch.randn(nf, N, device="cuda")
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1) + gb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(nf * H * W, N)
+    wp = wt.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = ops.conv3x3(x.reshape(nf * H * W, C), nf, H, W, wp, bias=bias, group_bias=gb, rows_per_group=H * W)
+    _close(out, ref, 1e-4)
+
+
+@pytest.mark.parametrize("B,T,HW,C,N", [(2, 16, 40, 128, 128), (1, 16, 160, 64, 320), (1, 16, 2, 64, 64)])
+def test_tconv3(B, T, HW, C, N):
+    from dynamicrafter_b200 import ops
+    x = _mk((B, T, HW, C), 9)
+    wt = _mk((N, C, 3, 1, 1), 10, (3 * C) ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    x5 = x.float().permute(0, 3, 1, 2).unsqueeze(-1)           # [B, C, T, HW, 1]
+    ref = F.conv3d(x5, wt.float(), bias, padding=(1, 0, 0)).squeeze(-1).permute(0, 2, 3, 1).reshape(B * T * HW, N)
+    wp = wt.reshape(N, C, 3).permute(0, 2, 1).reshape(N, 3 * C).contiguous()
+    res = torch.randn(B * T * HW, N, device="cuda")
+    out = ops.tconv3(x.reshape(-1, C), B, T, HW, wp, bias=bias, residual=res)
+    _close(out, ref + res, 1e-4)
+
+
+def test_gemm_throughput_smoke():
+    """Not a benchmark: just exercises a many-tile persistent launch and prints a rough rate."""
+    from dynamicrafter_b200 import ops
+    M, K, N = 40960, 1280, 1280
+    a, w = _mk((M, K), 11), _mk((N, K), 12, K ** -0.5)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    for _ in range(3):
+        ops.linear(a, w, out=out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.linear(a, w, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"\ntap_gemm {M}x{N}x{K}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+    ref = a.float() @ w.float().t()
+    _close(out, ref, 1e-2)
