@@ -23,10 +23,28 @@ class TapGemmArgs(ctypes.Structure):
         ("A1", c_int), ("A2", c_int), ("A3", c_int),
         ("b1", c_int), ("b2", c_int), ("b3", c_int),
         ("ntaps", c_int), ("taps", (c_int * 3) * MAX_TAPS),
-        ("w", c_vp), ("N", c_int), ("block_n", c_int),
+        ("w", c_vp), ("w_ld", c_i64), ("N", c_int), ("block_n", c_int),
         ("bias", c_vp), ("group_bias", c_vp), ("rows_per_group", c_int), ("ld_group_bias", c_int),
         ("residual", c_vp), ("ld_residual", c_int), ("geglu", c_int),
         ("out_f32", c_vp), ("out_bf16", c_vp), ("ld_out", c_int), ("out_scale", c_f),
+    ]
+
+
+class AttentionArgs(ctypes.Structure):
+    _fields_ = [
+        ("q", c_vp), ("ldq", c_i64),
+        ("k", c_vp * 2), ("v", c_vp * 2), ("ldk", c_i64 * 2), ("ldv", c_i64 * 2),
+        ("nk", c_int * 2), ("kv_batch_div", c_int * 2), ("seg_scale", c_f * 2),
+        ("nseg", c_int), ("batch", c_int), ("heads", c_int), ("nq", c_int), ("head_dim", c_int),
+        ("o", c_vp), ("ldo", c_i64), ("softmax_scale", c_f),
+    ]
+
+
+class DdimCoeffs(ctypes.Structure):
+    _fields_ = [
+        ("is_v", c_int), ("cfg_scale", c_f), ("guidance_rescale", c_f), ("one_minus_guidance_rescale", c_f),
+        ("sqrt_acp_t", c_f), ("sqrt_1m_acp_t", c_f), ("sqrt_a_t", c_f), ("sqrt_1m_a_t", c_f),
+        ("sqrt_a_prev", c_f), ("dir_coef", c_f), ("sigma_t", c_f), ("temperature", c_f), ("x0_rescale", c_f),
     ]
 
 
@@ -45,7 +63,9 @@ def lib():
         _lib.dcb_last_error.restype = ctypes.c_char_p
         for name in EXPORTS:
             fn = getattr(_lib, name)       # AttributeError if the symbol is absent
-            if name != "dcb_last_error":
+            if name == "dcb_group_norm_workspace_bytes":
+                fn.restype = ctypes.c_size_t
+            elif name != "dcb_last_error":
                 fn.restype = ctypes.c_int
     return _lib
 
@@ -53,6 +73,10 @@ def lib():
 # every symbol include/dcb200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "dcb_last_error", "dcb_abi_version", "dcb_check_device", "dcb_tap_gemm",
+    "dcb_group_norm_workspace_bytes", "dcb_group_norm_stats", "dcb_group_norm_apply", "dcb_layer_norm",
+    "dcb_flash_attention", "dcb_temporal_attention", "dcb_softmax_rows",
+    "dcb_nchw_to_rows", "dcb_rows_to_nchw", "dcb_upsample2x", "dcb_space_to_depth", "dcb_cast_bf16",
+    "dcb_timestep_embedding", "dcb_small_linear", "dcb_ddim_update",
 ]
 
 

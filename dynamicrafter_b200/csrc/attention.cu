@@ -1,0 +1,440 @@
+// Attention kernels, head dim 64, bf16 operands, fp32 online softmax.
+//
+//  * flash_attention_kernel: spatial self-attention (attention.py:101-125, K6) and the dual text+image
+//    cross-attention (attention.py:89-94,129-142, K7) as ONE kernel: up to two key/value segments, each with
+//    its own softmax, combined as out = seg_scale[0]*softmax(QK0^T)V0 + seg_scale[1]*softmax(QK1^T)V1.
+//    The N x N score matrix is never materialised.
+//  * temporal_attention_kernel: self-attention over <=16 frames per (batch, location, head)
+//    (attention.py:387-390, K8); reads q/k/v rows with the frame stride of the channels-last layout so no
+//    '(b t) hw c <-> (b hw) t c' transposes exist anywhere.
+//
+// Round-1 status: both use warp-level mma.sync (HMMA) tiles with cp.async double buffering; the tcgen05/TMEM
+// version of the spatial kernel is the next optimisation step.
+#include <cuda_bf16.h>
+
+#include "dcb_internal.h"
+
+namespace dcb {
+
+constexpr int kD = 64;   // head dim
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;   // src-size 0 => zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// tile rows are 64 bf16 = 8 chunks of 16 B; chunk index XOR (row & 7) => conflict-free ldmatrix
+__device__ __forceinline__ int swz(int row, int chunk) { return row * 64 + ((chunk ^ (row & 7)) << 3); }
+
+struct FlashParams {
+    const __nv_bfloat16* q; long long ldq;
+    const __nv_bfloat16* k[2]; const __nv_bfloat16* v[2]; long long ldk[2], ldv[2];
+    int nk[2]; int kv_div[2]; float seg_scale[2];
+    int nseg, nq, heads;
+    __nv_bfloat16* o; long long ldo;
+    float scale_log2;
+};
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32)
+flash_attention_kernel(const FlashParams p) {
+    constexpr int BM = kWarps * 16, BN = 64, kThreads = kWarps * 32;
+    extern __shared__ __align__(128) uint8_t fa_smem[];
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(fa_smem);
+    __nv_bfloat16* sK = sQ + BM * kD;            // [2][BN*kD]
+    __nv_bfloat16* sV = sK + 2 * BN * kD;        // [2][BN*kD]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+    const int g = lane >> 2, t = lane & 3;
+
+    // ---- Q tile -> smem (zero filled past nq)
+    {
+        const __nv_bfloat16* qb = p.q + (static_cast<long long>(b) * p.nq) * p.ldq + h * kD;
+        for (int i = tid; i < BM * 8; i += kThreads) {
+            const int r = i >> 3, c = i & 7;
+            const bool ok = (q0 + r) < p.nq;
+            cp_async16(sQ + swz(r, c), qb + static_cast<long long>(ok ? q0 + r : 0) * p.ldq + c * 8, ok);
+        }
+        cp_async_commit();
+    }
+    uint32_t qf[4][4];
+    float out[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { out[i][0] = out[i][1] = out[i][2] = out[i][3] = 0.f; }
+    bool q_loaded = false;
+
+    for (int seg = 0; seg < p.nseg; ++seg) {
+        const int nk = p.nk[seg];
+        const int kvb = b / p.kv_div[seg];
+        const __nv_bfloat16* kb = p.k[seg] + (static_cast<long long>(kvb) * nk) * p.ldk[seg] + h * kD;
+        const __nv_bfloat16* vb = p.v[seg] + (static_cast<long long>(kvb) * nk) * p.ldv[seg] + h * kD;
+        const int ntiles = (nk + BN - 1) / BN;
+        auto load_kv = [&](int tile, int buf) {
+            const int k0 = tile * BN;
+            for (int i = tid; i < BN * 8; i += kThreads) {
+                const int r = i >> 3, c = i & 7;
+                const bool ok = (k0 + r) < nk;
+                const long long row = ok ? (k0 + r) : 0;
+                cp_async16(sK + buf * BN * kD + swz(r, c), kb + row * p.ldk[seg] + c * 8, ok);
+                cp_async16(sV + buf * BN * kD + swz(r, c), vb + row * p.ldv[seg] + c * 8, ok);
+            }
+            cp_async_commit();
+        };
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+        float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+        load_kv(0, 0);
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const int buf = tile & 1;
+            if (tile + 1 < ntiles) { load_kv(tile + 1, buf ^ 1); cp_async_wait<1>(); }
+            else { cp_async_wait<0>(); }
+            __syncthreads();
+            if (!q_loaded) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, c = ks * 2 + (lane >> 4);
+                    ldsm_x4(smem_addr(sQ + swz(r, c)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+                }
+                q_loaded = true;
+            }
+            const __nv_bfloat16* tK = sK + buf * BN * kD;
+            const __nv_bfloat16* tV = sV + buf * BN * kD;
+            // ---- S = Q K^T  (16 x 64 per warp)
+            float s[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+                for (int kp = 0; kp < 2; ++kp) {
+                    uint32_t b0, b1, b2, b3;
+                    const int r = nt * 8 + (lane & 7), c = kp * 4 + (lane >> 3);
+                    ldsm_x4(smem_addr(tK + swz(r, c)), b0, b1, b2, b3);
+                    mma_bf16(s[nt], qf[kp * 2], b0, b1);
+                    mma_bf16(s[nt], qf[kp * 2 + 1], b2, b3);
+                }
+            }
+            // ---- mask the ragged last tile, online softmax (fp32)
+            const int k0 = tile * BN;
+            if (k0 + BN > nk) {
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const int key = k0 + nt * 8 + 2 * t;
+                    if (key >= nk) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+                    if (key + 1 >= nk) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+                }
+            }
+            float mx[2] = {m_run[0], m_run[1]};
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+                mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+                mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+            }
+            float corr[2], msc[2], rs[2] = {0.f, 0.f};
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                corr[hh] = exp2f((m_run[hh] - mx[hh]) * p.scale_log2);
+                msc[hh] = mx[hh] * p.scale_log2;
+                m_run[hh] = mx[hh];
+            }
+            uint32_t pf[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float p0 = exp2f(s[nt][0] * p.scale_log2 - msc[0]);
+                const float p1 = exp2f(s[nt][1] * p.scale_log2 - msc[0]);
+                const float p2 = exp2f(s[nt][2] * p.scale_log2 - msc[1]);
+                const float p3 = exp2f(s[nt][3] * p.scale_log2 - msc[1]);
+                rs[0] += p0 + p1;
+                rs[1] += p2 + p3;
+                // C fragment of S (n-tiles 2j, 2j+1) == A fragment of P for key block j
+                pf[nt >> 1][(nt & 1) * 2] = pack_bf16(p0, p1);
+                pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) l_run[hh] = l_run[hh] * corr[hh] + rs[hh];
+#pragma unroll
+            for (int nd = 0; nd < 8; ++nd) {
+                acc[nd][0] *= corr[0]; acc[nd][1] *= corr[0];
+                acc[nd][2] *= corr[1]; acc[nd][3] *= corr[1];
+            }
+            // ---- O += P V
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                for (int ndp = 0; ndp < 4; ++ndp) {
+                    uint32_t b0, b1, b2, b3;
+                    const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, c = ndp * 2 + (lane >> 4);
+                    ldsm_x4_t(smem_addr(tV + swz(r, c)), b0, b1, b2, b3);
+                    mma_bf16(acc[ndp * 2], pf[kk], b0, b1);
+                    mma_bf16(acc[ndp * 2 + 1], pf[kk], b2, b3);
+                }
+            }
+            __syncthreads();   // everyone done with buf before it is refilled
+        }
+        // ---- finish this segment's softmax and fold into the output
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 1);
+            l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 2);
+        }
+        const float i0 = p.seg_scale[seg] / l_run[0], i1 = p.seg_scale[seg] / l_run[1];
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) {
+            out[nd][0] += acc[nd][0] * i0; out[nd][1] += acc[nd][1] * i0;
+            out[nd][2] += acc[nd][2] * i1; out[nd][3] += acc[nd][3] * i1;
+        }
+    }
+    // ---- O -> bf16 via this warp's rows of sQ, then 16-byte coalesced stores
+    __syncwarp();
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+        const int r0 = warp * 16 + g, cchunk = nd, within = 2 * t;
+        *reinterpret_cast<uint32_t*>(sQ + swz(r0, cchunk) + within) = pack_bf16(out[nd][0], out[nd][1]);
+        *reinterpret_cast<uint32_t*>(sQ + swz(r0 + 8, cchunk) + within) = pack_bf16(out[nd][2], out[nd][3]);
+    }
+    __syncwarp();
+    __nv_bfloat16* ob = p.o + (static_cast<long long>(b) * p.nq) * p.ldo + h * kD;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = lane + i * 32, r = warp * 16 + (idx >> 3), c = idx & 7;
+        if (q0 + r < p.nq)
+            *reinterpret_cast<uint4*>(ob + static_cast<long long>(q0 + r) * p.ldo + c * 8) =
+                *reinterpret_cast<const uint4*>(sQ + swz(r, c));
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Temporal self-attention: one warp per (batch, location, head); L <= 16 frames.
+// Row of frame f at location pix of batch b: ((b*L + f)*HW + pix); q/k/v/o are column slices (head h at
+// column h*64) of row-major buffers with leading dims ldq/ldk/ldv/ldo.
+// -------------------------------------------------------------------------------------------------
+struct TemporalParams {
+    const __nv_bfloat16 *q, *k, *v;
+    __nv_bfloat16* o;
+    long long ldq, ldk, ldv, ldo;
+    int B, L, HW, heads;
+    float scale_log2;
+};
+
+__global__ void __launch_bounds__(128)
+temporal_attention_kernel(const TemporalParams p) {
+    __shared__ __align__(128) __nv_bfloat16 sm[4][3][16 * kD];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = blockIdx.x * 4LL + warp;
+    const long long items = static_cast<long long>(p.B) * p.HW * p.heads;
+    if (item >= items) return;
+    const int h = item % p.heads;
+    const long long bp = item / p.heads;
+    const int pix = bp % p.HW, b = bp / p.HW;
+    const int g = lane >> 2, t = lane & 3;
+    __nv_bfloat16* sQ = sm[warp][0];
+    __nv_bfloat16* sK = sm[warp][1];
+    __nv_bfloat16* sV = sm[warp][2];
+    const long long row0 = (static_cast<long long>(b) * p.L) * p.HW + pix;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = lane + i * 32, f = idx >> 3, c = idx & 7;
+        const bool ok = f < p.L;
+        const long long row = row0 + static_cast<long long>(ok ? f : 0) * p.HW;
+        cp_async16(sQ + swz(f, c), p.q + row * p.ldq + h * kD + c * 8, ok);
+        cp_async16(sK + swz(f, c), p.k + row * p.ldk + h * kD + c * 8, ok);
+        cp_async16(sV + swz(f, c), p.v + row * p.ldv + h * kD + c * 8, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+
+    float s[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            uint32_t a0[4], a1[4], b0, b1, b2, b3;
+            {
+                const int r = (lane & 7) + ((lane >> 3) & 1) * 8;
+                ldsm_x4(smem_addr(sQ + swz(r, (kp * 2) * 2 + (lane >> 4))), a0[0], a0[1], a0[2], a0[3]);
+                ldsm_x4(smem_addr(sQ + swz(r, (kp * 2 + 1) * 2 + (lane >> 4))), a1[0], a1[1], a1[2], a1[3]);
+            }
+            ldsm_x4(smem_addr(sK + swz(nt * 8 + (lane & 7), kp * 4 + (lane >> 3))), b0, b1, b2, b3);
+            mma_bf16(s[nt], a0, b0, b1);
+            mma_bf16(s[nt], a1, b2, b3);
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+        const int key = nt * 8 + 2 * t;
+        if (key >= p.L) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+        if (key + 1 >= p.L) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+    }
+    float mx[2], sum[2] = {0.f, 0.f};
+    mx[0] = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
+    mx[1] = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+    }
+    uint32_t pf[4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+        const float p0 = exp2f((s[nt][0] - mx[0]) * p.scale_log2), p1 = exp2f((s[nt][1] - mx[0]) * p.scale_log2);
+        const float p2 = exp2f((s[nt][2] - mx[1]) * p.scale_log2), p3 = exp2f((s[nt][3] - mx[1]) * p.scale_log2);
+        sum[0] += p0 + p1;
+        sum[1] += p2 + p3;
+        pf[nt * 2] = pack_bf16(p0, p1);
+        pf[nt * 2 + 1] = pack_bf16(p2, p3);
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 1);
+        sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 2);
+    }
+    const float inv0 = 1.f / sum[0], inv1 = 1.f / sum[1];
+    float acc[8][4];
+#pragma unroll
+    for (int ndp = 0; ndp < 4; ++ndp) {
+        uint32_t b0, b1, b2, b3;
+        const int r = (lane & 7) + ((lane >> 3) & 1) * 8, c = ndp * 2 + (lane >> 4);
+        ldsm_x4_t(smem_addr(sV + swz(r, c)), b0, b1, b2, b3);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[ndp * 2 + j][0] = acc[ndp * 2 + j][1] = acc[ndp * 2 + j][2] = acc[ndp * 2 + j][3] = 0.f;
+        mma_bf16(acc[ndp * 2], pf, b0, b1);
+        mma_bf16(acc[ndp * 2 + 1], pf, b2, b3);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+        *reinterpret_cast<uint32_t*>(sQ + swz(g, nd) + 2 * t) = pack_bf16(acc[nd][0] * inv0, acc[nd][1] * inv0);
+        *reinterpret_cast<uint32_t*>(sQ + swz(g + 8, nd) + 2 * t) = pack_bf16(acc[nd][2] * inv1, acc[nd][3] * inv1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = lane + i * 32, f = idx >> 3, c = idx & 7;
+        if (f < p.L)
+            *reinterpret_cast<uint4*>(p.o + (row0 + static_cast<long long>(f) * p.HW) * p.ldo + h * kD + c * 8) =
+                *reinterpret_cast<const uint4*>(sQ + swz(f, c));
+    }
+}
+
+// fp32 [rows, n] -> softmax(scale * x) bf16 [rows, n]; one warp per row.  VAE mid-block attention
+// (ae_modules.py:66-68) materialises its 1-head N x N scores (small: N = h*w of one latent frame).
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ x, long long rows, int n, long long ldx, float scale_log2,
+                    __nv_bfloat16* __restrict__ y, long long ldy) {
+    const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + row * ldx;
+    float mx = -INFINITY;
+    for (int i = lane; i < n; i += 32) mx = fmaxf(mx, xr[i]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int i = lane; i < n; i += 32) sum += exp2f((xr[i] - mx) * scale_log2);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    __nv_bfloat16* yr = y + row * ldy;
+    for (int i = lane; i < n; i += 32) yr[i] = __float2bfloat16_rn(exp2f((xr[i] - mx) * scale_log2) * inv);
+}
+
+}  // namespace dcb
+
+using namespace dcb;
+
+extern "C" int dcb_flash_attention(const dcb_attention_args* a, void* stream) {
+    if (a == nullptr || a->q == nullptr || a->o == nullptr || a->nseg < 1 || a->nseg > 2)
+        return set_error(DCB_ERR_INVALID, "flash_attention: bad argument");
+    if (a->head_dim != kD) return set_error(DCB_ERR_UNSUPPORTED, "flash_attention: head_dim must be 64");
+    if (a->batch < 1 || a->heads < 1 || a->nq < 1 || (a->ldq & 7) || (a->ldo & 7))
+        return set_error(DCB_ERR_INVALID, "flash_attention: shape/alignment");
+    FlashParams p;
+    p.q = static_cast<const __nv_bfloat16*>(a->q); p.ldq = a->ldq;
+    p.o = static_cast<__nv_bfloat16*>(a->o); p.ldo = a->ldo;
+    p.nseg = a->nseg; p.nq = a->nq; p.heads = a->heads;
+    for (int s = 0; s < 2; ++s) {
+        const bool on = s < a->nseg;
+        if (on && (a->k[s] == nullptr || a->v[s] == nullptr || a->nk[s] < 1 || a->kv_batch_div[s] < 1 ||
+                   (a->ldk[s] & 7) || (a->ldv[s] & 7)))
+            return set_error(DCB_ERR_INVALID, "flash_attention: segment %d", s);
+        p.k[s] = on ? static_cast<const __nv_bfloat16*>(a->k[s]) : nullptr;
+        p.v[s] = on ? static_cast<const __nv_bfloat16*>(a->v[s]) : nullptr;
+        p.ldk[s] = a->ldk[s]; p.ldv[s] = a->ldv[s];
+        p.nk[s] = on ? a->nk[s] : 0;
+        p.kv_div[s] = on ? a->kv_batch_div[s] : 1;
+        p.seg_scale[s] = a->seg_scale[s];
+    }
+    p.scale_log2 = a->softmax_scale * 1.4426950408889634f;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (a->heads > 65535 || a->batch > 65535) return set_error(DCB_ERR_INVALID, "flash_attention: grid too large");
+    if (a->nq >= 512) {
+        constexpr int W = 8, smem = (W * 16 + 4 * 64) * kD * 2;
+        static bool cfg = false;
+        if (!cfg) {
+            cudaFuncSetAttribute(flash_attention_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cfg = true;
+        }
+        dim3 grid((a->nq + W * 16 - 1) / (W * 16), a->heads, a->batch);
+        flash_attention_kernel<W><<<grid, W * 32, smem, st>>>(p);
+    } else {
+        constexpr int W = 4, smem = (W * 16 + 4 * 64) * kD * 2;
+        dim3 grid((a->nq + W * 16 - 1) / (W * 16), a->heads, a->batch);
+        flash_attention_kernel<W><<<grid, W * 32, smem, st>>>(p);
+    }
+    return check_launch("flash_attention");
+}
+
+extern "C" int dcb_temporal_attention(const void* q, const void* k, const void* v, void* o, long long ldq,
+                                      long long ldk, long long ldv, long long ldo, int B, int L, int HW, int heads,
+                                      int head_dim, float softmax_scale, void* stream) {
+    if (!q || !k || !v || !o || B < 1 || HW < 1 || heads < 1) return set_error(DCB_ERR_INVALID, "temporal_attention: bad argument");
+    if (head_dim != kD || L < 1 || L > 16) return set_error(DCB_ERR_UNSUPPORTED, "temporal_attention: head_dim 64 and <= 16 frames only");
+    if ((ldq & 7) || (ldk & 7) || (ldv & 7) || (ldo & 7)) return set_error(DCB_ERR_INVALID, "temporal_attention: alignment");
+    TemporalParams p;
+    p.q = static_cast<const __nv_bfloat16*>(q); p.k = static_cast<const __nv_bfloat16*>(k);
+    p.v = static_cast<const __nv_bfloat16*>(v); p.o = static_cast<__nv_bfloat16*>(o);
+    p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo;
+    p.B = B; p.L = L; p.HW = HW; p.heads = heads;
+    p.scale_log2 = softmax_scale * 1.4426950408889634f;
+    const long long items = static_cast<long long>(B) * HW * heads;
+    temporal_attention_kernel<<<static_cast<unsigned>((items + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("temporal_attention");
+}
+
+extern "C" int dcb_softmax_rows(const float* x, long long rows, int n, long long ldx, float scale, void* y_bf16,
+                                long long ldy, void* stream) {
+    if (!x || !y_bf16 || rows < 1 || n < 1) return set_error(DCB_ERR_INVALID, "softmax_rows: bad argument");
+    softmax_rows_kernel<<<static_cast<unsigned>((rows * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, rows, n, ldx, scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(y_bf16), ldy);
+    return check_launch("softmax_rows");
+}

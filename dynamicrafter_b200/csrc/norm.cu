@@ -11,6 +11,7 @@ namespace dcb {
 
 constexpr int kGroups = 32;
 constexpr int kMaxChunks = 128;
+constexpr int kMaxSplitChannels = 4096;   // smem slots of the stats kernel: row_split * C <= this
 
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
@@ -24,60 +25,58 @@ __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int S,
                 int rows_per_chunk, float* __restrict__ partial, unsigned* __restrict__ counters,
                 float* __restrict__ stats, float eps) {
-    __shared__ float s_acc[kGroups][2];
+    // per-(row split, channel) partial sums; every slot has exactly one writer and is folded in a
+    // fixed order -> bitwise reproducible (no floating-point atomics anywhere)
+    __shared__ float s_part[kMaxSplitChannels * 2];
     __shared__ bool s_last;
     const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = C1 + C2, cg = C / kGroups;
-    if (tid < kGroups * 2) (&s_acc[0][0])[tid] = 0.f;
-    __syncthreads();
     const int r0 = chunk * rows_per_chunk;
     const int r1 = min(S, r0 + rows_per_chunk);
+    const int Q1 = C1 >> 2, Q2 = C2 >> 2;
+    const int Qb1 = (Q1 + 31) >> 5, Qb2 = (Q2 + 31) >> 5, Qb = Qb1 + Qb2;
+    const int row_split = Qb >= 8 ? 1 : 8 / Qb;          // warps sharing one 128-channel block split its rows
 
-    for (int src = 0; src < 2; ++src) {
-        const float* x = src == 0 ? x1 : x2;
-        const int Cs = src == 0 ? C1 : C2;
-        const int coff = src == 0 ? 0 : C1;
-        if (x == nullptr || Cs == 0) continue;
-        const int Q = Cs >> 2;
+    for (int item = warp; item < Qb * row_split; item += 8) {
+        const int cb = item / row_split, split = item - cb * row_split;
+        const bool second = cb >= Qb1;
+        const float* x = second ? x2 : x1;
+        const int Cs = second ? C2 : C1;
+        const int coff = second ? C1 : 0;
+        const int q = (second ? cb - Qb1 : cb) * 32 + lane;
+        if (q >= (Cs >> 2)) continue;
         const float* base = x + (static_cast<size_t>(n) * S) * Cs;
-        for (int cb = 0; cb * 32 < Q; ++cb) {
-            const int q = cb * 32 + lane;
-            float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-            if (q < Q) {
-                int r = r0 + warp;
-                // two rows in flight per iteration for memory-level parallelism
-                for (; r + 8 < r1; r += 16) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * Cs) + q);
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(r + 8) * Cs) + q);
-                    s[0] += a.x + b.x; s[1] += a.y + b.y; s[2] += a.z + b.z; s[3] += a.w + b.w;
-                    ss[0] += a.x * a.x + b.x * b.x; ss[1] += a.y * a.y + b.y * b.y;
-                    ss[2] += a.z * a.z + b.z * b.z; ss[3] += a.w * a.w + b.w * b.w;
-                }
-                for (; r < r1; r += 8) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * Cs) + q);
-                    s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;
-                    ss[0] += a.x * a.x; ss[1] += a.y * a.y; ss[2] += a.z * a.z; ss[3] += a.w * a.w;
-                }
-                const int c0 = coff + q * 4;
-                const int g0 = c0 / cg, g3 = (c0 + 3) / cg;
-                if (g0 == g3) {
-                    atomicAdd(&s_acc[g0][0], (s[0] + s[1]) + (s[2] + s[3]));
-                    atomicAdd(&s_acc[g0][1], (ss[0] + ss[1]) + (ss[2] + ss[3]));
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        atomicAdd(&s_acc[(c0 + e) / cg][0], s[e]);
-                        atomicAdd(&s_acc[(c0 + e) / cg][1], ss[e]);
-                    }
-                }
-            }
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+        int r = r0 + split;
+        // two rows in flight per iteration for memory-level parallelism
+        for (; r + row_split < r1; r += 2 * row_split) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * Cs) + q);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(r + row_split) * Cs) + q);
+            s[0] += a.x + b.x; s[1] += a.y + b.y; s[2] += a.z + b.z; s[3] += a.w + b.w;
+            ss[0] += a.x * a.x + b.x * b.x; ss[1] += a.y * a.y + b.y * b.y;
+            ss[2] += a.z * a.z + b.z * b.z; ss[3] += a.w * a.w + b.w * b.w;
         }
+        for (; r < r1; r += row_split) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * Cs) + q);
+            s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;
+            ss[0] += a.x * a.x; ss[1] += a.y * a.y; ss[2] += a.z * a.z; ss[3] += a.w * a.w;
+        }
+        float* dst = s_part + (static_cast<size_t>(split) * C + coff + q * 4) * 2;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { dst[2 * e] = s[e]; dst[2 * e + 1] = ss[e]; }
     }
     __syncthreads();
     float* pbase = partial + (static_cast<size_t>(n) * nchunks + chunk) * (kGroups * 2);
-    if (tid < kGroups * 2) {
-        pbase[tid] = (&s_acc[0][0])[tid];
+    if (tid < kGroups) {
+        float a = 0.f, b = 0.f;
+        for (int sp = 0; sp < row_split; ++sp)
+            for (int c = tid * cg; c < (tid + 1) * cg; ++c) {
+                a += s_part[(static_cast<size_t>(sp) * C + c) * 2];
+                b += s_part[(static_cast<size_t>(sp) * C + c) * 2 + 1];
+            }
+        pbase[tid * 2] = a;
+        pbase[tid * 2 + 1] = b;
         __threadfence();
     }
     __syncthreads();
@@ -238,7 +237,7 @@ extern "C" int dcb_group_norm_stats(const float* x1, const float* x2, int C1, in
     const int C = C1 + C2;
     if (x1 == nullptr || stats == nullptr || workspace == nullptr || counters == nullptr)
         return set_error(DCB_ERR_INVALID, "group_norm_stats: null argument");
-    if (C % kGroups != 0 || (C1 & 3) || (C2 & 3) || G < 1 || S < 1 || (C2 > 0 && x2 == nullptr))
+    if (C % kGroups != 0 || (C1 & 3) || (C2 & 3) || G < 1 || S < 1 || (C2 > 0 && x2 == nullptr) || C > kMaxSplitChannels)
         return set_error(DCB_ERR_INVALID, "group_norm_stats: C1=%d C2=%d G=%d S=%d", C1, C2, G, S);
     const int nchunks = pick_chunks(G, S);
     const int rpc = (S + nchunks - 1) / nchunks;

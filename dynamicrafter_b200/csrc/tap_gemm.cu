@@ -318,7 +318,11 @@ using namespace dcb;
 extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
     if (a == nullptr || a->a == nullptr || a->w == nullptr) return set_error(DCB_ERR_INVALID, "tap_gemm: null argument");
     if (a->out_f32 == nullptr && a->out_bf16 == nullptr) return set_error(DCB_ERR_INVALID, "tap_gemm: no output");
-    if (a->C <= 0 || a->C % 64 != 0) return set_error(DCB_ERR_INVALID, "tap_gemm: C=%d must be a positive multiple of 64", a->C);
+    if (a->C <= 0 || a->C % 8 != 0 || (a->ntaps > 1 && a->C % 64 != 0))
+        return set_error(DCB_ERR_INVALID, "tap_gemm: C=%d must be a multiple of 8 (of 64 when ntaps > 1)", a->C);
+    const int64_t w_ld = a->w_ld > 0 ? a->w_ld : static_cast<int64_t>(a->ntaps) * a->C;
+    if (w_ld % 8 != 0 || w_ld < static_cast<int64_t>(a->ntaps) * a->C)
+        return set_error(DCB_ERR_INVALID, "tap_gemm: w_ld");
     if (a->ntaps < 1 || a->ntaps > DCB_MAX_TAPS) return set_error(DCB_ERR_INVALID, "tap_gemm: ntaps=%d", a->ntaps);
     if (a->b1 < 1 || a->b2 < 1 || a->b3 < 1 || a->b1 > 256 || a->b2 > 256 || a->b3 > 256 ||
         a->b1 * a->b2 * a->b3 > kBlockM)
@@ -346,7 +350,7 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
     {
         const uint64_t K = (uint64_t)a->ntaps * a->C;
         const uint64_t dims[2] = {K, (uint64_t)a->N};
-        const uint64_t str[2] = {1, K};
+        const uint64_t str[2] = {1, (uint64_t)w_ld};
         const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)bn};
         int rc = encode_bf16_map(&tmB, a->w, 2, dims, str, box);
         if (rc) return rc;
@@ -360,7 +364,7 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
     p.num_m_tiles = p.t1 * p.t2 * p.t3;
     p.num_n_tiles = (a->N + bn - 1) / bn;
     p.rows_per_tile = a->b1 * a->b2 * a->b3;
-    p.kchunks = a->C / 64;
+    p.kchunks = (a->C + 63) / 64;
     p.ntaps = a->ntaps;
     for (int t = 0; t < DCB_MAX_TAPS; ++t)
         for (int d = 0; d < 3; ++d) p.taps[t][d] = (t < a->ntaps) ? a->taps[t][d] : 0;

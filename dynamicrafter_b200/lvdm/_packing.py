@@ -1,0 +1,97 @@
+"""Weight packing shared by the mirror modules: fp32 nn.Parameters -> bf16 K-major GEMM operands.
+
+Packed tensors are plain attributes (never in ``state_dict``), rebuilt lazily whenever a parameter's
+``_version`` changes (``load_state_dict`` / in-place re-randomisation), so the modules keep the
+reference's checkpoint format (inference.py:34-59 loads with strict=True).
+"""
+import torch
+import torch.nn as nn
+
+BF16 = torch.bfloat16
+
+
+def _pad64(c):
+    return (c + 63) // 64 * 64
+
+
+def pack_linear(w):
+    """[N, K] (or Conv1d/Conv2d k=1 [N, K, 1(,1)]) -> bf16 [N, K]."""
+    return w.detach().reshape(w.shape[0], w.shape[1]).to(BF16).contiguous()
+
+
+def pack_conv3x3(w):
+    """[N, C, 3, 3] -> bf16 [N, 9*Cpad] ordered (ky, kx, c); input channels zero-padded to 64."""
+    N, C = w.shape[0], w.shape[1]
+    Cp = _pad64(C)
+    out = torch.zeros((N, 3, 3, Cp), dtype=BF16, device=w.device)
+    out[..., :C] = w.detach().permute(0, 2, 3, 1).to(BF16)
+    return out.reshape(N, 9 * Cp).contiguous()
+
+
+def pack_tconv3(w):
+    """[N, C, 3, 1, 1] -> bf16 [N, 3*C] ordered (kt, c)."""
+    N, C = w.shape[0], w.shape[1]
+    return w.detach().reshape(N, C, 3).permute(0, 2, 1).to(BF16).reshape(N, 3 * C).contiguous()
+
+
+def geglu_block_n(inner):
+    if inner % 80 == 0:
+        return 160
+    if inner % 64 == 0:
+        return 128
+    raise ValueError(f"GEGLU inner dim {inner} must be a multiple of 64 or 80")
+
+
+def pack_geglu(w, b):
+    """[2*inner, K] -> rows interleaved per output tile: (BN/2 value rows, BN/2 gate rows) * tiles."""
+    inner = w.shape[0] // 2
+    bn = geglu_block_n(inner)
+    half = bn // 2
+    idx = torch.arange(inner, device=w.device).reshape(inner // half, half)
+    idx = torch.cat([idx, idx + inner], dim=1).reshape(-1)
+    return w.detach()[idx].to(BF16).contiguous(), b.detach()[idx].float().contiguous(), bn
+
+
+class PackedModule(nn.Module):
+    """nn.Module whose kernels consume a lazily built dict of packed device tensors."""
+
+    def _pack(self):           # -> dict
+        raise NotImplementedError
+
+    def _own_version(self):
+        v = 0
+        for p in self.parameters(recurse=False):
+            v += p._version
+        for m in self.children():
+            if not isinstance(m, PackedModule):
+                for p in m.parameters():
+                    v += p._version
+        return v
+
+    def packed(self):
+        p0 = next(self.parameters(), None)
+        if p0 is None or not p0.is_cuda:
+            raise RuntimeError(f"{type(self).__name__}: parameters must live on a CUDA device "
+                               "(dcb200 has no CPU path)")
+        key = (p0.device, self._own_version())
+        cache = self.__dict__.get("_packed_cache")
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                cache = (key, self._pack())
+            self.__dict__["_packed_cache"] = cache
+        return cache[1]
+
+
+class Act:
+    """Channels-last activation: x is fp32 [B*T*H*W, C], rows ordered (b, t, y, x)."""
+    __slots__ = ("x", "B", "T", "H", "W")
+
+    def __init__(self, x, B, T, H, W):
+        self.x, self.B, self.T, self.H, self.W = x, B, T, H, W
+
+    @property
+    def C(self):
+        return self.x.shape[1]
+
+    def like(self, x, H=None, W=None):
+        return Act(x, self.B, self.T, self.H if H is None else H, self.W if W is None else W)

@@ -1,0 +1,421 @@
+"""Drop-in mirror of lvdm/modules/networks/openaimodel3d.py (reference) on the dcb200 CUDA kernels.
+
+Classes keep the reference's constructor arguments, ``state_dict`` keys (including the ``temopral_conv``
+typo, openaimodel3d.py:190) and call signatures: UNetModel.forward(x, timesteps, context,
+features_adapter, fs, **kwargs) (openaimodel3d.py:548), ResBlock.forward(x, emb, batch_size) (:197),
+TemporalConvBlock.forward(x) (:272), Downsample/Upsample.forward(x) (:75,:98),
+TimestepEmbedSequential.forward(x, emb, context, batch_size) (:36).
+
+Execution plan of one UNet forward (all in libdcb200.so):
+  pack x (NCTHW fp32 -> channels-last bf16, C padded to 64)  ->  3x3 implicit-GEMM conv_in
+  per ResBlock: GN-stats, GN-apply+SiLU (bf16 operand), conv3x3 (+bias +emb), GN, conv3x3 (+bias +skip),
+                4 x [GN(5-D) + SiLU, temporal 3-tap conv] (+identity in the last epilogue)
+  per transformer: GN, proj_in, [LN, fused-QKV GEMM, attention, out-proj(+res)] x2, LN, GEGLU GEMM, FF2(+res), proj_out(+res)
+  skip concats are read as two sources by the GN kernels; the residual stream is fp32, GEMM operands bf16.
+"""
+import torch
+import torch.nn as nn
+
+from dynamicrafter_b200 import ops
+from dynamicrafter_b200.lvdm._packing import PackedModule, Act, pack_linear, pack_conv3x3, pack_tconv3
+from dynamicrafter_b200.lvdm.modules.attention import SpatialTransformer, TemporalTransformer, make_context, CrossAttentionContext, TEXT_CONTEXT_LEN
+
+IMG_TOKENS_PER_FRAME = 16      # openaimodel3d.py:556 ("77 + t*16" hard-coded in the reference)
+
+
+def _f32(t):
+    return t.detach().float().contiguous()
+
+
+def _rows_from_nchw(x):
+    n, c, h, w = x.shape
+    return x.float().permute(0, 2, 3, 1).reshape(n * h * w, c).contiguous()
+
+
+def _nchw_from_rows(r, n, h, w):
+    return r.reshape(n, h, w, -1).permute(0, 3, 1, 2).contiguous()
+
+
+class TimestepBlock(nn.Module):
+    """Marker: forward takes the timestep embedding as 2nd argument (openaimodel3d.py:19-27)."""
+
+
+class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
+    def forward(self, x, emb, context=None, batch_size=None):
+        """Reference-layout dispatch (x: [(b f), c, h, w]); UNetModel uses the fused _fwd path instead."""
+        for layer in self:
+            if isinstance(layer, TimestepBlock):
+                x = layer(x, emb, batch_size=batch_size)
+            elif isinstance(layer, SpatialTransformer):
+                x = layer(x, context)
+            elif isinstance(layer, TemporalTransformer):
+                n, c, h, w = x.shape
+                x5 = x.reshape(batch_size, n // batch_size, c, h, w).permute(0, 2, 1, 3, 4)
+                x5 = layer(x5, context)
+                x = x5.permute(0, 2, 1, 3, 4).reshape(n, c, h, w)
+            else:
+                x = layer(x)
+        return x
+
+
+class Downsample(PackedModule):
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        if dims != 2 or not use_conv or padding != 1:
+            raise NotImplementedError("only the 2-D stride-2 conv Downsample is used by DynamiCrafter")
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.use_conv, self.dims = use_conv, dims
+        self.op = nn.Conv2d(self.channels, self.out_channels, 3, stride=2, padding=padding)
+
+    def _pack(self):
+        return {"w": pack_conv3x3(self.op.weight), "b": _f32(self.op.bias)}
+
+    def _fwd(self, h):
+        p = self.packed()
+        nf = h.B * h.T
+        planes = ops.space_to_depth(h.x, nf, h.H, h.W)
+        out = ops.conv3x3_s2(planes, nf, h.H, h.W, p["w"], bias=p["b"])
+        return h.like(out, (h.H - 1) // 2 + 1, (h.W - 1) // 2 + 1)
+
+    def forward(self, x):
+        assert x.shape[1] == self.channels
+        n, c, hh, ww = x.shape
+        o = self._fwd(Act(_rows_from_nchw(x), n, 1, hh, ww))
+        return _nchw_from_rows(o.x, n, o.H, o.W)
+
+
+class Upsample(PackedModule):
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        if dims != 2 or not use_conv or padding != 1:
+            raise NotImplementedError("only the 2-D nearest+conv Upsample is used by DynamiCrafter")
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.use_conv, self.dims = use_conv, dims
+        self.conv = nn.Conv2d(self.channels, self.out_channels, 3, padding=padding)
+
+    def _pack(self):
+        return {"w": pack_conv3x3(self.conv.weight), "b": _f32(self.conv.bias)}
+
+    def _fwd(self, h):
+        p = self.packed()
+        nf = h.B * h.T
+        up = ops.upsample2x(h.x, nf, h.H, h.W)
+        out = ops.conv3x3(up, nf, 2 * h.H, 2 * h.W, p["w"], bias=p["b"])
+        return h.like(out, 2 * h.H, 2 * h.W)
+
+    def forward(self, x):
+        assert x.shape[1] == self.channels
+        n, c, hh, ww = x.shape
+        o = self._fwd(Act(_rows_from_nchw(x), n, 1, hh, ww))
+        return _nchw_from_rows(o.x, n, o.H, o.W)
+
+
+class TemporalConvBlock(PackedModule):
+    def __init__(self, in_channels, out_channels=None, dropout=0.0, spatial_aware=False):
+        super().__init__()
+        if spatial_aware:
+            raise NotImplementedError("tempspatial_aware convs are not used by DynamiCrafter")
+        out_channels = in_channels if out_channels is None else out_channels
+        self.in_channels, self.out_channels = in_channels, out_channels
+        k, pad = (3, 1, 1), (1, 0, 0)
+        self.conv1 = nn.Sequential(nn.GroupNorm(32, in_channels), nn.SiLU(),
+                                   nn.Conv3d(in_channels, out_channels, k, padding=pad))
+        self.conv2 = nn.Sequential(nn.GroupNorm(32, out_channels), nn.SiLU(), nn.Dropout(dropout),
+                                   nn.Conv3d(out_channels, in_channels, k, padding=pad))
+        self.conv3 = nn.Sequential(nn.GroupNorm(32, out_channels), nn.SiLU(), nn.Dropout(dropout),
+                                   nn.Conv3d(out_channels, in_channels, k, padding=pad))
+        self.conv4 = nn.Sequential(nn.GroupNorm(32, out_channels), nn.SiLU(), nn.Dropout(dropout),
+                                   nn.Conv3d(out_channels, in_channels, k, padding=pad))
+        nn.init.zeros_(self.conv4[-1].weight)         # identity at init (openaimodel3d.py:269-270)
+        nn.init.zeros_(self.conv4[-1].bias)
+
+    def _stages(self):
+        return [self.conv1, self.conv2, self.conv3, self.conv4]
+
+    def _pack(self):
+        return {"w": [pack_tconv3(s[-1].weight) for s in self._stages()],
+                "b": [_f32(s[-1].bias) for s in self._stages()]}
+
+    def _fwd(self, h):
+        p = self.packed()
+        B, T, S = h.B, h.T, h.H * h.W
+        z = h.x
+        for i, st in enumerate(self._stages()):
+            gn = st[0]
+            y = ops.group_norm(z, B, T * S, gn.weight, gn.bias, gn.eps, silu=True)
+            z = ops.tconv3(y, B, T, S, p["w"][i], bias=p["b"][i], residual=h.x if i == 3 else None)
+        return h.like(z)
+
+    def forward(self, x):
+        """x: [b, c, t, h, w] (openaimodel3d.py:272)."""
+        b, c, t, hh, ww = x.shape
+        rows = x.float().permute(0, 2, 3, 4, 1).reshape(-1, c).contiguous()
+        o = self._fwd(Act(rows, b, t, hh, ww))
+        return o.x.reshape(b, t, hh, ww, c).permute(0, 4, 1, 2, 3).contiguous()
+
+
+class ResBlock(PackedModule, TimestepBlock):
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, use_scale_shift_norm=False, dims=2,
+                 use_checkpoint=False, use_conv=False, up=False, down=False, use_temporal_conv=False,
+                 tempspatial_aware=False):
+        super().__init__()
+        if use_scale_shift_norm or up or down or dims != 2 or use_conv:
+            raise NotImplementedError("scale-shift norm / resblock up-down are not used by DynamiCrafter")
+        self.channels, self.emb_channels, self.dropout = channels, emb_channels, dropout
+        self.out_channels = out_channels or channels
+        self.use_conv, self.use_checkpoint = use_conv, use_checkpoint
+        self.use_scale_shift_norm = use_scale_shift_norm
+        self.use_temporal_conv = use_temporal_conv
+        self.updown = False
+        self.in_layers = nn.Sequential(nn.GroupNorm(32, channels), nn.SiLU(),
+                                       nn.Conv2d(channels, self.out_channels, 3, padding=1))
+        self.h_upd = self.x_upd = nn.Identity()
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, self.out_channels))
+        self.out_layers = nn.Sequential(nn.GroupNorm(32, self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        nn.Conv2d(self.out_channels, self.out_channels, 3, padding=1))
+        for p in self.out_layers[-1].parameters():    # zero_module (openaimodel3d.py:179)
+            nn.init.zeros_(p)
+        if self.out_channels == channels:
+            self.skip_connection = nn.Identity()
+        else:
+            self.skip_connection = nn.Conv2d(channels, self.out_channels, 1)
+        if self.use_temporal_conv:
+            self.temopral_conv = TemporalConvBlock(self.out_channels, self.out_channels, dropout=0.1,
+                                                   spatial_aware=tempspatial_aware)
+
+    def _pack(self):
+        p = {"w1": pack_conv3x3(self.in_layers[2].weight), "b1": _f32(self.in_layers[2].bias),
+             "w2": pack_conv3x3(self.out_layers[3].weight), "b2": _f32(self.out_layers[3].bias),
+             "we": _f32(self.emb_layers[1].weight), "be": _f32(self.emb_layers[1].bias)}
+        if not isinstance(self.skip_connection, nn.Identity):
+            p["ws"] = pack_linear(self.skip_connection.weight)
+            p["bs"] = _f32(self.skip_connection.bias)
+        return p
+
+    def _fwd(self, h, emb_out, rows_per_emb, skip=None, temporal=True):
+        """h: Act; skip: optional fp32 rows concatenated on channels (openaimodel3d.py:596);
+        emb_out: fp32 [groups, Cout] = emb_layers(emb), one row per `rows_per_emb` activation rows."""
+        p = self.packed()
+        nf, S = h.B * h.T, h.H * h.W
+        g1 = self.in_layers[0]
+        has_skip_conv = "ws" in p
+        res = ops.group_norm(h.x, nf, S, g1.weight, g1.bias, g1.eps, x2=skip, silu=True, want_raw=has_skip_conv)
+        y, raw = res if has_skip_conv else (res, None)
+        h1 = ops.conv3x3(y, nf, h.H, h.W, p["w1"], bias=p["b1"], group_bias=emb_out, rows_per_group=rows_per_emb)
+        g2 = self.out_layers[0]
+        y2 = ops.group_norm(h1, nf, S, g2.weight, g2.bias, g2.eps, silu=True)
+        xs = ops.linear(raw, p["ws"], bias=p["bs"], f32=True, bf16=False) if has_skip_conv else h.x
+        h2 = ops.conv3x3(y2, nf, h.H, h.W, p["w2"], bias=p["b2"], residual=xs)
+        out = h.like(h2)
+        if self.use_temporal_conv and temporal:
+            out = self.temopral_conv._fwd(out)
+        return out
+
+    def forward(self, x, emb, batch_size=None):
+        """x: [(b t), c, h, w]; emb: [(b t), emb_channels] (openaimodel3d.py:197-236)."""
+        n, c, hh, ww = x.shape
+        p = self.packed()
+        emb_out = ops.small_linear(emb.float().contiguous(), p["we"], p["be"], silu_in=True)
+        b = batch_size if batch_size else n
+        act = Act(_rows_from_nchw(x), b, n // b, hh, ww)
+        o = self._fwd(act, emb_out, hh * ww, temporal=bool(batch_size))
+        return _nchw_from_rows(o.x, n, hh, ww)
+
+
+class UNetModel(PackedModule):
+    def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 dropout=0.0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, context_dim=None,
+                 use_scale_shift_norm=False, resblock_updown=False, num_heads=-1, num_head_channels=-1,
+                 transformer_depth=1, use_linear=False, use_checkpoint=False, temporal_conv=False,
+                 tempspatial_aware=False, temporal_attention=True, use_relative_position=True,
+                 use_causal_attention=False, temporal_length=None, use_fp16=False, addition_attention=False,
+                 temporal_selfatt_only=True, image_cross_attention=False,
+                 image_cross_attention_scale_learnable=False, default_fs=4, fs_condition=False):
+        super().__init__()
+        if num_heads == -1:
+            assert num_head_channels != -1, 'Either num_heads or num_head_channels has to be set'
+        if num_head_channels == -1:
+            assert num_heads != -1, 'Either num_heads or num_head_channels has to be set'
+        if resblock_updown or not conv_resample or dims != 2:
+            raise NotImplementedError("resblock_updown / pooling resample are not used by DynamiCrafter")
+        self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
+        self.num_res_blocks, self.attention_resolutions = num_res_blocks, attention_resolutions
+        self.dropout, self.channel_mult, self.conv_resample = dropout, channel_mult, conv_resample
+        self.temporal_attention = temporal_attention
+        time_embed_dim = model_channels * 4
+        self.use_checkpoint = use_checkpoint
+        self.dtype = torch.float16 if use_fp16 else torch.float32
+        self.addition_attention = addition_attention
+        self.temporal_length = temporal_length
+        self.image_cross_attention = image_cross_attention
+        self.image_cross_attention_scale_learnable = image_cross_attention_scale_learnable
+        self.default_fs, self.fs_condition = default_fs, fs_condition
+
+        def mlp():
+            return nn.Sequential(nn.Linear(model_channels, time_embed_dim), nn.SiLU(),
+                                 nn.Linear(time_embed_dim, time_embed_dim))
+        self.time_embed = mlp()
+        if fs_condition:
+            self.fps_embedding = mlp()
+            nn.init.zeros_(self.fps_embedding[-1].weight)
+            nn.init.zeros_(self.fps_embedding[-1].bias)
+
+        def res(cin, cout):
+            return ResBlock(cin, time_embed_dim, dropout, out_channels=cout, dims=dims, use_checkpoint=use_checkpoint,
+                            use_scale_shift_norm=use_scale_shift_norm, tempspatial_aware=tempspatial_aware,
+                            use_temporal_conv=temporal_conv)
+
+        def attn(ch):
+            if num_head_channels == -1:
+                heads, dim_head = num_heads, ch // num_heads
+            else:
+                heads, dim_head = ch // num_head_channels, num_head_channels
+            layers = [SpatialTransformer(ch, heads, dim_head, depth=transformer_depth, context_dim=context_dim,
+                                         use_linear=use_linear, use_checkpoint=use_checkpoint, disable_self_attn=False,
+                                         video_length=temporal_length, image_cross_attention=image_cross_attention,
+                                         image_cross_attention_scale_learnable=image_cross_attention_scale_learnable)]
+            if temporal_attention:
+                layers.append(TemporalTransformer(ch, heads, dim_head, depth=transformer_depth, context_dim=context_dim,
+                                                  use_linear=use_linear, use_checkpoint=use_checkpoint,
+                                                  only_self_att=True, causal_attention=use_causal_attention,
+                                                  relative_position=use_relative_position,
+                                                  temporal_length=temporal_length))
+            return layers
+
+        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(nn.Conv2d(in_channels, model_channels, 3, padding=1))])
+        if addition_attention:
+            self.init_attn = TimestepEmbedSequential(
+                TemporalTransformer(model_channels, n_heads=8, d_head=num_head_channels, depth=transformer_depth,
+                                    context_dim=context_dim, use_checkpoint=use_checkpoint,
+                                    only_self_att=temporal_selfatt_only, causal_attention=False,
+                                    relative_position=use_relative_position, temporal_length=temporal_length))
+        chans = [model_channels]
+        ch, ds = model_channels, 1
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [res(ch, mult * model_channels)]
+                ch = mult * model_channels
+                if ds in attention_resolutions:
+                    layers += attn(ch)
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                chans.append(ch)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample, dims=dims, out_channels=ch)))
+                chans.append(ch)
+                ds *= 2
+        self.middle_block = TimestepEmbedSequential(res(ch, ch), *attn(ch), res(ch, ch))
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                ich = chans.pop()
+                layers = [res(ch + ich, mult * model_channels)]
+                ch = model_channels * mult
+                if ds in attention_resolutions:
+                    layers += attn(ch)
+                if level and i == num_res_blocks:
+                    layers.append(Upsample(ch, conv_resample, dims=dims, out_channels=ch))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+        self.out = nn.Sequential(nn.GroupNorm(32, ch), nn.SiLU(), nn.Conv2d(model_channels, out_channels, 3, padding=1))
+        for p in self.out[-1].parameters():           # zero_module (openaimodel3d.py:545)
+            nn.init.zeros_(p)
+
+    # ------------------------------------------------------------------------------------------
+    def _resblocks(self):
+        return [m for m in self.modules() if isinstance(m, ResBlock)]
+
+    def _pack(self):
+        rbs = self._resblocks()
+        offs, o = [], 0
+        for rb in rbs:
+            offs.append(o)
+            o += rb.out_channels
+        p = {"w_in": pack_conv3x3(self.input_blocks[0][0].weight), "b_in": _f32(self.input_blocks[0][0].bias),
+             "w_out": pack_conv3x3(self.out[2].weight), "b_out": _f32(self.out[2].bias),
+             "te": [_f32(self.time_embed[0].weight), _f32(self.time_embed[0].bias),
+                    _f32(self.time_embed[2].weight), _f32(self.time_embed[2].bias)],
+             # all ResBlock emb_layers as ONE [sum(Cout), 4*mc] matrix (one launch per forward, not 22)
+             "we_all": torch.cat([_f32(rb.emb_layers[1].weight) for rb in rbs], 0).contiguous(),
+             "be_all": torch.cat([_f32(rb.emb_layers[1].bias) for rb in rbs], 0).contiguous(),
+             "emb_off": {id(rb): (off, rb.out_channels) for rb, off in zip(rbs, offs)}}
+        if self.fs_condition:
+            p["fe"] = [_f32(self.fps_embedding[0].weight), _f32(self.fps_embedding[0].bias),
+                       _f32(self.fps_embedding[2].weight), _f32(self.fps_embedding[2].bias)]
+        return p
+
+    def _own_version(self):
+        return sum(q._version for q in self.parameters())
+
+    def _context(self, context, b, t):
+        """openaimodel3d.py:555-562 without replicating anything: text rows are shared by the t frames of a
+        video (kv batch = frame // t), image tokens are already per frame in memory."""
+        L = context.shape[1]
+        if L == TEXT_CONTEXT_LEN + t * IMG_TOKENS_PER_FRAME:
+            ctx = context.float()
+            D = ctx.shape[2]
+            text = ops.cast_bf16(ctx[:, :TEXT_CONTEXT_LEN].reshape(b * TEXT_CONTEXT_LEN, D).contiguous())
+            image = ops.cast_bf16(ctx[:, TEXT_CONTEXT_LEN:].reshape(b * t * IMG_TOKENS_PER_FRAME, D).contiguous())
+            return CrossAttentionContext(text, TEXT_CONTEXT_LEN, t, image, IMG_TOKENS_PER_FRAME, 1)
+        return make_context(context, t, self.image_cross_attention)
+
+    def _run(self, layers, h, emb_all, pk, ctx, skip=None):
+        for layer in layers:
+            if isinstance(layer, ResBlock):
+                off, n = pk["emb_off"][id(layer)]
+                h = layer._fwd(h, emb_all[:, off:off + n], h.T * h.H * h.W, skip=skip)
+                skip = None
+            elif isinstance(layer, SpatialTransformer):
+                h = layer._fwd(h, ctx)
+            elif isinstance(layer, TemporalTransformer):
+                h = layer._fwd(h)
+            elif isinstance(layer, (Downsample, Upsample)):
+                h = layer._fwd(h)
+            else:
+                raise TypeError(type(layer))
+        return h
+
+    @torch.no_grad()
+    def forward(self, x, timesteps, context=None, features_adapter=None, fs=None, **kwargs):
+        """x: [b, in_channels, t, h, w]; timesteps: [b] long; context: [b, 77 + 16 t, context_dim];
+        fs: [b] long or None (-> default_fs).  Extra kwargs are accepted and ignored like the reference."""
+        if features_adapter is not None:
+            raise NotImplementedError("features_adapter is not used on the DynamiCrafter inference path")
+        if context is None:
+            raise ValueError("UNetModel.forward needs the cross-attention context")
+        if not x.is_cuda:
+            raise RuntimeError("dcb200 UNetModel runs on CUDA tensors only (no CPU path)")
+        pk = self.packed()
+        b, cin, t, hh, ww = x.shape
+        mc = self.model_channels
+        dev = x.device
+        # ---- embeddings (fp32, tiny): emb = time_embed(sin(t)) + fps_embedding(sin(fs))   (:550-577)
+        te = pk["te"]
+        e1 = ops.small_linear(ops.timestep_embedding(timesteps.to(dev), mc), te[0], te[1], silu_out=True)
+        emb = ops.small_linear(e1, te[2], te[3])
+        if self.fs_condition:
+            if fs is None:
+                fs = torch.full((b,), self.default_fs, dtype=torch.long, device=dev)
+            fe = pk["fe"]
+            f1 = ops.small_linear(ops.timestep_embedding(fs.to(dev), mc), fe[0], fe[1], silu_out=True)
+            ops.small_linear(f1, fe[2], fe[3], out=emb, accumulate=True)
+        emb_all = ops.small_linear(emb, pk["we_all"], pk["be_all"], silu_in=True)      # [b, sum(Cout)]
+        ctx = self._context(context.to(dev), b, t)
+        # ---- input conv
+        xr = ops.nchw_to_rows(x, 64 if cin <= 64 else (cin + 63) // 64 * 64)
+        h = Act(ops.conv3x3(xr, b * t, hh, ww, pk["w_in"], bias=pk["b_in"]), b, t, hh, ww)
+        hs = []
+        for i, module in enumerate(self.input_blocks):
+            if i > 0:
+                h = self._run(module, h, emb_all, pk, ctx)
+            if i == 0 and self.addition_attention:
+                h = self.init_attn[0]._fwd(h)
+            hs.append(h)
+        h = self._run(self.middle_block, h, emb_all, pk, ctx)
+        for module in self.output_blocks:
+            h = self._run(module, h, emb_all, pk, ctx, skip=hs.pop().x)
+        g = self.out[0]
+        y = ops.group_norm(h.x, b * t, hh * ww, g.weight, g.bias, g.eps, silu=True)
+        o = ops.conv3x3(y, b * t, hh, ww, pk["w_out"], bias=pk["b_out"])
+        return ops.rows_to_nchw(o, b, self.out_channels, t, hh, ww).to(x.dtype)

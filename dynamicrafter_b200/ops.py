@@ -54,7 +54,7 @@ def tap_gemm(a, dims, strides, adims, taps, w, N, *, bias=None, group_bias=None,
     """Raw launch.  a: bf16 tensor; dims=(D1,D2,D3) output domain; strides=(s1,s2,s3) element strides
     of A; adims=(A1,A2,A3) extents of A; taps=[(o1,o2,o3),...]; w: bf16 [N, ntaps*C]."""
     require_cuda(a, w, bias, group_bias, residual, out_f32, out_bf16)
-    assert a.dtype == BF16 and w.dtype == BF16
+    assert a.dtype == BF16 and w.dtype == BF16 and w.stride(1) == 1
     C = w.shape[1] // len(taps)
     args = TapGemmArgs()
     args.a = a.data_ptr()
@@ -69,6 +69,7 @@ def tap_gemm(a, dims, strides, adims, taps, w, N, *, bias=None, group_bias=None,
         for d in range(3):
             args.taps[i][d] = t[d]
     args.w = w.data_ptr()
+    args.w_ld = w.stride(0)
     args.N = N
     args.block_n = block_n
     args.bias = None if bias is None else bias.data_ptr()
@@ -140,3 +141,223 @@ def tconv3(a, B, T, HW, w, *, bias=None, residual=None, f32=True, bf16=False, ou
     tap_gemm(a, (HW, T, B), (C, C * HW, C * HW * T), (HW, T, B), TAPS_T3, w, N, bias=bias, residual=residual,
              out_f32=of, out_bf16=ob, ld_out=ld)
     return of if (of is not None and ob is None) else (ob if of is None else (of, ob))
+
+
+# ------------------------------------------------------------------------------------------ norms
+_GN_SCRATCH = {}
+
+
+def _gn_scratch(dev, G):
+    """(workspace, counters) reused by every GroupNorm launch on this device (stream ordered)."""
+    key = (dev.index, )
+    ent = _GN_SCRATCH.get(key)
+    if ent is None or ent[2] < G:
+        cap = max(G, 64)
+        nbytes = _lib.lib().dcb_group_norm_workspace_bytes(cap)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        cnt = torch.zeros(cap, dtype=torch.int32, device=dev)
+        ent = (ws, cnt, cap)
+        _GN_SCRATCH[key] = ent
+    return ent[0], ent[1]
+
+
+def _c_i(v):
+    return ctypes.c_int(int(v))
+
+
+def _c_ll(v):
+    return ctypes.c_longlong(int(v))
+
+
+def _c_f(v):
+    return ctypes.c_float(float(v))
+
+
+def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False, want_norm=True):
+    """x1: fp32 [G*S, C1] (+ x2 [G*S, C2] concatenated on channels) -> bf16 normalised operand
+    (and/or bf16 raw copy of the concat)."""
+    require_cuda(x1, x2, gamma, beta)
+    assert x1.dtype == F32 and x1.is_contiguous() and x1.shape[0] == G * S
+    C1 = x1.shape[1]
+    C2 = 0 if x2 is None else x2.shape[1]
+    if x2 is not None:
+        assert x2.dtype == F32 and x2.is_contiguous() and x2.shape[0] == G * S
+    dev = x1.device
+    L = _lib.lib()
+    y = raw = stats = None
+    if want_norm:
+        ws, cnt = _gn_scratch(dev, G)
+        stats = torch.empty((G, 32, 2), dtype=F32, device=dev)
+        check(L.dcb_group_norm_stats(ptr(x1), ptr(x2), _c_i(C1), _c_i(C2), _c_i(G), _c_i(S), _c_f(eps), ptr(stats),
+                                     ptr(ws), ptr(cnt), _stream()), "dcb_group_norm_stats")
+        y = torch.empty((G * S, C1 + C2), dtype=BF16, device=dev)
+    if want_raw:
+        raw = torch.empty((G * S, C1 + C2), dtype=BF16, device=dev)
+    check(L.dcb_group_norm_apply(ptr(x1), ptr(x2), _c_i(C1), _c_i(C2), _c_i(G), _c_i(S), ptr(stats), ptr(gamma),
+                                 ptr(beta), _c_i(1 if silu else 0), ptr(y), ptr(raw), _stream()),
+          "dcb_group_norm_apply")
+    if want_norm and want_raw:
+        return y, raw
+    return y if want_norm else raw
+
+
+def layer_norm(x, gamma, beta, eps=1e-5):
+    require_cuda(x, gamma, beta)
+    assert x.dtype == F32 and x.is_contiguous()
+    rows, C = x.shape
+    y = torch.empty((rows, C), dtype=BF16, device=x.device)
+    check(_lib.lib().dcb_layer_norm(ptr(x), _c_i(rows), _c_i(C), ptr(gamma), ptr(beta), _c_f(eps), ptr(y), _stream()),
+          "dcb_layer_norm")
+    return y
+
+
+# ------------------------------------------------------------------------------------------ attention
+def flash_attention(q, segments, batch, heads, nq, scale, out=None):
+    """q: bf16 2-D view [batch*nq, >= heads*64]; segments: list of (k, v, nk, kv_batch_div, seg_scale) with
+    k/v 2-D views [kv_batches*nk, >= heads*64].  Returns bf16 [batch*nq, heads*64]."""
+    require_cuda(q)
+    a = _lib.AttentionArgs()
+    a.q, a.ldq = q.data_ptr(), q.stride(0)
+    a.nseg = len(segments)
+    for i, (k, v, nk, div, sc) in enumerate(segments):
+        require_cuda(k, v)
+        assert k.dtype == BF16 and v.dtype == BF16 and k.stride(1) == 1 and v.stride(1) == 1
+        a.k[i], a.v[i] = k.data_ptr(), v.data_ptr()
+        a.ldk[i], a.ldv[i] = k.stride(0), v.stride(0)
+        a.nk[i], a.kv_batch_div[i], a.seg_scale[i] = nk, div, sc
+    a.batch, a.heads, a.nq, a.head_dim = batch, heads, nq, 64
+    if out is None:
+        out = torch.empty((batch * nq, heads * 64), dtype=BF16, device=q.device)
+    a.o, a.ldo = out.data_ptr(), out.stride(0)
+    a.softmax_scale = scale
+    check(_lib.lib().dcb_flash_attention(ctypes.byref(a), _stream()), "dcb_flash_attention")
+    return out
+
+
+def temporal_attention(q, k, v, B, L, HW, heads, scale, out=None):
+    """q/k/v: bf16 2-D views [B*L*HW, >= heads*64] (rows ordered b, frame, pixel)."""
+    require_cuda(q, k, v)
+    if out is None:
+        out = torch.empty((B * L * HW, heads * 64), dtype=BF16, device=q.device)
+    check(_lib.lib().dcb_temporal_attention(ptr(q), ptr(k), ptr(v), ptr(out), _c_ll(q.stride(0)), _c_ll(k.stride(0)),
+                                            _c_ll(v.stride(0)), _c_ll(out.stride(0)), _c_i(B), _c_i(L), _c_i(HW),
+                                            _c_i(heads), _c_i(64), _c_f(scale), _stream()), "dcb_temporal_attention")
+    return out
+
+
+def softmax_rows(x, scale):
+    require_cuda(x)
+    rows, n = x.shape
+    y = torch.empty((rows, n), dtype=BF16, device=x.device)
+    check(_lib.lib().dcb_softmax_rows(ptr(x), _c_ll(rows), _c_i(n), _c_ll(x.stride(0)), _c_f(scale), ptr(y),
+                                      _c_ll(y.stride(0)), _stream()), "dcb_softmax_rows")
+    return y
+
+
+# ------------------------------------------------------------------------------------------ layout / misc
+def nchw_to_rows(x, Cpad):
+    """fp32 [B, C, T, H, W] (or [B, C, H, W]) -> bf16 [B*T*H*W, Cpad] channels-last, zero padded."""
+    require_cuda(x)
+    x = x.contiguous().float()
+    if x.dim() == 4:
+        B, C, H, W = x.shape
+        T = 1
+    else:
+        B, C, T, H, W = x.shape
+    out = torch.empty((B * T * H * W, Cpad), dtype=BF16, device=x.device)
+    check(_lib.lib().dcb_nchw_to_rows(ptr(x), _c_i(B), _c_i(C), _c_i(T), _c_i(H * W), _c_i(Cpad), ptr(out), _stream()),
+          "dcb_nchw_to_rows")
+    return out
+
+
+def rows_to_nchw(rows, B, C, T, H, W, five_d=True):
+    require_cuda(rows)
+    assert rows.dtype == F32 and rows.stride(1) == 1
+    out = torch.empty((B, C, T, H, W) if five_d else (B, C, H, W), dtype=F32, device=rows.device)
+    check(_lib.lib().dcb_rows_to_nchw(ptr(rows), _c_i(rows.stride(0)), _c_i(B), _c_i(C), _c_i(T), _c_i(H * W), ptr(out),
+                                      _stream()), "dcb_rows_to_nchw")
+    return out
+
+
+def upsample2x(x, nf, H, W):
+    require_cuda(x)
+    C = x.shape[1]
+    out = torch.empty((nf * 4 * H * W, C), dtype=BF16, device=x.device)
+    check(_lib.lib().dcb_upsample2x(ptr(x), _c_i(nf), _c_i(H), _c_i(W), _c_i(C), ptr(out), _stream()), "dcb_upsample2x")
+    return out
+
+
+def space_to_depth(x, nf, H, W):
+    require_cuda(x)
+    C = x.shape[1]
+    Hp, Wp = (H + 1) // 2, (W + 1) // 2
+    out = torch.empty((4 * nf * Hp * Wp, C), dtype=BF16, device=x.device)
+    check(_lib.lib().dcb_space_to_depth(ptr(x), _c_i(nf), _c_i(H), _c_i(W), _c_i(C), ptr(out), _stream()),
+          "dcb_space_to_depth")
+    return out
+
+
+# stride-2 pad-1 3x3 conv on the 2x2 phase planes: tap (ky,kx) reads plane (py,px) at offset (-1 or 0)
+_S2 = {0: (1, -1), 1: (0, 0), 2: (1, 0)}   # k -> (phase, offset)
+
+
+def conv3x3_s2(planes, nf, H, W, w, *, bias=None, f32=True, bf16=False):
+    """planes: output of space_to_depth ([4*nf*Hp*Wp, C]); w: bf16 [N, 9*C] (ky,kx,c). -> [nf*Ho*Wo, N]"""
+    C = planes.shape[1]
+    Hp, Wp = (H + 1) // 2, (W + 1) // 2
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    taps = []
+    for ky in range(3):
+        py, oy = _S2[ky]
+        for kx in range(3):
+            px, ox = _S2[kx]
+            taps.append((ox, oy, (py * 2 + px) * nf))
+    N = w.shape[0]
+    of, ob, ld = _outputs(nf * Ho * Wo, N, None, f32, bf16, planes.device)
+    tap_gemm(planes, (Wo, Ho, nf), (C, C * Wp, C * Wp * Hp), (Wp, Hp, 4 * nf), taps, w, N, bias=bias,
+             out_f32=of, out_bf16=ob, ld_out=ld)
+    return of if (of is not None and ob is None) else (ob if of is None else (of, ob))
+
+
+def cast_bf16(x):
+    require_cuda(x)
+    assert x.dtype == F32 and x.is_contiguous() and x.numel() % 8 == 0
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(_lib.lib().dcb_cast_bf16(ptr(x), _c_ll(x.numel()), ptr(out), _stream()), "dcb_cast_bf16")
+    return out
+
+
+def timestep_embedding(t, dim):
+    require_cuda(t)
+    t = t.to(torch.int64).contiguous()
+    out = torch.empty((t.shape[0], dim), dtype=F32, device=t.device)
+    check(_lib.lib().dcb_timestep_embedding(ptr(t), _c_i(t.shape[0]), _c_i(dim), ptr(out), _stream()),
+          "dcb_timestep_embedding")
+    return out
+
+
+def small_linear(a, w, bias=None, *, silu_in=False, silu_out=False, out=None, accumulate=False):
+    """fp32 [M, K] x fp32 [N, K]^T for tiny M (embedding MLPs)."""
+    require_cuda(a, w, bias, out)
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=F32, device=a.device)
+    check(_lib.lib().dcb_small_linear(ptr(a), _c_i(a.stride(0)), ptr(w), ptr(bias), _c_i(M), _c_i(N), _c_i(K),
+                                      _c_i(silu_in), _c_i(silu_out), _c_i(accumulate), ptr(out), _c_i(out.stride(0)),
+                                      _stream()), "dcb_small_linear")
+    return out
+
+
+def ddim_update(x, e_cond, e_uncond, noise, coeffs):
+    """coeffs: _lib.DdimCoeffs.  Returns (x_prev, pred_x0)."""
+    require_cuda(x, e_cond, e_uncond, noise)
+    B = x.shape[0]
+    per = x.numel() // B
+    x_prev = torch.empty_like(x)
+    pred = torch.empty_like(x)
+    stds = torch.empty((B, 2), dtype=F32, device=x.device)
+    check(_lib.lib().dcb_ddim_update(ptr(x), ptr(e_cond), ptr(e_uncond), ptr(noise), _c_i(B), _c_ll(per),
+                                     ctypes.byref(coeffs), ptr(stds), ptr(x_prev), ptr(pred), _stream()),
+          "dcb_ddim_update")
+    return x_prev, pred

@@ -51,7 +51,8 @@ int dcb_check_device(void);
  * multiples of 8).  The output domain is [D3, D2, D1]; an M-tile is a box (b1,b2,b3) of it with
  * b1*b2*b3 <= 128.  For each tap the box is shifted by (o1,o2,o3); reads outside the tensor are
  * zero (TMA out-of-bounds fill) which implements the convolution padding.  W is bf16 [N, ntaps*C]
- * row-major ("K-major").  C % 64 == 0.
+ * row-major ("K-major").  C % 8 == 0, and C % 64 == 0 when ntaps > 1
+ * (a ragged last K chunk is zero-filled by TMA).
  *
  * Epilogue (fp32): acc + bias[n] + group_bias[r / rows_per_group, n]; if geglu, tile columns
  * [0,BN/2) are values and [BN/2,BN) gates and out = v * gelu_erf(g) (N_out = N/2, attention.py:421-422);
@@ -67,6 +68,7 @@ typedef struct {
     int32_t ntaps;
     int32_t taps[DCB_MAX_TAPS][3];
     const void* w;            /* bf16 [N, ntaps*C] */
+    int64_t w_ld;             /* row stride of w in elements (0 = ntaps*C) */
     int32_t N;                /* GEMM N (rows of w) */
     int32_t block_n;          /* 128 or 160 (0 = choose) */
     const float* bias;        /* [N_out] or NULL (for geglu: [N], value half then gate half per tile) */
@@ -83,6 +85,87 @@ typedef struct {
 } dcb_tap_gemm_args;
 
 int dcb_tap_gemm(const dcb_tap_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GroupNorm(32 groups) over channels-last fp32 activations, split in statistics + apply.
+ * Replaces ATen group_norm at basics.py:76-87 (eps 1e-5), attention.py:265,331 (1e-6),
+ * openaimodel3d.py:256-262 (1e-5, 5-D: an instance spans all frames), ae_modules.py:15-16 (1e-6).
+ *
+ * x = channel concat of x1 [G*S, C1] and optional x2 [G*S, C2] (the UNet skip concat,
+ * openaimodel3d.py:596, is never materialised in fp32).  G instances of S rows each.
+ * stats: [G, 32, 2] (mean, rstd).  workspace: dcb_group_norm_workspace_bytes(G) bytes.
+ * counters: G zero-initialised uint32 (left zero on return).
+ * apply writes bf16 y = silu?(norm(x)*gamma+beta) and/or raw = bf16(x), both [G*S, C1+C2].
+ * ------------------------------------------------------------------------------------------ */
+size_t dcb_group_norm_workspace_bytes(int G);
+int dcb_group_norm_stats(const float* x1, const float* x2, int C1, int C2, int G, int S, float eps,
+                         float* stats, void* workspace, unsigned* counters, void* stream);
+int dcb_group_norm_apply(const float* x1, const float* x2, int C1, int C2, int G, int S,
+                         const float* stats, const float* gamma, const float* beta, int silu_act,
+                         void* y_bf16, void* raw_bf16, void* stream);
+/* LayerNorm over the last dim (attention.py:225-227), fp32 in, bf16 out. C % 4 == 0, C <= 2560. */
+int dcb_layer_norm(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,
+                   void* y_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention (head_dim 64).  q/k/v/o are bf16 column slices of row-major buffers: head h lives at
+ * columns [h*64, h*64+64) and rows advance by ld* elements.
+ *
+ * dcb_flash_attention: batch x heads independent problems, nq queries each; up to two key/value
+ * segments with independent softmaxes:  o = sum_s seg_scale[s] * softmax(q k_s^T * scale) v_s.
+ * Segment s of batch b reads kv batch b / kv_batch_div[s] (text keys are shared by the 16 frames of
+ * a video).  Replaces attention.py:101-125 (self) and :89-94,129-142 (text + image cross-attention).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const void* q; int64_t ldq;
+    const void* k[2]; const void* v[2]; int64_t ldk[2]; int64_t ldv[2];
+    int32_t nk[2]; int32_t kv_batch_div[2]; float seg_scale[2];
+    int32_t nseg, batch, heads, nq, head_dim;
+    void* o; int64_t ldo;
+    float softmax_scale;
+} dcb_attention_args;
+int dcb_flash_attention(const dcb_attention_args* args, void* stream);
+
+/* Self-attention over L <= 16 frames for every (batch, location, head); token row of frame f is
+ * ((b*L + f)*HW + pix).  Replaces attention.py:387-390 on '(b hw) t c' tensors (no transposes). */
+int dcb_temporal_attention(const void* q, const void* k, const void* v, void* o, long long ldq,
+                           long long ldk, long long ldv, long long ldo, int B, int L, int HW, int heads,
+                           int head_dim, float softmax_scale, void* stream);
+/* y = softmax(scale * x) row-wise, fp32 in, bf16 out (VAE AttnBlock, ae_modules.py:66-68). */
+int dcb_softmax_rows(const float* x, long long rows, int n, long long ldx, float scale, void* y_bf16,
+                     long long ldy, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / resampling helpers (replace einops rearranges and F.interpolate, openaimodel3d.py:566,
+ * 602,103; ae_modules.py:124) and the embedding MLPs (openaimodel3d.py:168-174,370-380,550-577).
+ * ------------------------------------------------------------------------------------------ */
+int dcb_nchw_to_rows(const float* src, int B, int C, int T, int HW, int Cpad, void* dst_bf16, void* stream);
+int dcb_rows_to_nchw(const float* src, int ld, int B, int C, int T, int HW, float* dst, void* stream);
+int dcb_upsample2x(const float* src, int nf, int H, int W, int C, void* dst_bf16, void* stream);
+int dcb_space_to_depth(const float* src, int nf, int H, int W, int C, void* dst_bf16, void* stream);
+int dcb_cast_bf16(const float* src, long long n, void* dst_bf16, void* stream);
+int dcb_timestep_embedding(const long long* t, int B, int dim, float* out, void* stream);
+/* out[m,n] (+)= silu_out?( sum_k silu_in?(a[m,k]) * w[n,k] + bias[n] ); fp32, tiny M. */
+int dcb_small_linear(const float* a, int lda, const float* w, const float* bias, int M, int N, int K,
+                     int silu_in, int silu_out, int accumulate, float* out, int ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused classifier-free guidance + guidance rescale + v/eps conversion + DDIM x_{t-1} update.
+ * Replaces ~25 pointwise launches of DDIMSampler.p_sample_ddim (ddim.py:226-277),
+ * rescale_noise_cfg (utils_diffusion.py:147-158), predict_*_from_z_and_v (ddpm3d.py:239-251).
+ * Scalars are computed by the host in the reference's fp32 order (see DDIMSampler); e_uncond
+ * NULL = no guidance.  stds_ws: 2*B floats (needed when guidance_rescale > 0).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t is_v;
+    float cfg_scale, guidance_rescale, one_minus_guidance_rescale;
+    float sqrt_acp_t, sqrt_1m_acp_t;   /* sqrt_alphas_cumprod[t], sqrt_one_minus_alphas_cumprod[t] (v-param) */
+    float sqrt_a_t, sqrt_1m_a_t;       /* sqrt(ddim_alphas[index]), ddim_sqrt_one_minus_alphas[index] (eps-param) */
+    float sqrt_a_prev, dir_coef, sigma_t, temperature, x0_rescale;
+} dcb_ddim_coeffs;
+int dcb_ddim_update(const float* x, const float* e_cond, const float* e_uncond, const float* noise,
+                    int B, long long per_sample, const dcb_ddim_coeffs* c, float* stds_ws, float* x_prev,
+                    float* pred_x0, void* stream);
 
 #ifdef __cplusplus
 }

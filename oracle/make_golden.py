@@ -90,7 +90,7 @@ TINY_UNET = dict(in_channels=8, out_channels=4, model_channels=64, attention_res
                  use_relative_position=False, use_causal_attention=False, temporal_length=16,
                  addition_attention=True, image_cross_attention=True, default_fs=24, fs_condition=True)
 TINY_UNET_256 = dict(TINY_UNET, image_cross_attention_scale_learnable=True, default_fs=3)
-TINY_VAE = dict(double_z=True, z_channels=4, resolution=64, in_channels=3, out_ch=3, ch=32,
+TINY_VAE = dict(double_z=True, z_channels=4, resolution=64, in_channels=3, out_ch=3, ch=64,
                 ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)
 
 
@@ -262,6 +262,11 @@ def golden_keys():
         with torch.device("meta"):
             u = UNetModel(**cfg["unet_config"]["params"])
             d = Decoder(**cfg["first_stage_config"]["params"]["ddconfig"])
+        from lvdm.models.autoencoder import AutoencoderKL
+        with torch.device("meta"):
+            ae = AutoencoderKL(ddconfig=cfg["first_stage_config"]["params"]["ddconfig"],
+                               lossconfig={"target": "torch.nn.Identity"}, embed_dim=4)
+        res["autoencoder_" + tag] = {k: list(v.shape) for k, v in ae.state_dict().items()}
         res["unet_" + tag] = {k: list(v.shape) for k, v in u.state_dict().items()}
         res["decoder_" + tag] = {k: list(v.shape) for k, v in d.state_dict().items()}
         res["unet_cfg_" + tag] = cfg["unet_config"]["params"]
