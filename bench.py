@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""Benchmark of the DynamiCrafter denoising hot path on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 512]
+
+One "step" = one classifier-free-guided DDIM step of the 320x512x16-frame model (BASELINE.json configs[1]):
+cond + uncond UNet forward (issued as one batch-2 forward) + the fused CFG/DDIM update.  `value` = steps/s with
+all inputs resident in HBM; `e2e` = the same step driven through the public DDIMSampler API with the step's inputs
+(x_t, conditioning) coming from pinned HOST memory and x_{t-1} read back to the host every step.  With N>1 GPUs
+every rank denoises its own video (the reference's own scaling mode: independent prompts per rank) -> weak scaling,
+no collective on the data path; the final latents are all-gathered once (NCCL) outside the timed steps.
+
+Extra objects: `roofline` (tcgen05 implicit-GEMM kernel: algorithmic FLOPs / CUDA-event time of every launch of one
+step, against the measured bf16 peak), `cpu_baseline` (the CPU oracle restatement of the reference, timed on the
+host cores on a bounded sample), `breakdown_ms` (per kernel class), `video` (full 50-step sample + VAE decode).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "UNet denoise steps/s at 320x512x16f, 50 DDIM, CFG (1 step = cond+uncond UNet forward + DDIM update)"
+SEED = 7
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d.get("bf16_tflops_sustained", 1379.1), burst=d.get("bf16_tflops", 1636.3),
+                    hbm=d.get("hbm_gbs", 6535.4), source="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(tflops=1400.0, burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in open(self.path):
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(sm)[len(sm) // 2:]
+        return {"sm_mhz": sorted(busy)[len(busy) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w_max": max(pw), "samples": len(sm)}
+
+
+def build_host(cfg_name, device, with_vae=True):
+    from dynamicrafter_b200.configs import model_params
+    from dynamicrafter_b200.host import DiffusionHost
+    from dynamicrafter_b200.synth import synth_tensor
+    mp = model_params(cfg_name)
+    if not with_vae:
+        mp.pop("first_stage_config")
+    with torch.device("meta"):
+        host = DiffusionHost.from_model_params(mp)
+    host = host.to_empty(device=device)
+    # to_empty() discards buffer values: rebuild the schedule buffers from a CPU instance without networks
+    ref = DiffusionHost.from_model_params(dict(mp, unet_config=dict(params=_tiny_unet()), first_stage_config=None))
+    for name, buf in ref.named_buffers():
+        if "." not in name:
+            getattr(host, name).copy_(buf)
+    with torch.no_grad():
+        for mod, prefix in ((host.unet, "unet."), (host.first_stage_model, "vae.")):
+            if mod is None:
+                continue
+            for k, p in list(mod.named_parameters()) + list(mod.named_buffers()):
+                p.copy_(synth_tensor(prefix + k, p.shape, SEED).to(device))
+    return host.eval(), mp
+
+
+def _tiny_unet():
+    return dict(in_channels=8, out_channels=4, model_channels=64, attention_resolutions=[1], num_res_blocks=1,
+                channel_mult=[1], num_head_channels=64, context_dim=64, use_linear=True, temporal_length=16,
+                use_relative_position=False)
+
+
+def make_inputs(mp, B, T, device, pinned=False):
+    from dynamicrafter_b200.synth import synth_input
+    h, w = mp["image_size"]
+    t = {"x_T": synth_input("x_T", (B, 4, T, h, w), SEED), "concat": synth_input("concat", (B, 4, T, h, w), SEED),
+         "cond": synth_input("cond", (B, 77 + 16 * T, 1024), SEED), "uncond": synth_input("uncond", (B, 77 + 16 * T, 1024), SEED)}
+    if pinned:
+        return {k: v.pin_memory() for k, v in t.items()}
+    return {k: v.to(device) for k, v in t.items()}
+
+
+# ------------------------------------------------------------------------------------------- instrumentation
+class OpTimer:
+    """Wraps the ops.* launch helpers with CUDA events (on the launching stream) for ONE eager step."""
+    CLASSES = {"tap_gemm": "tcgen05_gemm_conv", "flash_attention": "attention_spatial",
+               "temporal_attention": "attention_temporal", "group_norm": "groupnorm", "layer_norm": "layernorm",
+               "ddim_update": "ddim_update"}
+
+    def __init__(self):
+        from dynamicrafter_b200 import ops
+        self.ops, self.saved, self.records, self.gemm = ops, {}, [], []
+
+    def __enter__(self):
+        ops = self.ops
+        names = ["tap_gemm", "flash_attention", "temporal_attention", "group_norm", "layer_norm", "ddim_update",
+                 "softmax_rows", "nchw_to_rows", "rows_to_nchw", "upsample2x", "space_to_depth", "cast_bf16",
+                 "timestep_embedding", "small_linear"]
+        for n in names:
+            fn = getattr(ops, n)
+            self.saved[n] = fn
+            setattr(ops, n, self._wrap(n, fn))
+        return self
+
+    def _wrap(self, name, fn):
+        def inner(*a, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **kw)
+            e1.record()
+            flops = 0
+            if name == "tap_gemm":
+                dims, taps, w, N = a[1], a[4], a[5], a[6]
+                flops = 2.0 * dims[0] * dims[1] * dims[2] * N * w.shape[1]
+            self.records.append((self.CLASSES.get(name, "layout_misc"), e0, e1, flops))
+            return out
+        return inner
+
+    def __exit__(self, *exc):
+        for n, fn in self.saved.items():
+            setattr(self.ops, n, fn)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        by, gemm_ms, gemm_flops, n_gemm = {}, 0.0, 0.0, 0
+        for cls, e0, e1, fl in self.records:
+            ms = e0.elapsed_time(e1)
+            by[cls] = by.get(cls, 0.0) + ms
+            if cls == "tcgen05_gemm_conv":
+                gemm_ms += ms; gemm_flops += fl; n_gemm += 1
+        return by, gemm_ms, gemm_flops, n_gemm, len(self.records)
+
+
+# ------------------------------------------------------------------------------------------- CPU baseline
+def cpu_sample_seconds(cfg_name, frames, threads):
+    """One cond-branch UNet forward of the CPU oracle (fp32 eager restatement of the reference) on `frames` of the
+    16 frames of the workload latent.  Returns (seconds, description)."""
+    from dynamicrafter_b200.configs import model_params
+    from dynamicrafter_b200.host import DiffusionHost
+    from dynamicrafter_b200.synth import synth_input
+    from oracle import unet_oracle
+    torch.set_num_threads(threads)
+    mp = model_params(cfg_name)
+    ucfg = mp["unet_config"]["params"]
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in DiffusionHost(ucfg).unet.state_dict().items()}
+    g = torch.Generator().manual_seed(SEED)
+    sd = {}
+    for k, s in shapes.items():      # cheap non-degenerate init: timing does not depend on the values
+        t = torch.empty(s)
+        t.uniform_(-1, 1, generator=g)
+        if len(s) >= 2:
+            t.mul_(1.0 / (t[0].numel() ** 0.5))
+        elif k.endswith("weight"):
+            t.mul_(0.1).add_(1.0)
+        sd[k] = t
+    h, w = mp["image_size"]
+    x = synth_input("x", (1, 8, frames, h, w), SEED)
+    ctx = synth_input("ctx", (1, 77 + 16 * frames, 1024), SEED)
+    ts = torch.tensor([500], dtype=torch.long)
+    fs = torch.tensor([24], dtype=torch.long)
+    return sd, (lambda: unet_oracle.unet_forward(sd, ucfg, x, ts, ctx, fs))
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation (oracle port: the reference is pure Python and its host
+    needs pytorch_lightning/open_clip which are absent, so the functional torch restatement pinned to it is timed)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count()
+    frames = 2
+    sd, fwd = cpu_sample_seconds(args.config, frames, threads)
+    for _ in range(min(args.warmup, 1)):
+        fwd()
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        fwd()
+        times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    step_s = sec * (16 / frames) * 2                  # 16 frames, cond + uncond
+    val = 1.0 / step_s
+    sample = (f"oracle UNet forward (fp32 eager torch, {threads} threads), 1 CFG branch, {frames} of 16 frames at latent 40x64; "
+              f"step time extrapolated x{16 // frames} frames x2 branches")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "DynamiCrafter 512 (320x512x16f latent 40x64), DDIM 50 CFG 7.5, UNet step; CPU"},
+            "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="512", choices=["256", "512", "1024"])
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-video", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from dynamicrafter_b200 import _lib, ops
+    from dynamicrafter_b200.configs import SAMPLER, UNET_TFLOP, VAE_TFLOP
+    from dynamicrafter_b200.lvdm.models.samplers.ddim import DDIMSampler
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.lib().dcb_check_device(), "dcb_check_device")
+    peaks = load_peaks()
+
+    host, mp = build_host(args.config, dev, with_vae=not args.no_video)
+    host.unet.use_cuda_graph = not args.no_graph
+    sm = SAMPLER[args.config]
+    B, T = 1, 16
+    h, w = mp["image_size"]
+    inp = make_inputs(mp, B, T, dev)
+    pin = make_inputs(mp, B, T, dev, pinned=True)
+    fs = torch.tensor([sm["fs"]] * B, dtype=torch.long, device=dev)
+    cond = {"c_crossattn": [inp["cond"]], "c_concat": [inp["concat"]]}
+    uc = {"c_crossattn": [inp["uncond"]], "c_concat": [inp["concat"]]}
+    smp = DDIMSampler(host)
+    smp.make_schedule(sm["S"], ddim_discretize=sm["timestep_spacing"], ddim_eta=sm["eta"], verbose=False)
+    steps_desc = list(reversed(list(smp.ddim_timesteps)))
+    total = len(steps_desc)
+    kw = dict(unconditional_guidance_scale=sm["cfg"], unconditional_conditioning=uc, fs=fs,
+              guidance_rescale=sm["guidance_rescale"])
+
+    def one_step(x, i, c=cond, extra=kw):
+        i = i % total
+        step = int(steps_desc[i])
+        ts = torch.full((B,), step, device=dev, dtype=torch.long)
+        smp._step_hint = step
+        return smp.p_sample_ddim(x, c, ts, index=total - i - 1, **extra)[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing
+    x = inp["x_T"].clone()
+    for i in range(args.warmup):
+        x = one_step(x, i)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        x = one_step(x, args.warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms) / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    assert torch.isfinite(x).all(), "non-finite latents"
+
+    # ---------------- end-to-end through the public API from HOST buffers (pinned), result read back every step
+    hx = pin["x_T"].clone().pin_memory()
+    out_host = torch.empty_like(hx).pin_memory()
+    h2d = sum(pin[k].numel() * 4 for k in ("x_T", "cond", "uncond", "concat"))
+    d2h = hx.numel() * 4
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        dx = hx.to(dev, non_blocking=True)
+        c_i = {"c_crossattn": [pin["cond"].to(dev, non_blocking=True)], "c_concat": [pin["concat"].to(dev, non_blocking=True)]}
+        uc_i = {"c_crossattn": [pin["uncond"].to(dev, non_blocking=True)], "c_concat": c_i["c_concat"]}
+        xo = one_step(dx, args.warmup + i, c=c_i, extra=dict(kw, unconditional_conditioning=uc_i))
+        out_host.copy_(xo, non_blocking=True)
+        torch.cuda.synchronize()
+        hx.copy_(out_host)
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / (float(e2e_ms) / args.steps * 1e-3)
+
+    # ---------------- instrumented eager step: per-launch CUDA events -> roofline of the tcgen05 kernel + breakdown
+    host.unet.use_cuda_graph = False
+    one_step(inp["x_T"].clone(), 0)
+    torch.cuda.synchronize()
+    calls0 = _lib.CALLS[0]
+    with OpTimer() as ot:
+        one_step(inp["x_T"].clone(), 1)
+    by, gemm_ms, gemm_flops, n_gemm, n_launch = ot.summary()
+    launches_per_step = _lib.CALLS[0] - calls0
+    host.unet.use_cuda_graph = not args.no_graph
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    step_tflop = 2 * UNET_TFLOP[args.config] * B
+    roofline = {"bound": "tensor", "kernel": "tap_gemm_kernel (tcgen05 implicit GEMM: linear + conv3x3 + temporal conv)",
+                "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
+                "frac": round(achieved / peaks["tflops"], 4), "traffic": None, "peak_source": peaks["source"],
+                "launches_per_step": n_gemm, "avg_launch_us": round(gemm_ms * 1e3 / max(n_gemm, 1), 2),
+                "kernel_share_of_step": round(gemm_ms / max(sum(by.values()), 1e-9), 4),
+                "whole_step_tflops": round(step_tflop / (ms_per_step * 1e-3), 1),
+                "whole_step_frac_of_peak": round(step_tflop / (ms_per_step * 1e-3) / peaks["tflops"], 4),
+                "whole_step_frac_of_spec_2250": round(step_tflop / (ms_per_step * 1e-3) / 2250.0, 4)}
+
+    # ---------------- one full video through the public API: sample(50 steps) + all-gather + VAE decode
+    video = None
+    if not args.no_video:
+        barrier()
+        t0 = time.perf_counter()
+        samples, _ = smp.sample(S=sm["S"], batch_size=B, shape=(4, T, h, w), conditioning=cond,
+                                unconditional_guidance_scale=sm["cfg"], unconditional_conditioning=uc, eta=sm["eta"],
+                                verbose=False, x_T=inp["x_T"], fs=fs, timestep_spacing=sm["timestep_spacing"],
+                                guidance_rescale=sm["guidance_rescale"])
+        torch.cuda.synchronize()
+        t_s = time.perf_counter() - t0
+        if world > 1:
+            gathered = [torch.empty_like(samples) for _ in range(world)]
+            dist.all_gather(gathered, samples)        # the single collective of this mode
+        t1 = time.perf_counter()
+        frames = host.decode_first_stage(samples, frames_per_call=8)
+        torch.cuda.synchronize()
+        t_d = time.perf_counter() - t1
+        tv = torch.tensor([t_s + t_d, t_s, t_d], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        vid_tflop = 100 * UNET_TFLOP[args.config] + VAE_TFLOP[args.config]
+        video = {"s_per_video": round(float(tv[0]), 3), "sample_s": round(float(tv[1]), 3), "decode_s": round(float(tv[2]), 3),
+                 "videos_per_s_all_gpus": round(world / float(tv[0]), 4), "tflops": round(vid_tflop / float(tv[0]), 1),
+                 "frac_of_peak": round(vid_tflop / float(tv[0]) / peaks["tflops"], 4),
+                 "finite": bool(torch.isfinite(frames).all())}
+
+    # ---------------- CPU baseline (rank 0, N=1): the oracle on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count()
+        frames_s = 2
+        _, fwd = cpu_sample_seconds(args.config, frames_s, threads)
+        t0 = time.perf_counter()
+        fwd()
+        sec = time.perf_counter() - t0
+        cpu = {"value": 1.0 / (sec * (16 / frames_s) * 2), "unit": "steps/s", "cores": threads, "kind": "port",
+               "sample": f"1 oracle UNet forward (1 CFG branch, {frames_s} of 16 frames, latent {h}x{w}) = {sec:.1f} s; "
+                         f"x{16 // frames_s} frames x2 branches extrapolated"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 4), "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"DynamiCrafter {args.config} ({h * 8}x{w * 8}x16f, latent {h}x{w}), DDIM {sm['S']} "
+                                       f"{sm['timestep_spacing']} eta {sm['eta']}, CFG {sm['cfg']}, guidance_rescale "
+                                       f"{sm['guidance_rescale']}; 1 video per GPU; random-init weights (1.44 B params)",
+                           "videos_per_gpu": B, "cuda_graph": not args.no_graph,
+                           "l2": "not flushed: per-step working set (2.9 GB bf16 weights + activations) >> 126 MB L2"},
+                "s_per_video_unet_only": round(sm["S"] * ms_per_step * 1e-3, 3),
+                "e2e": {"value": round(e2e_value, 4), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
+                "clocks": clk, "roofline": roofline, "breakdown_ms": {k: round(v, 3) for k, v in sorted(by.items())},
+                "video": video, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -80,7 +80,11 @@ EXPORTS = [
 ]
 
 
+CALLS = [0]     # number of successful C-ABI launches (bench.py reports it as gpu_launches)
+
+
 def check(rc, what=""):
+    CALLS[0] += 1
     if rc != 0:
         msg = lib().dcb_last_error().decode(errors="replace")
         raise DcbError(f"{what} failed ({rc}): {msg}")
