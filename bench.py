@@ -155,11 +155,20 @@ class OpTimer:
             e0.record()
             out = fn(*a, **kw)
             e1.record()
-            flops = 0
+            flops, key = 0, name
             if name == "tap_gemm":
                 dims, taps, w, N = a[1], a[4], a[5], a[6]
                 flops = 2.0 * dims[0] * dims[1] * dims[2] * N * w.shape[1]
-            self.records.append((self.CLASSES.get(name, "layout_misc"), e0, e1, flops))
+                key = (f"gemm M={dims[0] * dims[1] * dims[2]} N={N} K={w.shape[1]} taps={len(taps)} "
+                       f"f32={kw.get('out_f32') is not None} bf16={kw.get('out_bf16') is not None} "
+                       f"res={kw.get('residual') is not None} geglu={bool(kw.get('geglu'))}")
+            elif name == "group_norm":
+                key = f"group_norm G={a[1]} S={a[2]} C={a[0].shape[1] + (kw['x2'].shape[1] if kw.get('x2') is not None else 0)}"
+            elif name == "flash_attention":
+                key = f"flash_attention B={a[2]} H={a[3]} nq={a[4]} nk={[s[2] for s in a[1]]}"
+            elif name == "layer_norm":
+                key = f"layer_norm rows={a[0].shape[0]} C={a[0].shape[1]}"
+            self.records.append((self.CLASSES.get(name, "layout_misc"), e0, e1, flops, key))
             return out
         return inner
 
@@ -169,12 +178,20 @@ class OpTimer:
 
     def summary(self):
         torch.cuda.synchronize()
-        by, gemm_ms, gemm_flops, n_gemm = {}, 0.0, 0.0, 0
-        for cls, e0, e1, fl in self.records:
+        by, gemm_ms, gemm_flops, n_gemm, shapes = {}, 0.0, 0.0, 0, {}
+        for cls, e0, e1, fl, key in self.records:
             ms = e0.elapsed_time(e1)
             by[cls] = by.get(cls, 0.0) + ms
+            ent = shapes.setdefault(key, [0, 0.0, 0.0])
+            ent[0] += 1; ent[1] += ms; ent[2] += fl
             if cls == "tcgen05_gemm_conv":
                 gemm_ms += ms; gemm_flops += fl; n_gemm += 1
+        dump = os.environ.get("DCB_BENCH_SHAPES")
+        if dump:       # per-shape table for kernel tuning: count, total ms, TFLOP/s
+            rows = sorted(shapes.items(), key=lambda kv: -kv[1][1])
+            with open(dump, "w") as f:
+                for k, (n, ms, fl) in rows:
+                    f.write(f"{ms:9.3f} ms  x{n:<4d} {fl / max(ms, 1e-9) / 1e9:8.1f} TFLOP/s  {k}\n")
         return by, gemm_ms, gemm_flops, n_gemm, len(self.records)
 
 
