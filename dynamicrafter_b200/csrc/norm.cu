@@ -10,7 +10,7 @@
 namespace dcb {
 
 constexpr int kGroups = 32;
-constexpr int kMaxChunks = 128;
+constexpr int kMaxChunks = 1024;
 constexpr int kMaxSplitChannels = 4096;   // smem slots of the stats kernel: row_split * C <= this
 
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
@@ -87,19 +87,26 @@ gn_stats_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
     __syncthreads();
     if (s_last) {
         __threadfence();
-        if (tid < kGroups) {
-            double sum = 0.0, sq = 0.0;
-            const volatile float* pp = partial + static_cast<size_t>(n) * nchunks * (kGroups * 2);
-            for (int c = 0; c < nchunks; ++c) {
-                sum += static_cast<double>(pp[c * kGroups * 2 + tid * 2]);
-                sq += static_cast<double>(pp[c * kGroups * 2 + tid * 2 + 1]);
-            }
+        // 8 threads per group, each a fixed strided subset of the chunks, then a fixed-order shuffle tree
+        const int g = tid >> 3, sub = tid & 7;
+        double sum = 0.0, sq = 0.0;
+        const volatile float* pp = partial + static_cast<size_t>(n) * nchunks * (kGroups * 2);
+        for (int c = sub; c < nchunks; c += 8) {
+            sum += static_cast<double>(pp[c * kGroups * 2 + g * 2]);
+            sq += static_cast<double>(pp[c * kGroups * 2 + g * 2 + 1]);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        }
+        if (sub == 0) {
             const double cnt = static_cast<double>(S) * cg;
             const double mean = sum / cnt;
             double var = sq / cnt - mean * mean;
             if (var < 0.0) var = 0.0;
-            stats[(static_cast<size_t>(n) * kGroups + tid) * 2] = static_cast<float>(mean);
-            stats[(static_cast<size_t>(n) * kGroups + tid) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+            stats[(static_cast<size_t>(n) * kGroups + g) * 2] = static_cast<float>(mean);
+            stats[(static_cast<size_t>(n) * kGroups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
         }
         if (tid == 0) counters[n] = 0;   // self-cleaning: ready for the next launch
     }
@@ -216,8 +223,8 @@ layer_norm_kernel(const float* __restrict__ x, int rows, int C, const float* __r
 
 static int pick_chunks(int G, int S) {
     // enough blocks to fill the machine (~4 per SM) without making chunks smaller than 32 rows
-    int want = (4 * num_sms() + G - 1) / G;
-    int maxc = (S + 31) / 32;
+    int want = (8 * num_sms() + G - 1) / G;   // ~8 resident 256-thread blocks per SM keeps enough bytes in flight
+    int maxc = (S + 15) / 16;
     int c = want < maxc ? want : maxc;
     if (c > kMaxChunks) c = kMaxChunks;
     if (c < 1) c = 1;

@@ -6,21 +6,30 @@
 // (3 taps over frames): the A operand is fetched by TMA as a box of a 4-D channels-last tensor and a
 // tap is just a coordinate shift of that box; TMA's out-of-bounds zero fill is the conv padding.
 //
-// CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> fused bias / embedding / GEGLU / residual -> HBM).
-// Pipelines: smem ring (full/empty mbarriers, 6 stages of {A 128x64, B BNx64} bf16, SWIZZLE_128B)
-// and a 2-deep TMEM accumulator ring so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Grid = min(#tiles, #SMs); tiles are strided over CTAs with N fastest so an A tile is re-read from L2.
+// CTA = 320 threads, one CTA per SM, persistent over tiles (N fastest so an A tile is re-read from L2):
+//   warp 0      TMA producer: {A 128x64, B BNx64} bf16 stages, SWIZZLE_128B, full/empty mbarrier ring
+//   warp 1      TMEM owner + single-thread tcgen05.mma issuer (128 x BN x 16), 2-deep TMEM accumulator ring
+//   warps 2..9  epilogue, two groups of 4 warps (each group covers the 128 TMEM lanes and takes every other
+//               32-column chunk): tcgen05.ld -> fused bias / per-video embedding / exact-erf GEGLU / residual
+//               -> swizzled smem slot -> TMA tile store.  The fp32 residual chunk is PREFETCHED by TMA into
+//               the same slot (in place), so the epilogue issues no per-thread global loads or stores and
+//               all HBM traffic of the kernel is asynchronous and fully coalesced.  Out-of-range rows and
+//               columns (ragged tiles, N < 32) are clipped by the TMA unit.
 #include "dcb_internal.h"
 #include "ptx.cuh"
 
 namespace dcb {
 
-constexpr int kStages = 6;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kABytes = kBlockM * kBlockK * 2;
+constexpr int kChunkCols = 32;                       // epilogue chunk: 32 output columns
+constexpr int kSlotBytes = kBlockM * kChunkCols * 4;  // fp32 chunk (bf16 chunks use the first half)
+constexpr int kEpiBytes = 2 * 2 * kSlotBytes;         // 2 groups x 2 slots
+
+template <int BN> struct StageCount { static constexpr int value = (BN <= 128) ? 5 : 4; };
 
 struct TapGemmParams {
     int D1, D2, D3, b1, b2, b3, t1, t2, t3;
@@ -31,14 +40,9 @@ struct TapGemmParams {
     const float* bias;
     const float* group_bias;
     int rows_per_group, ld_group_bias;
-    const float* residual;
-    int ld_residual;
-    int geglu;
-    float* out_f32;
-    __nv_bfloat16* out_bf16;
-    int ld_out;
+    int has_residual, geglu, out_bf16;
     float out_scale;
-    uint32_t stage_bytes;
+    uint32_t stage_bytes, res_bytes;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -46,7 +50,9 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                 const TapGemmParams p) {
+    constexpr int kStages = StageCount<BN>::value;
     constexpr int kBBytes = BN * kBlockK * 2;
     constexpr int kStageBytes = kABytes + kBBytes;
     constexpr int kAccStride = (BN <= 128) ? 128 : 256;
@@ -55,12 +61,14 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint8_t* epi = smem + kStages * kStageBytes;                      // 1024-aligned (stage sizes are multiples)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi + kEpiBytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + kStages;
     uint64_t* tfull = bars + 2 * kStages;
     uint64_t* tempty = bars + 2 * kStages + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint64_t* rfull = bars + 2 * kStages + 4;                         // [group][slot]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -70,14 +78,17 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmOut);
+        if (p.has_residual) tma_prefetch_desc(&tmRes);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 4);
+            mbar_init(&tempty[a], kEpiWarps);
         }
+        for (int i = 0; i < 4; ++i) mbar_init(&rfull[i], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -136,117 +147,147 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else {
-        // ------------------------------------------------------------ epilogue warps 2..5
-        const int q = warp & 3;                   // TMEM lane quarter this warp may access
-        const int r = q * 32 + lane;              // row of the tile owned by this thread
-        constexpr int kCols = 16;
-        uint32_t tc = 0;
+        // ------------------------------------------------------------ epilogue: 2 groups x 4 warps
+        const int q = warp & 3;                    // TMEM lane quarter this warp may access
+        const int grp = (warp - 2) >> 2;           // chunk parity handled by this group
+        const int r = q * 32 + lane;               // tile row owned by this thread
+        const bool leader = (q == 0 && lane == 0);
+        const int bar_id = 1 + grp;
+        uint8_t* slots = epi + grp * 2 * kSlotBytes;
+        uint64_t* my_rfull = rfull + grp * 2;
+        const int ncols = p.geglu ? BN / 2 : BN;   // output columns per tile
+        const int nch = ncols / kChunkCols;
+        const int my_nch = (nch - grp + 1) / 2;    // chunks grp, grp+2, ...
+        uint32_t tc = 0, cnt = 0;
+
+        // leader only: TMA-prefetch the residual chunk of work item (tile, ci) into slot (cnt & 1)
+        auto prefetch_res = [&](int tile, int ci, uint32_t cnt_item) {
+            const int m_tile = tile / p.num_n_tiles;
+            const int n_tile = tile - m_tile * p.num_n_tiles;
+            const int s = cnt_item & 1;
+            mbar_arrive_expect_tx(&my_rfull[s], p.res_bytes);
+            tma_load_4d(slots + s * kSlotBytes, &tmRes, &my_rfull[s], n_tile * ncols + ci * kChunkCols,
+                        (m_tile % p.t1) * p.b1, ((m_tile / p.t1) % p.t2) * p.b2, (m_tile / (p.t1 * p.t2)) * p.b3);
+        };
+        if (p.has_residual && leader && my_nch > 0 && static_cast<int>(blockIdx.x) < num_tiles)
+            prefetch_res(blockIdx.x, grp, 0);
+
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
             const int m_tile = tile / p.num_n_tiles;
             const int n_tile = tile - m_tile * p.num_n_tiles;
-            const int j1 = r % p.b1, j2 = (r / p.b1) % p.b2, j3 = r / (p.b1 * p.b2);
-            const int g1 = (m_tile % p.t1) * p.b1 + j1;
-            const int g2 = ((m_tile / p.t1) % p.t2) * p.b2 + j2;
-            const int g3 = (m_tile / (p.t1 * p.t2)) * p.b3 + j3;
-            const bool row_ok = (r < p.rows_per_tile) && g1 < p.D1 && g2 < p.D2 && g3 < p.D3;
-            const long long grow = (static_cast<long long>(g3) * p.D2 + g2) * p.D1 + g1;
+            const int o1 = (m_tile % p.t1) * p.b1, o2 = ((m_tile / p.t1) % p.t2) * p.b2;
+            const int o3 = (m_tile / (p.t1 * p.t2)) * p.b3;
             const float* gb = nullptr;
-            if (p.group_bias != nullptr && row_ok)
-                gb = p.group_bias + (grow / p.rows_per_group) * p.ld_group_bias;
-
+            if (p.group_bias != nullptr) {
+                const int g1 = o1 + r % p.b1, g2 = o2 + (r / p.b1) % p.b2, g3 = o3 + r / (p.b1 * p.b2);
+                if (r < p.rows_per_tile && g1 < p.D1 && g2 < p.D2 && g3 < p.D3) {
+                    const long long grow = (static_cast<long long>(g3) * p.D2 + g2) * p.D1 + g1;
+                    gb = p.group_bias + (grow / p.rows_per_group) * p.ld_group_bias;
+                }
+            }
             const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
             mbar_wait(&tfull[a], aph);
             tc_fence_after();
             const uint32_t t_row = tmem_base + a * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-            const int ncols = p.geglu ? BN / 2 : BN;
-            const int out_n0 = n_tile * ncols;
 
-            for (int j0 = 0; j0 < ncols; j0 += kCols) {
-                uint32_t v[kCols], g[kCols];
-                tmem_ld16(t_row + j0, v);
-                if (p.geglu) tmem_ld16(t_row + BN / 2 + j0, g);
+            for (int ci = grp; ci < nch; ci += 2, ++cnt) {
+                const int s = cnt & 1;
+                uint8_t* slot = slots + s * kSlotBytes;
+                if (p.has_residual) {
+                    if (leader) {
+                        // next work item of this group: next chunk of this tile, else first chunk of the next tile
+                        int ntile = tile, nci = ci + 2;
+                        if (nci >= nch) { ntile = tile + gridDim.x; nci = grp; }
+                        if (ntile < num_tiles) {
+                            tma_store_wait_read<0>();            // slot s^1 was last read by the previous store
+                            prefetch_res(ntile, nci, cnt + 1);
+                        }
+                    }
+                    mbar_wait(&my_rfull[s], (cnt >> 1) & 1);
+                } else {
+                    if (leader) tma_store_wait_read<1>();        // the store issued from this slot two chunks ago
+                    named_bar_sync(bar_id, 128);
+                }
+                // ---- accumulator chunk -> registers
+                uint32_t v[32], g[32];
+                tmem_ld32(t_row + ci * kChunkCols, v);
+                if (p.geglu) tmem_ld32(t_row + BN / 2 + ci * kChunkCols, g);
                 tmem_ld_wait();
-                const int col0 = out_n0 + j0;
-                if (row_ok && col0 < p.N_out) {
-                    float o[kCols];
+                float o[32];
+                const int col0 = n_tile * ncols + ci * kChunkCols;      // first output column of this chunk
 #pragma unroll
-                    for (int j = 0; j < kCols; ++j) o[j] = __uint_as_float(v[j]) * p.out_scale;
-                    const bool full_chunk = (col0 + kCols <= p.N_out);
-                    if (p.geglu) {
-                        const int wn = n_tile * BN + j0;   // packed weight column of the value half
+                for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) * p.out_scale;
+                if (p.geglu) {
+                    const int wn = n_tile * BN + ci * kChunkCols;       // packed weight column of the value half
 #pragma unroll
-                        for (int j = 0; j < kCols; ++j) {
-                            float val = o[j], gate = __uint_as_float(g[j]) * p.out_scale;
-                            if (p.bias != nullptr) {
-                                val += p.bias[wn + j];
-                                gate += p.bias[wn + BN / 2 + j];
-                            }
-                            o[j] = val * gelu_erf(gate);
+                    for (int j = 0; j < 32; ++j) {
+                        float val = o[j], gate = __uint_as_float(g[j]) * p.out_scale;
+                        if (p.bias != nullptr) {
+                            val += __ldg(p.bias + wn + j);
+                            gate += __ldg(p.bias + wn + BN / 2 + j);
                         }
-                    } else if (p.bias != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < kCols; ++j)
-                            if (full_chunk || col0 + j < p.N_out) o[j] += p.bias[col0 + j];
+                        o[j] = val * gelu_erf(gate);
                     }
-                    if (gb != nullptr) {
+                } else if (p.bias != nullptr) {
+                    if (col0 + 32 <= p.N_out) {
 #pragma unroll
-                        for (int j = 0; j < kCols; ++j)
-                            if (full_chunk || col0 + j < p.N_out) o[j] += gb[col0 + j];
-                    }
-                    if (p.residual != nullptr) {
-                        const float* rp = p.residual + grow * p.ld_residual + col0;
-                        if (full_chunk && (p.ld_residual & 3) == 0) {
-#pragma unroll
-                            for (int j = 0; j < kCols; j += 4) {
-                                const float4 t = *reinterpret_cast<const float4*>(rp + j);
-                                o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < kCols; ++j)
-                                if (col0 + j < p.N_out) o[j] += rp[j];
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                            o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w;
                         }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N_out) o[j] += __ldg(p.bias + col0 + j);
                     }
-                    if (p.out_f32 != nullptr) {
-                        float* op = p.out_f32 + grow * p.ld_out + col0;
-                        if (full_chunk && (p.ld_out & 3) == 0) {
+                }
+                if (gb != nullptr) {
 #pragma unroll
-                            for (int j = 0; j < kCols; j += 4)
-                                *reinterpret_cast<float4*>(op + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                        } else {
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N_out) o[j] += __ldg(gb + col0 + j);
+                }
+                if (p.has_residual) {
+                    // fp32 residual chunk sits in this slot, 128-byte rows, SWIZZLE_128B
+                    const uint8_t* rrow = slot + r * 128;
 #pragma unroll
-                            for (int j = 0; j < kCols; ++j)
-                                if (col0 + j < p.N_out) op[j] = o[j];
-                        }
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 t = *reinterpret_cast<const float4*>(rrow + ((c ^ (r & 7)) << 4));
+                        o[4 * c] += t.x; o[4 * c + 1] += t.y; o[4 * c + 2] += t.z; o[4 * c + 3] += t.w;
                     }
-                    if (p.out_bf16 != nullptr) {
-                        __nv_bfloat16* op = p.out_bf16 + grow * p.ld_out + col0;
-                        if (full_chunk && (p.ld_out & 7) == 0) {
+                    if (p.out_bf16) named_bar_sync(bar_id, 128);        // bf16 rows overlap other threads' fp32 rows
+                }
+                if (p.out_bf16) {
+                    uint8_t* orow = slot + r * 64;                      // 64-byte rows, SWIZZLE_64B
 #pragma unroll
-                            for (int j = 0; j < kCols; j += 8) {
-                                uint4 pk;
-                                __nv_bfloat162 h0 = __floats2bfloat162_rn(o[j], o[j + 1]);
-                                __nv_bfloat162 h1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]);
-                                __nv_bfloat162 h3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
-                                pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                                pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                                pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                                pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                                *reinterpret_cast<uint4*>(op + j) = pk;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < kCols; ++j)
-                                if (col0 + j < p.N_out) op[j] = __float2bfloat16_rn(o[j]);
-                        }
+                    for (int c = 0; c < 4; ++c) {
+                        uint4 pk;
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * c], o[8 * c + 1]);
+                        __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * c + 2], o[8 * c + 3]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * c + 4], o[8 * c + 5]);
+                        __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * c + 6], o[8 * c + 7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(orow + ((c ^ ((r >> 1) & 3)) << 4)) = pk;
                     }
+                } else {
+                    uint8_t* orow = slot + r * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<float4*>(orow + ((c ^ (r & 7)) << 4)) =
+                            make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                }
+                fence_proxy_async();                                     // generic-proxy writes -> visible to TMA
+                named_bar_sync(bar_id, 128);
+                if (leader) {
+                    tma_store_4d(&tmOut, slot, col0, o1, o2, o3);
+                    tma_store_commit();
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[a]);
         }
+        if (leader) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -272,8 +313,9 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-static int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
-                           const uint64_t* strides_elems, const uint32_t* box) {
+static int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, CUtensorMapSwizzle swz, const void* base,
+                      int rank, const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box,
+                      CUtensorMapL2promotion promo) {
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) return set_error(DCB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t gdim[5], gstr[4];
@@ -282,19 +324,20 @@ static int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const uin
         gdim[i] = dims[i];
         bx[i] = box[i];
         es[i] = 1;
-        if (i > 0) gstr[i - 1] = strides_elems[i] * 2;
+        if (i > 0) gstr[i - 1] = strides_elems[i] * elem_bytes;
     }
-    CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult rc = fn(m, dt, rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                     promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return set_error(DCB_ERR_CUDA, "cuTensorMapEncodeTiled failed (rc=%d)", (int)rc);
     return DCB_OK;
 }
 
 template <int BN>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
+                  TapGemmParams& p, cudaStream_t stream) {
     constexpr int kStageBytes = kABytes + BN * kBlockK * 2;
-    constexpr int smem_bytes = kStages * kStageBytes + 1024 + 256;
+    constexpr int smem_bytes = StageCount<BN>::value * kStageBytes + kEpiBytes + 1024 + 256;
+    static_assert(smem_bytes <= 232448, "shared memory budget");
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -303,9 +346,10 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams&
         configured = true;
     }
     p.stage_bytes = static_cast<uint32_t>(p.rows_per_tile * kBlockK * 2 + BN * kBlockK * 2);
+    p.res_bytes = static_cast<uint32_t>(p.rows_per_tile * kChunkCols * 4);
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    tap_gemm_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+    tap_gemm_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmOut, tmRes, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "tap_gemm launch: %s", cudaGetErrorString(e));
     return DCB_OK;
@@ -317,7 +361,8 @@ using namespace dcb;
 
 extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
     if (a == nullptr || a->a == nullptr || a->w == nullptr) return set_error(DCB_ERR_INVALID, "tap_gemm: null argument");
-    if (a->out_f32 == nullptr && a->out_bf16 == nullptr) return set_error(DCB_ERR_INVALID, "tap_gemm: no output");
+    if ((a->out_f32 == nullptr) == (a->out_bf16 == nullptr))
+        return set_error(DCB_ERR_INVALID, "tap_gemm: exactly one of out_f32 / out_bf16 must be given");
     if (a->C <= 0 || a->C % 8 != 0 || (a->ntaps > 1 && a->C % 64 != 0))
         return set_error(DCB_ERR_INVALID, "tap_gemm: C=%d must be a multiple of 8 (of 64 when ntaps > 1)", a->C);
     const int64_t w_ld = a->w_ld > 0 ? a->w_ld : static_cast<int64_t>(a->ntaps) * a->C;
@@ -334,17 +379,28 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
         return set_error(DCB_ERR_INVALID, "tap_gemm: A/W need 16-byte aligned base and strides");
     if (a->N < 1) return set_error(DCB_ERR_INVALID, "tap_gemm: N");
     int bn = a->block_n;
-    if (bn == 0) bn = (a->N % 160 == 0) ? 160 : 128;
+    if (bn == 0) bn = a->geglu ? 128 : ((a->N % 160 == 0) ? 160 : 128);
     if (bn != 128 && bn != 160) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: block_n must be 128 or 160");
-    if (a->geglu && (a->N % bn != 0)) return set_error(DCB_ERR_INVALID, "tap_gemm: geglu needs N %% block_n == 0");
+    if (a->geglu && (bn != 128 || a->N % 128 != 0))
+        return set_error(DCB_ERR_INVALID, "tap_gemm: geglu needs block_n == 128 and N %% 128 == 0");
     if (a->group_bias != nullptr && a->rows_per_group < 1) return set_error(DCB_ERR_INVALID, "tap_gemm: rows_per_group");
+    const bool obf = a->out_bf16 != nullptr;
+    const void* outp = obf ? a->out_bf16 : static_cast<const void*>(a->out_f32);
+    const int oes = obf ? 2 : 4;
+    if ((reinterpret_cast<uintptr_t>(outp) & 15) || (static_cast<int64_t>(a->ld_out) * oes) % 16 != 0)
+        return set_error(DCB_ERR_INVALID, "tap_gemm: out needs a 16-byte aligned base and row pitch");
+    if (a->residual != nullptr &&
+        ((reinterpret_cast<uintptr_t>(a->residual) & 15) || (static_cast<int64_t>(a->ld_residual) * 4) % 16 != 0))
+        return set_error(DCB_ERR_INVALID, "tap_gemm: residual needs a 16-byte aligned base and row pitch");
+    const int n_out = a->geglu ? a->N / 2 : a->N;
 
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmOut, tmRes;
     {
         const uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->A1, (uint64_t)a->A2, (uint64_t)a->A3};
         const uint64_t str[4] = {1, (uint64_t)a->a_s1, (uint64_t)a->a_s2, (uint64_t)a->a_s3};
         const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)a->b1, (uint32_t)a->b2, (uint32_t)a->b3};
-        int rc = encode_bf16_map(&tmA, a->a, 4, dims, str, box);
+        int rc = encode_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, CU_TENSOR_MAP_SWIZZLE_128B, a->a, 4, dims, str, box,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
     }
     {
@@ -352,7 +408,28 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
         const uint64_t dims[2] = {K, (uint64_t)a->N};
         const uint64_t str[2] = {1, (uint64_t)w_ld};
         const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)bn};
-        int rc = encode_bf16_map(&tmB, a->w, 2, dims, str, box);
+        int rc = encode_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, CU_TENSOR_MAP_SWIZZLE_128B, a->w, 2, dims, str, box,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t ld = (uint64_t)a->ld_out;
+        const uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)a->D1, (uint64_t)a->D2, (uint64_t)a->D3};
+        const uint64_t str[4] = {1, ld, ld * a->D1, ld * a->D1 * a->D2};
+        const uint32_t box[4] = {(uint32_t)kChunkCols, (uint32_t)a->b1, (uint32_t)a->b2, (uint32_t)a->b3};
+        int rc = encode_map(&tmOut, obf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, oes,
+                            obf ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, outp, 4, dims, str, box,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE);
+        if (rc) return rc;
+    }
+    tmRes = tmOut;
+    if (a->residual != nullptr) {
+        const uint64_t ld = (uint64_t)a->ld_residual;
+        const uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)a->D1, (uint64_t)a->D2, (uint64_t)a->D3};
+        const uint64_t str[4] = {1, ld, ld * a->D1, ld * a->D1 * a->D2};
+        const uint32_t box[4] = {(uint32_t)kChunkCols, (uint32_t)a->b1, (uint32_t)a->b2, (uint32_t)a->b3};
+        int rc = encode_map(&tmRes, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_128B, a->residual, 4, dims,
+                            str, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);
         if (rc) return rc;
     }
     TapGemmParams p;
@@ -369,18 +446,15 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
     for (int t = 0; t < DCB_MAX_TAPS; ++t)
         for (int d = 0; d < 3; ++d) p.taps[t][d] = (t < a->ntaps) ? a->taps[t][d] : 0;
     p.N = a->N;
-    p.N_out = a->geglu ? a->N / 2 : a->N;
+    p.N_out = n_out;
     p.bias = a->bias;
     p.group_bias = a->group_bias;
     p.rows_per_group = a->rows_per_group;
     p.ld_group_bias = a->ld_group_bias;
-    p.residual = a->residual;
-    p.ld_residual = a->ld_residual;
+    p.has_residual = a->residual != nullptr ? 1 : 0;
     p.geglu = a->geglu;
-    p.out_f32 = a->out_f32;
-    p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
-    p.ld_out = a->ld_out;
+    p.out_bf16 = obf ? 1 : 0;
     p.out_scale = a->out_scale;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    return bn == 160 ? launch<160>(tmA, tmB, p, s) : launch<128>(tmA, tmB, p, s);
+    return bn == 160 ? launch<160>(tmA, tmB, tmOut, tmRes, p, s) : launch<128>(tmA, tmB, tmOut, tmRes, p, s);
 }

@@ -35,11 +35,10 @@ def pack_tconv3(w):
 
 
 def geglu_block_n(inner):
-    if inner % 80 == 0:
-        return 160
+    """The GEGLU epilogue pairs value/gate columns inside a 128-wide tile (64 values | 64 gates)."""
     if inner % 64 == 0:
         return 128
-    raise ValueError(f"GEGLU inner dim {inner} must be a multiple of 64 or 80")
+    raise ValueError(f"GEGLU inner dim {inner} must be a multiple of 64")
 
 
 def pack_geglu(w, b):

@@ -94,11 +94,15 @@ def _outputs(rows, n_out, out, want_f32, want_bf16, dev):
         else:
             ob = out
         return of, ob, out.stride(0)
+    assert want_f32 != want_bf16, "exactly one output dtype per launch"
+    # the TMA store needs a 16-byte row pitch: pad the leading dimension, hand back a [:, :n_out] view
     if want_f32:
-        of = torch.empty((rows, n_out), dtype=F32, device=dev)
-    if want_bf16:
-        ob = torch.empty((rows, n_out), dtype=BF16, device=dev)
-    return of, ob, n_out
+        ld = (n_out + 3) // 4 * 4
+        of = torch.empty((rows, ld), dtype=F32, device=dev)[:, :n_out]
+    else:
+        ld = (n_out + 7) // 8 * 8
+        ob = torch.empty((rows, ld), dtype=BF16, device=dev)[:, :n_out]
+    return of, ob, ld
 
 
 def linear(a, w, *, bias=None, residual=None, geglu=False, f32=False, bf16=True, out=None, N=None,

@@ -35,6 +35,8 @@ def test_linear_bias_residual(M, K, N):
     _close(out, ref, 1e-4)
     ob = ops.linear(a, w, bias=bias, residual=res, f32=False, bf16=True)
     _close(ob, ref, 1e-2)
+    _close(ops.linear(a, w, f32=True, bf16=False), a.float() @ w.float().t(), 1e-4)
+    _close(ops.linear(a, w, bias=bias), a.float() @ w.float().t() + bias, 1e-2)
 
 
 def test_linear_strided_a_and_small_n():
@@ -47,7 +49,7 @@ def test_linear_strided_a_and_small_n():
     _close(out, ref, 1e-4)
 
 
-@pytest.mark.parametrize("K,inner,bn", [(128, 320, 160), (64, 256, 128)])
+@pytest.mark.parametrize("K,inner,bn", [(128, 320, 128), (64, 256, 128), (320, 1280, 128)])
 def test_geglu(K, inner, bn):
     from dynamicrafter_b200 import ops
     M = 200
