@@ -1,5 +1,5 @@
 // GroupNorm (32 groups) statistics + apply(+SiLU) and LayerNorm for channels-last fp32 activations.
-// HBM-bound: 128-bit loads, warp-shuffle / register accumulation, bf16 operand written once.
+// HBM-bound: 128-bit loads with 4 rows in flight per lane, register accumulation, bf16 operand written once.
 //
 // Replaces ATen native_group_norm / layer_norm at basics.py:76-87 (eps 1e-5, fp32), attention.py:225-227,
 // 265,331 (LN eps 1e-5, GN eps 1e-6), openaimodel3d.py:256-262, ae_modules.py:15-16 (eps 1e-6).
@@ -10,33 +10,53 @@
 namespace dcb {
 
 constexpr int kGroups = 32;
-constexpr int kMaxChunks = 1024;
-constexpr int kMaxSplitChannels = 4096;   // smem slots of the stats kernel: row_split * C <= this
+constexpr int kMaxChunks = 256;
+constexpr int kMaxC = 4096;
+constexpr int kMaxSplitC = 4096;          // row_split * C bound (dynamic smem of the stats kernel = 8 B each)
 
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+struct GnPlan { int row_split, rows_per_chunk, nchunks; };
+
+static int gcd_i(int a, int b) { return b == 0 ? a : gcd_i(b, a % b); }
+
+// One work item = (128-channel block, row split); a block's 8 warps share Qb*row_split items evenly.
+static GnPlan plan_stats(int C1, int C2, int S) {
+    const int Qb = ((C1 >> 2) + 31) / 32 + ((C2 >> 2) + 31) / 32;
+    int s = 8 / gcd_i(Qb, 8);
+    const int cap = kMaxSplitC / (C1 + C2) > 0 ? kMaxSplitC / (C1 + C2) : 1;
+    if (s > cap) s = cap;
+    GnPlan p;
+    p.row_split = s;
+    p.rows_per_chunk = 8 * s;                                   // 8 rows per item: 2 rounds of 4 loads in flight
+    p.nchunks = (S + p.rows_per_chunk - 1) / p.rows_per_chunk;
+    if (p.nchunks > kMaxChunks) {
+        p.rows_per_chunk = (S + kMaxChunks - 1) / kMaxChunks;
+        p.rows_per_chunk = (p.rows_per_chunk + s - 1) / s * s;
+        p.nchunks = (S + p.rows_per_chunk - 1) / p.rows_per_chunk;
+    }
+    return p;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Stats.  Instance n covers S consecutive rows of C = C1 + C2 channels (x2 = channel-concatenated
-// second source or null).  grid = (nchunks, G).  Each block reduces its rows into 32 (sum, sumsq)
-// pairs; the last block of an instance (threadfence + counter) folds the partials in double and
-// writes (mean, rstd).  Deterministic: partials are combined in a fixed order.
+// second source or null).  grid = (nchunks, G).  Per-(row split, channel) partial sums land in smem
+// slots with exactly one writer each and are folded in a fixed order; the last block of an instance
+// (threadfence + counter) folds the per-chunk partials in double and writes (mean, rstd).
+// Bitwise reproducible: no floating-point atomics anywhere.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int S,
-                int rows_per_chunk, float* __restrict__ partial, unsigned* __restrict__ counters,
+                int rows_per_chunk, int row_split, float* __restrict__ partial, unsigned* __restrict__ counters,
                 float* __restrict__ stats, float eps) {
-    // per-(row split, channel) partial sums; every slot has exactly one writer and is folded in a
-    // fixed order -> bitwise reproducible (no floating-point atomics anywhere)
-    __shared__ float s_part[kMaxSplitChannels * 2];
+    extern __shared__ float s_part[];       // [row_split][C][2]
     __shared__ bool s_last;
     const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = C1 + C2, cg = C / kGroups;
     const int r0 = chunk * rows_per_chunk;
     const int r1 = min(S, r0 + rows_per_chunk);
-    const int Q1 = C1 >> 2, Q2 = C2 >> 2;
-    const int Qb1 = (Q1 + 31) >> 5, Qb2 = (Q2 + 31) >> 5, Qb = Qb1 + Qb2;
-    const int row_split = Qb >= 8 ? 1 : 8 / Qb;          // warps sharing one 128-channel block split its rows
+    const int Qb1 = ((C1 >> 2) + 31) >> 5, Qb2 = ((C2 >> 2) + 31) >> 5, Qb = Qb1 + Qb2;
 
     for (int item = warp; item < Qb * row_split; item += 8) {
         const int cb = item / row_split, split = item - cb * row_split;
@@ -46,21 +66,21 @@ gn_stats_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
         const int coff = second ? C1 : 0;
         const int q = (second ? cb - Qb1 : cb) * 32 + lane;
         if (q >= (Cs >> 2)) continue;
-        const float* base = x + (static_cast<size_t>(n) * S) * Cs;
+        const float4* base = reinterpret_cast<const float4*>(x + (static_cast<size_t>(n) * S) * Cs) + q;
+        const size_t rs = static_cast<size_t>(Cs >> 2);       // row stride in float4
         float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-        int r = r0 + split;
-        // two rows in flight per iteration for memory-level parallelism
-        for (; r + row_split < r1; r += 2 * row_split) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * Cs) + q);
-            const float4 b = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(r + row_split) * Cs) + q);
-            s[0] += a.x + b.x; s[1] += a.y + b.y; s[2] += a.z + b.z; s[3] += a.w + b.w;
-            ss[0] += a.x * a.x + b.x * b.x; ss[1] += a.y * a.y + b.y * b.y;
-            ss[2] += a.z * a.z + b.z * b.z; ss[3] += a.w * a.w + b.w * b.w;
-        }
-        for (; r < r1; r += row_split) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * Cs) + q);
-            s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;
-            ss[0] += a.x * a.x; ss[1] += a.y * a.y; ss[2] += a.z * a.z; ss[3] += a.w * a.w;
+        for (int r = r0 + split; r < r1; r += 4 * row_split) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rr = r + u * row_split;
+                v[u] = rr < r1 ? __ldg(base + rr * rs) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
+                ss[0] += v[u].x * v[u].x; ss[1] += v[u].y * v[u].y; ss[2] += v[u].z * v[u].z; ss[3] += v[u].w * v[u].w;
+            }
         }
         float* dst = s_part + (static_cast<size_t>(split) * C + coff + q * 4) * 2;
 #pragma unroll
@@ -68,16 +88,26 @@ gn_stats_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
     }
     __syncthreads();
     float* pbase = partial + (static_cast<size_t>(n) * nchunks + chunk) * (kGroups * 2);
-    if (tid < kGroups) {
+    {
+        // 8 threads per group: fixed strided subset of the (split, channel) slots, then a fixed shuffle tree
+        const int g = tid >> 3, sub = tid & 7;
         float a = 0.f, b = 0.f;
-        for (int sp = 0; sp < row_split; ++sp)
-            for (int c = tid * cg; c < (tid + 1) * cg; ++c) {
-                a += s_part[(static_cast<size_t>(sp) * C + c) * 2];
-                b += s_part[(static_cast<size_t>(sp) * C + c) * 2 + 1];
-            }
-        pbase[tid * 2] = a;
-        pbase[tid * 2 + 1] = b;
-        __threadfence();
+        const int slots = row_split * cg;
+        for (int i = sub; i < slots; i += 8) {
+            const int sp = i / cg, c = g * cg + (i - sp * cg);
+            a += s_part[(static_cast<size_t>(sp) * C + c) * 2];
+            b += s_part[(static_cast<size_t>(sp) * C + c) * 2 + 1];
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (sub == 0) {
+            pbase[g * 2] = a;
+            pbase[g * 2 + 1] = b;
+            __threadfence();
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -87,20 +117,25 @@ gn_stats_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
     __syncthreads();
     if (s_last) {
         __threadfence();
-        // 8 threads per group, each a fixed strided subset of the chunks, then a fixed-order shuffle tree
-        const int g = tid >> 3, sub = tid & 7;
-        double sum = 0.0, sq = 0.0;
-        const volatile float* pp = partial + static_cast<size_t>(n) * nchunks * (kGroups * 2);
-        for (int c = sub; c < nchunks; c += 8) {
-            sum += static_cast<double>(pp[c * kGroups * 2 + g * 2]);
-            sq += static_cast<double>(pp[c * kGroups * 2 + g * 2 + 1]);
-        }
+        // coalesced fold of the [nchunks][64] partials: thread (crow = tid/64, col = tid%64) takes chunks crow, crow+4,
+        // ... with 8 independent loads in flight; the 4 row partials are then added in a fixed order (deterministic).
+        __shared__ double s_fold[4][kGroups * 2];
+        const int col = tid & 63, crow = tid >> 6;
+        const float* pp = partial + static_cast<size_t>(n) * nchunks * (kGroups * 2) + col;
+        double acc = 0.0;
+        for (int c = crow; c < nchunks; c += 32) {
+            float v[8];
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            for (int u = 0; u < 8; ++u) v[u] = (c + 4 * u < nchunks) ? __ldcg(pp + static_cast<size_t>(c + 4 * u) * (kGroups * 2)) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += static_cast<double>(v[u]);
         }
-        if (sub == 0) {
+        s_fold[crow][col] = acc;
+        __syncthreads();
+        if (tid < kGroups) {
+            const int g = tid;
+            const double sum = ((s_fold[0][2 * g] + s_fold[1][2 * g]) + s_fold[2][2 * g]) + s_fold[3][2 * g];
+            const double sq = ((s_fold[0][2 * g + 1] + s_fold[1][2 * g + 1]) + s_fold[2][2 * g + 1]) + s_fold[3][2 * g + 1];
             const double cnt = static_cast<double>(S) * cg;
             const double mean = sum / cnt;
             double var = sq / cnt - mean * mean;
@@ -113,9 +148,9 @@ gn_stats_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Apply: y = (x - mean) * rstd * gamma + beta, optional SiLU, bf16 out [rows, C] (the tensor-core
-// operand of the consumer GEMM/conv).  Optionally also emits bf16(x) (raw copy / channel concat)
-// for the 1x1 skip convolution.  grid = (chunks, G).
+// Apply: y = silu?(x * A[c] + B[c]) with A = rstd*gamma, B = beta - mean*rstd*gamma folded once per
+// block into smem; bf16 out [rows, C] (the tensor-core operand of the consumer GEMM/conv).  Optionally
+// also emits bf16(x) (raw copy / channel concat) for the 1x1 skip convolution.  grid = (chunks, G).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 pack8(const float* v) {
     uint4 p;
@@ -131,17 +166,27 @@ gn_apply_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
                 int rows_per_chunk, const float* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int do_silu, __nv_bfloat16* __restrict__ y,
                 __nv_bfloat16* __restrict__ raw) {
-    __shared__ float s_stat[kGroups * 2];
+    extern __shared__ float s_ab[];          // A[C] | B[C]
     const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
     const int C = C1 + C2, cg = C / kGroups;
-    if (tid < kGroups * 2) s_stat[tid] = stats[static_cast<size_t>(n) * kGroups * 2 + tid];
-    __syncthreads();
+    if (y != nullptr) {
+        for (int c = tid; c < C; c += 256) {
+            const int g = c / cg;
+            const float mean = stats[(static_cast<size_t>(n) * kGroups + g) * 2];
+            const float rstd = stats[(static_cast<size_t>(n) * kGroups + g) * 2 + 1];
+            const float a = rstd * gamma[c];
+            s_ab[c] = a;
+            s_ab[C + c] = beta[c] - mean * a;
+        }
+        __syncthreads();
+    }
     const int r0 = chunk * rows_per_chunk;
     const int r1 = min(S, r0 + rows_per_chunk);
     const int O = C >> 3, O1 = C1 >> 3;
     const int items = (r1 - r0) * O;
+    int rr = tid / O, o = tid - rr * O;
+    const int drr = 256 / O, dO = 256 - drr * O;          // idx += 256 without a division per item
     for (int idx = tid; idx < items; idx += 256) {
-        const int rr = idx / O, o = idx - rr * O;
         const size_t row = static_cast<size_t>(n) * S + r0 + rr;
         const float* src = (o < O1) ? (x1 + row * C1 + o * 8) : (x2 + row * C2 + (o - O1) * 8);
         const float4 a = __ldg(reinterpret_cast<const float4*>(src));
@@ -150,20 +195,20 @@ gn_apply_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
         const int c0 = o * 8;
         if (raw != nullptr) *reinterpret_cast<uint4*>(raw + row * C + c0) = pack8(v);
         if (y != nullptr) {
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
-            const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const float4 A0 = *reinterpret_cast<const float4*>(s_ab + c0), A1 = *reinterpret_cast<const float4*>(s_ab + c0 + 4);
+            const float4 B0 = *reinterpret_cast<const float4*>(s_ab + C + c0), B1 = *reinterpret_cast<const float4*>(s_ab + C + c0 + 4);
+            const float am[8] = {A0.x, A0.y, A0.z, A0.w, A1.x, A1.y, A1.z, A1.w};
+            const float bm[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int g = (c0 + e) / cg;
-                float t = (v[e] - s_stat[2 * g]) * s_stat[2 * g + 1] * gm[e] + bt[e];
-                v[e] = do_silu ? silu(t) : t;
+                const float t = fmaf(v[e], am[e], bm[e]);
+                v[e] = do_silu ? silu_fast(t) : t;
             }
             *reinterpret_cast<uint4*>(y + row * C + c0) = pack8(v);
         }
+        rr += drr;
+        o += dO;
+        if (o >= O) { o -= O; ++rr; }
     }
 }
 
@@ -221,14 +266,15 @@ layer_norm_kernel(const float* __restrict__ x, int rows, int C, const float* __r
     }
 }
 
-static int pick_chunks(int G, int S) {
-    // enough blocks to fill the machine (~4 per SM) without making chunks smaller than 32 rows
-    int want = (8 * num_sms() + G - 1) / G;   // ~8 resident 256-thread blocks per SM keeps enough bytes in flight
-    int maxc = (S + 15) / 16;
-    int c = want < maxc ? want : maxc;
-    if (c > kMaxChunks) c = kMaxChunks;
-    if (c < 1) c = 1;
-    return c;
+static int apply_rows_per_chunk(int G, int S, int C, int* nchunks) {
+    // ~64 KB of fp32 input per block, at least 8 resident blocks' worth of chunks
+    int rpc = (16384 + C - 1) / C;
+    if (rpc < 1) rpc = 1;
+    int nch = (S + rpc - 1) / rpc;
+    if (nch > 65535) { nch = 65535; rpc = (S + nch - 1) / nch; nch = (S + rpc - 1) / rpc; }
+    *nchunks = nch;
+    (void)G;
+    return rpc;
 }
 
 }  // namespace dcb
@@ -244,13 +290,12 @@ extern "C" int dcb_group_norm_stats(const float* x1, const float* x2, int C1, in
     const int C = C1 + C2;
     if (x1 == nullptr || stats == nullptr || workspace == nullptr || counters == nullptr)
         return set_error(DCB_ERR_INVALID, "group_norm_stats: null argument");
-    if (C % kGroups != 0 || (C1 & 3) || (C2 & 3) || G < 1 || S < 1 || (C2 > 0 && x2 == nullptr) || C > kMaxSplitChannels)
+    if (C % kGroups != 0 || (C1 & 3) || (C2 & 3) || G < 1 || S < 1 || (C2 > 0 && x2 == nullptr) || C > kMaxC)
         return set_error(DCB_ERR_INVALID, "group_norm_stats: C1=%d C2=%d G=%d S=%d", C1, C2, G, S);
-    const int nchunks = pick_chunks(G, S);
-    const int rpc = (S + nchunks - 1) / nchunks;
-    const int nch = (S + rpc - 1) / rpc;
-    gn_stats_kernel<<<dim3(nch, G), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x1, x2, C1, C2, S, rpc, static_cast<float*>(workspace), counters, stats, eps);
+    const GnPlan pl = plan_stats(C1, C2, S);
+    const size_t smem = static_cast<size_t>(pl.row_split) * C * 2 * sizeof(float);
+    gn_stats_kernel<<<dim3(pl.nchunks, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        x1, x2, C1, C2, S, pl.rows_per_chunk, pl.row_split, static_cast<float*>(workspace), counters, stats, eps);
     return check_launch("group_norm_stats");
 }
 
@@ -262,12 +307,13 @@ extern "C" int dcb_group_norm_apply(const float* x1, const float* x2, int C1, in
         return set_error(DCB_ERR_INVALID, "group_norm_apply: null argument");
     if (y_bf16 != nullptr && (stats == nullptr || gamma == nullptr || beta == nullptr))
         return set_error(DCB_ERR_INVALID, "group_norm_apply: stats/gamma/beta required");
-    if ((y_bf16 != nullptr && C % kGroups != 0) || (C1 & 7) || (C2 & 7) || G < 1 || S < 1 || (C2 > 0 && x2 == nullptr))
+    if ((y_bf16 != nullptr && C % kGroups != 0) || (C1 & 7) || (C2 & 7) || G < 1 || S < 1 || (C2 > 0 && x2 == nullptr) ||
+        C > kMaxC)
         return set_error(DCB_ERR_INVALID, "group_norm_apply: C1=%d C2=%d G=%d S=%d", C1, C2, G, S);
-    const int nchunks = pick_chunks(G, S);
-    const int rpc = (S + nchunks - 1) / nchunks;
-    const int nch = (S + rpc - 1) / rpc;
-    gn_apply_kernel<<<dim3(nch, G), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    int nch = 1;
+    const int rpc = apply_rows_per_chunk(G, S, C, &nch);
+    const size_t smem = static_cast<size_t>(C) * 2 * sizeof(float);
+    gn_apply_kernel<<<dim3(nch, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         x1, x2, C1, C2, S, rpc, stats, gamma, beta, silu_act, static_cast<__nv_bfloat16*>(y_bf16),
         static_cast<__nv_bfloat16*>(raw_bf16));
     return check_launch("group_norm_apply");

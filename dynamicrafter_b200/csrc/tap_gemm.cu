@@ -25,11 +25,11 @@ constexpr int kBlockK = 64;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kABytes = kBlockM * kBlockK * 2;
-constexpr int kChunkCols = 32;                       // epilogue chunk: 32 output columns
-constexpr int kSlotBytes = kBlockM * kChunkCols * 4;  // fp32 chunk (bf16 chunks use the first half)
+// epilogue chunk = 64-byte rows (SWIZZLE_64B): 16 fp32 or 32 bf16 output columns x 128 rows = 8 KB per slot
+constexpr int kSlotBytes = kBlockM * 64;
 constexpr int kEpiBytes = 2 * 2 * kSlotBytes;         // 2 groups x 2 slots
 
-template <int BN> struct StageCount { static constexpr int value = (BN <= 128) ? 5 : 4; };
+template <int BN> struct StageCount { static constexpr int value = (BN <= 128) ? 6 : (BN <= 160 ? 5 : 4); };
 
 struct TapGemmParams {
     int D1, D2, D3, b1, b2, b3, t1, t2, t3;
@@ -41,13 +41,32 @@ struct TapGemmParams {
     const float* group_bias;
     int rows_per_group, ld_group_bias;
     int has_residual, geglu, out_bf16;
+    const float* residual;
+    int ld_residual;
     float out_scale;
     uint32_t stage_bytes, res_bytes;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact (erf-based) GELU, attention.py:422.  erfc(z) via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, i.e.
+// fp32 round-off level): branch-free, ~16 instructions instead of libm erff's two divergent paths.  The epilogue
+// of the K=320 GEGLU GEMMs is issue-bound on this function, not on the tensor cores.
+//   x >= 0: gelu = x - 0.5 x erfc(x/sqrt2)      x < 0: gelu = 0.5 x erfc(|x|/sqrt2)   (no cancellation)
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));      // MUFU.RCP
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));   // MUFU.EX2
+    e *= poly;                                                                               // erfc(z)
+    const float h = 0.5f * x * e;
+    return x >= 0.f ? x - h : h;
+}
 
-template <int BN>
+template <int BN, bool kF32>
 __global__ void __launch_bounds__(kThreads, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -148,6 +167,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
     } else {
         // ------------------------------------------------------------ epilogue: 2 groups x 4 warps
+        constexpr int CW = kF32 ? 16 : 32;         // output columns per chunk (64-byte smem rows)
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
         const int grp = (warp - 2) >> 2;           // chunk parity handled by this group
         const int r = q * 32 + lane;               // tile row owned by this thread
@@ -156,8 +176,12 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint8_t* slots = epi + grp * 2 * kSlotBytes;
         uint64_t* my_rfull = rfull + grp * 2;
         const int ncols = p.geglu ? BN / 2 : BN;   // output columns per tile
-        const int nch = ncols / kChunkCols;
+        const int nch = ncols / CW;
         const int my_nch = (nch - grp + 1) / 2;    // chunks grp, grp+2, ...
+        const bool tma_res = kF32 && p.has_residual;          // fp32 out: residual chunk prefetched in place by TMA
+        const int swz = (r >> 1) & 3;              // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
+        uint8_t* const row_base = nullptr;
+        (void)row_base;
         uint32_t tc = 0, cnt = 0;
 
         // leader only: TMA-prefetch the residual chunk of work item (tile, ci) into slot (cnt & 1)
@@ -166,10 +190,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int n_tile = tile - m_tile * p.num_n_tiles;
             const int s = cnt_item & 1;
             mbar_arrive_expect_tx(&my_rfull[s], p.res_bytes);
-            tma_load_4d(slots + s * kSlotBytes, &tmRes, &my_rfull[s], n_tile * ncols + ci * kChunkCols,
+            tma_load_4d(slots + s * kSlotBytes, &tmRes, &my_rfull[s], n_tile * ncols + ci * CW,
                         (m_tile % p.t1) * p.b1, ((m_tile / p.t1) % p.t2) * p.b2, (m_tile / (p.t1 * p.t2)) * p.b3);
         };
-        if (p.has_residual && leader && my_nch > 0 && static_cast<int>(blockIdx.x) < num_tiles)
+        if (tma_res && leader && my_nch > 0 && static_cast<int>(blockIdx.x) < num_tiles)
             prefetch_res(blockIdx.x, grp, 0);
 
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
@@ -178,22 +202,47 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int o1 = (m_tile % p.t1) * p.b1, o2 = ((m_tile / p.t1) % p.t2) * p.b2;
             const int o3 = (m_tile / (p.t1 * p.t2)) * p.b3;
             const float* gb = nullptr;
-            if (p.group_bias != nullptr) {
+            const float* res_row = nullptr;        // bf16-out path: residual row read straight from global
+            if (p.group_bias != nullptr || (!kF32 && p.has_residual)) {
                 const int g1 = o1 + r % p.b1, g2 = o2 + (r / p.b1) % p.b2, g3 = o3 + r / (p.b1 * p.b2);
                 if (r < p.rows_per_tile && g1 < p.D1 && g2 < p.D2 && g3 < p.D3) {
                     const long long grow = (static_cast<long long>(g3) * p.D2 + g2) * p.D1 + g1;
-                    gb = p.group_bias + (grow / p.rows_per_group) * p.ld_group_bias;
+                    if (p.group_bias != nullptr) gb = p.group_bias + (grow / p.rows_per_group) * p.ld_group_bias;
+                    if (!kF32 && p.has_residual) res_row = p.residual + grow * p.ld_residual;
                 }
             }
             const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
-            mbar_wait(&tfull[a], aph);
-            tc_fence_after();
+            bool acc_ready = false;
             const uint32_t t_row = tmem_base + a * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 
             for (int ci = grp; ci < nch; ci += 2, ++cnt) {
                 const int s = cnt & 1;
                 uint8_t* slot = slots + s * kSlotBytes;
-                if (p.has_residual) {
+                const int col0 = n_tile * ncols + ci * CW;              // first output column of this chunk
+                float o[CW];
+                if (!kF32 && p.has_residual) {
+                    // issue the residual loads before waiting for the accumulator (fp32 rows, 128 B per chunk)
+                    if (res_row != nullptr && col0 + CW <= p.N_out) {
+#pragma unroll
+                        for (int j = 0; j < CW; j += 4) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(res_row + col0 + j));
+                            o[j] = t.x; o[j + 1] = t.y; o[j + 2] = t.z; o[j + 3] = t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CW; ++j)
+                            o[j] = (res_row != nullptr && col0 + j < p.N_out) ? __ldg(res_row + col0 + j) : 0.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) o[j] = 0.f;
+                }
+                if (!acc_ready) {
+                    mbar_wait(&tfull[a], aph);
+                    tc_fence_after();
+                    acc_ready = true;
+                }
+                if (tma_res) {
                     if (leader) {
                         // next work item of this group: next chunk of this tile, else first chunk of the next tile
                         int ntile = tile, nci = ci + 2;
@@ -209,55 +258,79 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     named_bar_sync(bar_id, 128);
                 }
                 // ---- accumulator chunk -> registers
-                uint32_t v[32], g[32];
-                tmem_ld32(t_row + ci * kChunkCols, v);
-                if (p.geglu) tmem_ld32(t_row + BN / 2 + ci * kChunkCols, g);
-                tmem_ld_wait();
-                float o[32];
-                const int col0 = n_tile * ncols + ci * kChunkCols;      // first output column of this chunk
+                uint32_t v[CW];
+                if constexpr (kF32) tmem_ld16(t_row + ci * CW, v); else tmem_ld32(t_row + ci * CW, v);
+                if constexpr (!kF32) {
+                    if (p.geglu) {
+                        uint32_t g[CW];
+                        tmem_ld32(t_row + BN / 2 + ci * CW, g);
+                        tmem_ld_wait();
+                        const int wn = n_tile * BN + ci * CW;           // packed weight column of the value half
 #pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) * p.out_scale;
-                if (p.geglu) {
-                    const int wn = n_tile * BN + ci * kChunkCols;       // packed weight column of the value half
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float val = o[j], gate = __uint_as_float(g[j]) * p.out_scale;
-                        if (p.bias != nullptr) {
-                            val += __ldg(p.bias + wn + j);
-                            gate += __ldg(p.bias + wn + BN / 2 + j);
+                        for (int j = 0; j < CW; j += 4) {
+                            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
+                            if (p.bias != nullptr) {
+                                bv = __ldg(reinterpret_cast<const float4*>(p.bias + wn + j));
+                                bg = __ldg(reinterpret_cast<const float4*>(p.bias + wn + BN / 2 + j));
+                            }
+                            const float s_ = p.out_scale;
+                            o[j] += (__uint_as_float(v[j]) * s_ + bv.x) * gelu_erf(__uint_as_float(g[j]) * s_ + bg.x);
+                            o[j + 1] += (__uint_as_float(v[j + 1]) * s_ + bv.y) * gelu_erf(__uint_as_float(g[j + 1]) * s_ + bg.y);
+                            o[j + 2] += (__uint_as_float(v[j + 2]) * s_ + bv.z) * gelu_erf(__uint_as_float(g[j + 2]) * s_ + bg.z);
+                            o[j + 3] += (__uint_as_float(v[j + 3]) * s_ + bv.w) * gelu_erf(__uint_as_float(g[j + 3]) * s_ + bg.w);
                         }
-                        o[j] = val * gelu_erf(gate);
                     }
-                } else if (p.bias != nullptr) {
-                    if (col0 + 32 <= p.N_out) {
+                }
+                if (!p.geglu) {
+                    tmem_ld_wait();
+                    if (p.out_scale != 1.0f) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                        for (int j = 0; j < CW; ++j) o[j] = fmaf(__uint_as_float(v[j]), p.out_scale, o[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) o[j] += __uint_as_float(v[j]);
+                    }
+                    if (p.bias != nullptr) {
+                        if (col0 + CW <= p.N_out) {
+#pragma unroll
+                            for (int j = 0; j < CW; j += 4) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                                o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CW; ++j)
+                                if (col0 + j < p.N_out) o[j] += __ldg(p.bias + col0 + j);
+                        }
+                    }
+                }
+                if (gb != nullptr) {
+                    if (col0 + CW <= p.N_out && (reinterpret_cast<uintptr_t>(gb + col0) & 15) == 0) {
+#pragma unroll
+                        for (int j = 0; j < CW; j += 4) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(gb + col0 + j));
                             o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w;
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.N_out) o[j] += __ldg(p.bias + col0 + j);
+                        for (int j = 0; j < CW; ++j)
+                            if (col0 + j < p.N_out) o[j] += __ldg(gb + col0 + j);
                     }
                 }
-                if (gb != nullptr) {
+                uint8_t* orow = slot + r * 64;                          // 64-byte rows, SWIZZLE_64B
+                if constexpr (kF32) {
+                    if (tma_res) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < p.N_out) o[j] += __ldg(gb + col0 + j);
-                }
-                if (p.has_residual) {
-                    // fp32 residual chunk sits in this slot, 128-byte rows, SWIZZLE_128B
-                    const uint8_t* rrow = slot + r * 128;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float4 t = *reinterpret_cast<const float4*>(rrow + ((c ^ (r & 7)) << 4));
-                        o[4 * c] += t.x; o[4 * c + 1] += t.y; o[4 * c + 2] += t.z; o[4 * c + 3] += t.w;
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 t = *reinterpret_cast<const float4*>(orow + ((c ^ swz) << 4));
+                            o[4 * c] += t.x; o[4 * c + 1] += t.y; o[4 * c + 2] += t.z; o[4 * c + 3] += t.w;
+                        }
                     }
-                    if (p.out_bf16) named_bar_sync(bar_id, 128);        // bf16 rows overlap other threads' fp32 rows
-                }
-                if (p.out_bf16) {
-                    uint8_t* orow = slot + r * 64;                      // 64-byte rows, SWIZZLE_64B
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<float4*>(orow + ((c ^ swz) << 4)) =
+                            make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                } else {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         uint4 pk;
@@ -267,14 +340,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * c + 6], o[8 * c + 7]);
                         pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
                         pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                        *reinterpret_cast<uint4*>(orow + ((c ^ ((r >> 1) & 3)) << 4)) = pk;
+                        *reinterpret_cast<uint4*>(orow + ((c ^ swz) << 4)) = pk;
                     }
-                } else {
-                    uint8_t* orow = slot + r * 128;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        *reinterpret_cast<float4*>(orow + ((c ^ (r & 7)) << 4)) =
-                            make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
                 }
                 fence_proxy_async();                                     // generic-proxy writes -> visible to TMA
                 named_bar_sync(bar_id, 128);
@@ -282,6 +349,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tma_store_4d(&tmOut, slot, col0, o1, o2, o3);
                     tma_store_commit();
                 }
+            }
+            if (!acc_ready) {                                            // group without chunks still tracks the ring
+                mbar_wait(&tfull[a], aph);
+                tc_fence_after();
             }
             tc_fence_before();
             __syncwarp();
@@ -332,7 +403,7 @@ static int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, CU
     return DCB_OK;
 }
 
-template <int BN>
+template <int BN, bool kF32>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
                   TapGemmParams& p, cudaStream_t stream) {
     constexpr int kStageBytes = kABytes + BN * kBlockK * 2;
@@ -340,16 +411,16 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     static_assert(smem_bytes <= 232448, "shared memory budget");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BN, kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              smem_bytes);
         if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     p.stage_bytes = static_cast<uint32_t>(p.rows_per_tile * kBlockK * 2 + BN * kBlockK * 2);
-    p.res_bytes = static_cast<uint32_t>(p.rows_per_tile * kChunkCols * 4);
+    p.res_bytes = static_cast<uint32_t>(p.rows_per_tile * 64);
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    tap_gemm_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmOut, tmRes, p);
+    tap_gemm_kernel<BN, kF32><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmOut, tmRes, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "tap_gemm launch: %s", cudaGetErrorString(e));
     return DCB_OK;
@@ -379,8 +450,15 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
         return set_error(DCB_ERR_INVALID, "tap_gemm: A/W need 16-byte aligned base and strides");
     if (a->N < 1) return set_error(DCB_ERR_INVALID, "tap_gemm: N");
     int bn = a->block_n;
-    if (bn == 0) bn = a->geglu ? 128 : ((a->N % 160 == 0) ? 160 : 128);
-    if (bn != 128 && bn != 160) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: block_n must be 128 or 160");
+    if (bn == 0) {
+        // wider N tiles cut shared-memory bytes per MMA (the 1-CTA limiter) but need enough tiles to fill the SMs
+        const long long m_tiles = static_cast<long long>((a->D1 + a->b1 - 1) / a->b1) * ((a->D2 + a->b2 - 1) / a->b2) *
+                                  ((a->D3 + a->b3 - 1) / a->b3);
+        if (a->geglu) bn = 128;
+        else if (a->N % 256 == 0 && m_tiles * (a->N / 256) >= 2LL * num_sms()) bn = 256;
+        else bn = (a->N % 160 == 0) ? 160 : 128;
+    }
+    if (bn != 128 && bn != 160 && bn != 256) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: block_n must be 128, 160 or 256");
     if (a->geglu && (bn != 128 || a->N % 128 != 0))
         return set_error(DCB_ERR_INVALID, "tap_gemm: geglu needs block_n == 128 and N %% 128 == 0");
     if (a->group_bias != nullptr && a->rows_per_group < 1) return set_error(DCB_ERR_INVALID, "tap_gemm: rows_per_group");
@@ -416,19 +494,19 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
         const uint64_t ld = (uint64_t)a->ld_out;
         const uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)a->D1, (uint64_t)a->D2, (uint64_t)a->D3};
         const uint64_t str[4] = {1, ld, ld * a->D1, ld * a->D1 * a->D2};
-        const uint32_t box[4] = {(uint32_t)kChunkCols, (uint32_t)a->b1, (uint32_t)a->b2, (uint32_t)a->b3};
+        const uint32_t box[4] = {(uint32_t)(obf ? 32 : 16), (uint32_t)a->b1, (uint32_t)a->b2, (uint32_t)a->b3};
         int rc = encode_map(&tmOut, obf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, oes,
-                            obf ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, outp, 4, dims, str, box,
+                            CU_TENSOR_MAP_SWIZZLE_64B, outp, 4, dims, str, box,
                             CU_TENSOR_MAP_L2_PROMOTION_NONE);
         if (rc) return rc;
     }
     tmRes = tmOut;
-    if (a->residual != nullptr) {
+    if (a->residual != nullptr && !obf) {
         const uint64_t ld = (uint64_t)a->ld_residual;
         const uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)a->D1, (uint64_t)a->D2, (uint64_t)a->D3};
         const uint64_t str[4] = {1, ld, ld * a->D1, ld * a->D1 * a->D2};
-        const uint32_t box[4] = {(uint32_t)kChunkCols, (uint32_t)a->b1, (uint32_t)a->b2, (uint32_t)a->b3};
-        int rc = encode_map(&tmRes, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_128B, a->residual, 4, dims,
+        const uint32_t box[4] = {16u, (uint32_t)a->b1, (uint32_t)a->b2, (uint32_t)a->b3};
+        int rc = encode_map(&tmRes, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_64B, a->residual, 4, dims,
                             str, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);
         if (rc) return rc;
     }
@@ -452,9 +530,17 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
     p.rows_per_group = a->rows_per_group;
     p.ld_group_bias = a->ld_group_bias;
     p.has_residual = a->residual != nullptr ? 1 : 0;
+    p.residual = a->residual;
+    p.ld_residual = a->ld_residual;
     p.geglu = a->geglu;
     p.out_bf16 = obf ? 1 : 0;
     p.out_scale = a->out_scale;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    return bn == 160 ? launch<160>(tmA, tmB, tmOut, tmRes, p, s) : launch<128>(tmA, tmB, tmOut, tmRes, p, s);
+    if (a->geglu && !obf) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: geglu writes bf16 only");
+    if (obf) {
+        if (bn == 256) return launch<256, false>(tmA, tmB, tmOut, tmRes, p, s);
+        return bn == 160 ? launch<160, false>(tmA, tmB, tmOut, tmRes, p, s) : launch<128, false>(tmA, tmB, tmOut, tmRes, p, s);
+    }
+    if (bn == 256) return launch<256, true>(tmA, tmB, tmOut, tmRes, p, s);
+    return bn == 160 ? launch<160, true>(tmA, tmB, tmOut, tmRes, p, s) : launch<128, true>(tmA, tmB, tmOut, tmRes, p, s);
 }

@@ -23,7 +23,8 @@ def _no_tf32():
     torch.backends.cudnn.allow_tf32 = False
 
 
-@pytest.mark.parametrize("M,K,N", [(300, 320, 320), (128, 64, 128), (1000, 1280, 512), (77, 1024, 640), (4096, 320, 960)])
+@pytest.mark.parametrize("M,K,N", [(300, 320, 320), (128, 64, 128), (1000, 1280, 512), (77, 1024, 640), (4096, 320, 960),
+                                   (40000, 128, 1280), (20480, 640, 512)])
 def test_linear_bias_residual(M, K, N):
     from dynamicrafter_b200 import ops
     a, w = _mk((M, K), 1), _mk((N, K), 2, K ** -0.5)
@@ -60,8 +61,8 @@ def test_geglu(K, inner, bn):
     half = bn // 2
     idx = torch.cat([torch.cat([torch.arange(j * half, (j + 1) * half), inner + torch.arange(j * half, (j + 1) * half)])
                      for j in range(inner // half)]).cuda()
-    out = ops.linear(a, w[idx].contiguous(), bias=bias[idx].contiguous(), geglu=True, f32=True, bf16=False, block_n=bn)
-    _close(out, ref, 1e-4)
+    out = ops.linear(a, w[idx].contiguous(), bias=bias[idx].contiguous(), geglu=True, block_n=bn)
+    _close(out, ref, 1e-2)
 
 
 @pytest.mark.parametrize("nf,H,W,C,N", [(3, 10, 16, 64, 128), (2, 5, 8, 128, 320), (1, 40, 64, 64, 160), (4, 3, 2, 64, 64)])
