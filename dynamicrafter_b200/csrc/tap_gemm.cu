@@ -15,6 +15,8 @@
 //               the same slot (in place), so the epilogue issues no per-thread global loads or stores and
 //               all HBM traffic of the kernel is asynchronous and fully coalesced.  Out-of-range rows and
 //               columns (ragged tiles, N < 32) are clipped by the TMA unit.
+#include <cstdlib>
+
 #include "dcb_internal.h"
 #include "ptx.cuh"
 
@@ -29,7 +31,12 @@ constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kSlotBytes = kBlockM * 64;
 constexpr int kEpiBytes = 2 * 2 * kSlotBytes;         // 2 groups x 2 slots
 
-template <int BN> struct StageCount { static constexpr int value = (BN <= 128) ? 6 : (BN <= 160 ? 5 : 4); };
+// smem ring depth: {A 16 KB + B rows x 128 B} per stage, 32 KB of epilogue slots, <= 227 KB in total.
+// In CTA-pair mode (k2) each CTA stages only half of the B tile.
+template <int BN, bool k2> struct StageCount {
+    static constexpr int stage_bytes = kABytes + (k2 ? BN / 2 : BN) * kBlockK * 2;
+    static constexpr int value = (232448 - kEpiBytes - 1024 - 256) / stage_bytes > 8 ? 8 : (232448 - kEpiBytes - 1024 - 256) / stage_bytes;
+};
 
 struct TapGemmParams {
     int D1, D2, D3, b1, b2, b3, t1, t2, t3;
@@ -66,17 +73,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return x >= 0.f ? x - h : h;
 }
 
-template <int BN, bool kF32>
+template <int BN, bool kF32, bool k2>
 __global__ void __launch_bounds__(kThreads, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                 const TapGemmParams p) {
-    constexpr int kStages = StageCount<BN>::value;
-    constexpr int kBBytes = BN * kBlockK * 2;
+    constexpr int kStages = StageCount<BN, k2>::value;
+    constexpr int kBRows = k2 ? BN / 2 : BN;               // B rows staged by this CTA
+    constexpr int kBBytes = kBRows * kBlockK * 2;
     constexpr int kStageBytes = kABytes + kBBytes;
     constexpr int kAccStride = (BN <= 128) ? 128 : 256;
     constexpr int kTmemCols = 2 * kAccStride;
-    constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BN);
+    constexpr uint32_t kIdesc = make_idesc_bf16(k2 ? 2 * kBlockM : kBlockM, BN);
+    // CTA pair: rank 0 (leader) issues tcgen05.mma.cta_group::2 for the 256 x BN tile; each CTA owns 128 of its rows
+    const uint32_t rank = k2 ? cluster_ctarank() : 0u;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -91,8 +101,12 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    // work item = (m tile [pair], n tile); workers = CTAs (or CTA pairs) striding over the items
+    const int num_tiles = (k2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
+    const int worker = k2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int nworkers = k2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     const int kblocks = p.ntaps * p.kchunks;
+    auto m_tile_of = [&](int tile) { const int mt = tile / p.num_n_tiles; return k2 ? 2 * mt + static_cast<int>(rank) : mt; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -100,50 +114,62 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tma_prefetch_desc(&tmOut);
         if (p.has_residual) tma_prefetch_desc(&tmRes);
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], k2 ? 2 : 1);              // pair: both producers arrive on the leader's barrier
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], kEpiWarps);
+            mbar_init(&tempty[a], k2 ? 2 * kEpiWarps : kEpiWarps);
         }
         for (int i = 0; i < 4; ++i) mbar_init(&rfull[i], 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    if (warp == 1) {
+        if constexpr (k2) tmem_alloc_pair<kTmemCols>(tmem_slot); else tmem_alloc<kTmemCols>(tmem_slot);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (k2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.num_n_tiles;
-                const int n_tile = tile - m_tile * p.num_n_tiles;
-                const int i1 = (m_tile % p.t1) * p.b1;
-                const int i2 = ((m_tile / p.t1) % p.t2) * p.b2;
-                const int i3 = (m_tile / (p.t1 * p.t2)) * p.b3;
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    const int c1 = i1 + p.taps[tap][0], c2 = i2 + p.taps[tap][1], c3 = i3 + p.taps[tap][2];
-                    for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                        mbar_wait(&empty[s], ph ^ 1);
-                        mbar_arrive_expect_tx(&full[s], p.stage_bytes);
+        // ------------------------------------------------------------ TMA producer (whole warp runs the loop with
+        // warp-uniform state; one elected lane issues, so operands stay in uniform registers)
+        uint32_t it = 0;
+        for (int tile = worker; tile < num_tiles; tile += nworkers) {
+            const int m_tile = m_tile_of(tile);
+            const int n_tile = tile % p.num_n_tiles;
+            const int i1 = (m_tile % p.t1) * p.b1;
+            const int i2 = ((m_tile / p.t1) % p.t2) * p.b2;
+            const int i3 = (m_tile / (p.t1 * p.t2)) * p.b3;
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+                const int c1 = i1 + p.taps[tap][0], c2 = i2 + p.taps[tap][1], c3 = i3 + p.taps[tap][2];
+                for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (elect_one()) {
                         uint8_t* sa = smem + s * kStageBytes;
-                        tma_load_4d(sa, &tmA, &full[s], kc * kBlockK, c1, c2, c3);
-                        tma_load_2d(sa + kABytes, &tmB, &full[s], (tap * p.kchunks + kc) * kBlockK, n_tile * BN);
+                        if constexpr (k2) {
+                            const uint32_t lfull = mapa_cluster(smem_u32(&full[s]), 0);      // leader's barrier
+                            mbar_arrive_expect_tx_cluster(lfull, p.stage_bytes);
+                            tma_load_4d_pair(sa, &tmA, lfull, kc * kBlockK, c1, c2, c3);
+                            tma_load_2d_pair(sa + kABytes, &tmB, lfull, (tap * p.kchunks + kc) * kBlockK,
+                                             n_tile * BN + static_cast<int>(rank) * kBRows);
+                        } else {
+                            mbar_arrive_expect_tx(&full[s], p.stage_bytes);
+                            tma_load_4d(sa, &tmA, &full[s], kc * kBlockK, c1, c2, c3);
+                            tma_load_2d(sa + kABytes, &tmB, &full[s], (tap * p.kchunks + kc) * kBlockK, n_tile * BN);
+                        }
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA; one elected lane issues)
+        if (rank == 0) {
             uint32_t it = 0, tc = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
+            for (int tile = worker; tile < num_tiles; tile += nworkers, ++tc) {
                 const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
                 mbar_wait(&tempty[a], aph ^ 1);
                 tc_fence_after();
@@ -152,17 +178,25 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + s * kStageBytes);
-                    const uint64_t adesc = make_sw128_kmajor_desc(sa);
-                    const uint64_t bdesc = make_sw128_kmajor_desc(sa + kABytes);
+                    if (elect_one()) {
+                        const uint32_t sa = smem_u32(smem + s * kStageBytes);
+                        const uint64_t adesc = make_sw128_kmajor_desc(sa);
+                        const uint64_t bdesc = make_sw128_kmajor_desc(sa + kABytes);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
-                        umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
+                            if constexpr (k2) umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+                            else umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+                        }
+                        // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+                        if constexpr (k2) umma_commit_pair(&empty[s]); else umma_commit(&empty[s]);
+                        // accumulator complete -> epilogue (of both CTAs)
+                        if (kb == kblocks - 1) {
+                            if constexpr (k2) umma_commit_pair(&tfull[a]); else umma_commit(&tfull[a]);
+                        }
                     }
-                    umma_commit(&empty[s]);       // frees the smem stage when these MMAs retire
+                    __syncwarp();
                 }
-                umma_commit(&tfull[a]);           // accumulator complete -> epilogue
             }
         }
     } else {
@@ -186,19 +220,20 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
         // leader only: TMA-prefetch the residual chunk of work item (tile, ci) into slot (cnt & 1)
         auto prefetch_res = [&](int tile, int ci, uint32_t cnt_item) {
-            const int m_tile = tile / p.num_n_tiles;
-            const int n_tile = tile - m_tile * p.num_n_tiles;
+            const int m_tile = m_tile_of(tile);
+            const int n_tile = tile % p.num_n_tiles;
             const int s = cnt_item & 1;
             mbar_arrive_expect_tx(&my_rfull[s], p.res_bytes);
             tma_load_4d(slots + s * kSlotBytes, &tmRes, &my_rfull[s], n_tile * ncols + ci * CW,
                         (m_tile % p.t1) * p.b1, ((m_tile / p.t1) % p.t2) * p.b2, (m_tile / (p.t1 * p.t2)) * p.b3);
         };
-        if (tma_res && leader && my_nch > 0 && static_cast<int>(blockIdx.x) < num_tiles)
-            prefetch_res(blockIdx.x, grp, 0);
+        if (tma_res && leader && my_nch > 0 && worker < num_tiles)
+            prefetch_res(worker, grp, 0);
+        const uint32_t tempty_addr0 = k2 ? mapa_cluster(smem_u32(&tempty[0]), 0) : 0u;   // leader's ring barriers
 
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
-            const int m_tile = tile / p.num_n_tiles;
-            const int n_tile = tile - m_tile * p.num_n_tiles;
+        for (int tile = worker; tile < num_tiles; tile += nworkers, ++tc) {
+            const int m_tile = m_tile_of(tile);
+            const int n_tile = tile % p.num_n_tiles;
             const int o1 = (m_tile % p.t1) * p.b1, o2 = ((m_tile / p.t1) % p.t2) * p.b2;
             const int o3 = (m_tile / (p.t1 * p.t2)) * p.b3;
             const float* gb = nullptr;
@@ -246,7 +281,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (leader) {
                         // next work item of this group: next chunk of this tile, else first chunk of the next tile
                         int ntile = tile, nci = ci + 2;
-                        if (nci >= nch) { ntile = tile + gridDim.x; nci = grp; }
+                        if (nci >= nch) { ntile = tile + nworkers; nci = grp; }
                         if (ntile < num_tiles) {
                             tma_store_wait_read<0>();            // slot s^1 was last read by the previous store
                             prefetch_res(ntile, nci, cnt + 1);
@@ -356,14 +391,18 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[a]);
+            if (lane == 0) {
+                if constexpr (k2) mbar_arrive_cluster(tempty_addr0 + a * 8); else mbar_arrive(&tempty[a]);
+            }
         }
         if (leader) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+    if constexpr (k2) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) {
+        if constexpr (k2) tmem_dealloc_pair<kTmemCols>(tmem_base); else tmem_dealloc<kTmemCols>(tmem_base);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -403,27 +442,60 @@ static int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, CU
     return DCB_OK;
 }
 
-template <int BN, bool kF32>
+template <int BN, bool kF32, bool k2>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
                   TapGemmParams& p, cudaStream_t stream) {
-    constexpr int kStageBytes = kABytes + BN * kBlockK * 2;
-    constexpr int smem_bytes = StageCount<BN>::value * kStageBytes + kEpiBytes + 1024 + 256;
+    constexpr int kBRows = k2 ? BN / 2 : BN;
+    constexpr int kStageBytes = kABytes + kBRows * kBlockK * 2;
+    constexpr int smem_bytes = StageCount<BN, k2>::value * kStageBytes + kEpiBytes + 1024 + 256;
     static_assert(smem_bytes <= 232448, "shared memory budget");
+    static_assert(StageCount<BN, k2>::value >= 4, "pipeline depth");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BN, kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BN, kF32, k2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              smem_bytes);
         if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
-    p.stage_bytes = static_cast<uint32_t>(p.rows_per_tile * kBlockK * 2 + BN * kBlockK * 2);
+    p.stage_bytes = static_cast<uint32_t>(p.rows_per_tile * kBlockK * 2 + kBRows * kBlockK * 2);
     p.res_bytes = static_cast<uint32_t>(p.rows_per_tile * 64);
-    const int tiles = p.num_m_tiles * p.num_n_tiles;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    tap_gemm_kernel<BN, kF32><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmOut, tmRes, p);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    if (k2) {
+        const int items = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+        const int pairs = items < num_sms() / 2 ? items : num_sms() / 2;
+        cfg.gridDim = dim3(2 * pairs);
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    } else {
+        const int tiles = p.num_m_tiles * p.num_n_tiles;
+        cfg.gridDim = dim3(tiles < num_sms() ? tiles : num_sms());
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tap_gemm_kernel<BN, kF32, k2>, tmA, tmB, tmOut, tmRes, p);
     if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "tap_gemm launch: %s", cudaGetErrorString(e));
     return DCB_OK;
+}
+
+template <int BN, bool kF32>
+static int launch_mode(bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                       const CUtensorMap& tmRes, TapGemmParams& p, cudaStream_t s) {
+    return pair ? launch<BN, kF32, true>(tmA, tmB, tmOut, tmRes, p, s) : launch<BN, kF32, false>(tmA, tmB, tmOut, tmRes, p, s);
+}
+
+static int pair_mode_env() {       // DCB_GEMM_PAIR=0 forces single-CTA tiles, =1 forces CTA pairs, unset: heuristic
+    static int v = -2;
+    if (v == -2) {
+        const char* e = getenv("DCB_GEMM_PAIR");
+        v = (e == nullptr) ? -1 : atoi(e);
+    }
+    return v;
 }
 
 }  // namespace dcb
@@ -450,6 +522,11 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
         return set_error(DCB_ERR_INVALID, "tap_gemm: A/W need 16-byte aligned base and strides");
     if (a->N < 1) return set_error(DCB_ERR_INVALID, "tap_gemm: N");
     int bn = a->block_n;
+    if (bn == 0 && !a->geglu) {
+        static int env_bn = -1;                      // DCB_GEMM_BN: tuning override (tools/bench_kernels.py)
+        if (env_bn < 0) { const char* e = getenv("DCB_GEMM_BN"); env_bn = e ? atoi(e) : 0; }
+        if (env_bn > 0 && a->N % env_bn == 0) bn = env_bn;
+    }
     if (bn == 0) {
         // wider N tiles cut shared-memory bytes per MMA (the 1-CTA limiter) but need enough tiles to fill the SMs
         const long long m_tiles = static_cast<long long>((a->D1 + a->b1 - 1) / a->b1) * ((a->D2 + a->b2 - 1) / a->b2) *
@@ -459,6 +536,17 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
         else bn = (a->N % 160 == 0) ? 160 : 128;
     }
     if (bn != 128 && bn != 160 && bn != 256) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: block_n must be 128, 160 or 256");
+    // CTA pairs (cta_group::2): each SM stages half of B, halving shared-memory traffic per MMA. Worth it when
+    // there is at least one 256-row work item per SM pair.
+    bool pair;
+    {
+        const long long m_tiles = static_cast<long long>((a->D1 + a->b1 - 1) / a->b1) * ((a->D2 + a->b2 - 1) / a->b2) *
+                                  ((a->D3 + a->b3 - 1) / a->b3);
+        const long long items = ((m_tiles + 1) / 2) * ((a->N + bn - 1) / bn);
+        pair = items >= num_sms() / 2;
+        if (pair_mode_env() == 0) pair = false;
+        if (pair_mode_env() == 1) pair = true;
+    }
     if (a->geglu && (bn != 128 || a->N % 128 != 0))
         return set_error(DCB_ERR_INVALID, "tap_gemm: geglu needs block_n == 128 and N %% 128 == 0");
     if (a->group_bias != nullptr && a->rows_per_group < 1) return set_error(DCB_ERR_INVALID, "tap_gemm: rows_per_group");
@@ -485,7 +573,7 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
         const uint64_t K = (uint64_t)a->ntaps * a->C;
         const uint64_t dims[2] = {K, (uint64_t)a->N};
         const uint64_t str[2] = {1, (uint64_t)w_ld};
-        const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)bn};
+        const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)(pair ? bn / 2 : bn)};
         int rc = encode_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, CU_TENSOR_MAP_SWIZZLE_128B, a->w, 2, dims, str, box,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
@@ -538,9 +626,11 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (a->geglu && !obf) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: geglu writes bf16 only");
     if (obf) {
-        if (bn == 256) return launch<256, false>(tmA, tmB, tmOut, tmRes, p, s);
-        return bn == 160 ? launch<160, false>(tmA, tmB, tmOut, tmRes, p, s) : launch<128, false>(tmA, tmB, tmOut, tmRes, p, s);
+        if (bn == 256) return launch_mode<256, false>(pair, tmA, tmB, tmOut, tmRes, p, s);
+        return bn == 160 ? launch_mode<160, false>(pair, tmA, tmB, tmOut, tmRes, p, s)
+                         : launch_mode<128, false>(pair, tmA, tmB, tmOut, tmRes, p, s);
     }
-    if (bn == 256) return launch<256, true>(tmA, tmB, tmOut, tmRes, p, s);
-    return bn == 160 ? launch<160, true>(tmA, tmB, tmOut, tmRes, p, s) : launch<128, true>(tmA, tmB, tmOut, tmRes, p, s);
+    if (bn == 256) return launch_mode<256, true>(pair, tmA, tmB, tmOut, tmRes, p, s);
+    return bn == 160 ? launch_mode<160, true>(pair, tmA, tmB, tmOut, tmRes, p, s)
+                     : launch_mode<128, true>(pair, tmA, tmB, tmOut, tmRes, p, s);
 }
