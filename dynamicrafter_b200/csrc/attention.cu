@@ -10,6 +10,7 @@
 //
 // Round-1 status: both use warp-level mma.sync (HMMA) tiles with cp.async double buffering; the tcgen05/TMEM
 // version of the spatial kernel is the next optimisation step.
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "dcb_internal.h"
@@ -378,6 +379,15 @@ extern "C" int dcb_flash_attention(const dcb_attention_args* a, void* stream) {
     if (a->head_dim != kD) return set_error(DCB_ERR_UNSUPPORTED, "flash_attention: head_dim must be 64");
     if (a->batch < 1 || a->heads < 1 || a->nq < 1 || (a->ldq & 7) || (a->ldo & 7))
         return set_error(DCB_ERR_INVALID, "flash_attention: shape/alignment");
+    if (a->nq >= 256) {
+        // long sequences (spatial self-attention at the two finest UNet levels): tcgen05 / TMEM kernel
+        static int use_tc = -1;                 // DCB_FLASH_TC=0 forces the mma.sync kernel (A/B testing)
+        if (use_tc < 0) { const char* e = getenv("DCB_FLASH_TC"); use_tc = (e == nullptr) ? 1 : atoi(e); }
+        if (use_tc) {
+            const int rc = flash_tc_launch(a, static_cast<cudaStream_t>(stream));
+            if (rc != DCB_ERR_UNSUPPORTED) return rc;
+        }
+    }
     FlashParams p;
     p.q = static_cast<const __nv_bfloat16*>(a->q); p.ldq = a->ldq;
     p.o = static_cast<__nv_bfloat16*>(a->o); p.ldo = a->ldo;

@@ -29,13 +29,16 @@ constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kABytes = kBlockM * kBlockK * 2;
 // epilogue chunk = 64-byte rows (SWIZZLE_64B): 16 fp32 or 32 bf16 output columns x 128 rows = 8 KB per slot
 constexpr int kSlotBytes = kBlockM * 64;
-constexpr int kEpiBytes = 2 * 2 * kSlotBytes;         // 2 groups x 2 slots
+// slots per epilogue group: depth of the TMA store / residual-prefetch ring (pairs are the HBM-heavy big launches)
+template <bool k2> struct EpiSlots { static constexpr int value = k2 ? 4 : 2; };
 
 // smem ring depth: {A 16 KB + B rows x 128 B} per stage, 32 KB of epilogue slots, <= 227 KB in total.
 // In CTA-pair mode (k2) each CTA stages only half of the B tile.
 template <int BN, bool k2> struct StageCount {
     static constexpr int stage_bytes = kABytes + (k2 ? BN / 2 : BN) * kBlockK * 2;
-    static constexpr int value = (232448 - kEpiBytes - 1024 - 256) / stage_bytes > 8 ? 8 : (232448 - kEpiBytes - 1024 - 256) / stage_bytes;
+    static constexpr int epi_bytes = 2 * EpiSlots<k2>::value * kSlotBytes;
+    static constexpr int fit = (232448 - epi_bytes - 1024 - 256) / stage_bytes;
+    static constexpr int value = fit > 8 ? 8 : fit;
 };
 
 struct TapGemmParams {
@@ -79,6 +82,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                 const TapGemmParams p) {
     constexpr int kStages = StageCount<BN, k2>::value;
+    constexpr int kSlots = EpiSlots<k2>::value;
+    constexpr int kEpiBytes = 2 * kSlots * kSlotBytes;
     constexpr int kBRows = k2 ? BN / 2 : BN;               // B rows staged by this CTA
     constexpr int kBBytes = kBRows * kBlockK * 2;
     constexpr int kStageBytes = kABytes + kBBytes;
@@ -97,7 +102,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint64_t* tfull = bars + 2 * kStages;
     uint64_t* tempty = bars + 2 * kStages + 2;
     uint64_t* rfull = bars + 2 * kStages + 4;                         // [group][slot]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + 2 * kSlots);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -121,7 +126,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], k2 ? 2 * kEpiWarps : kEpiWarps);
         }
-        for (int i = 0; i < 4; ++i) mbar_init(&rfull[i], 1);
+        for (int i = 0; i < 2 * kSlots; ++i) mbar_init(&rfull[i], 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -207,8 +212,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int r = q * 32 + lane;               // tile row owned by this thread
         const bool leader = (q == 0 && lane == 0);
         const int bar_id = 1 + grp;
-        uint8_t* slots = epi + grp * 2 * kSlotBytes;
-        uint64_t* my_rfull = rfull + grp * 2;
+        uint8_t* slots = epi + grp * kSlots * kSlotBytes;
+        uint64_t* my_rfull = rfull + grp * kSlots;
         const int ncols = p.geglu ? BN / 2 : BN;   // output columns per tile
         const int nch = ncols / CW;
         const int my_nch = (nch - grp + 1) / 2;    // chunks grp, grp+2, ...
@@ -218,17 +223,23 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         (void)row_base;
         uint32_t tc = 0, cnt = 0;
 
-        // leader only: TMA-prefetch the residual chunk of work item (tile, ci) into slot (cnt & 1)
-        auto prefetch_res = [&](int tile, int ci, uint32_t cnt_item) {
-            const int m_tile = m_tile_of(tile);
-            const int n_tile = tile % p.num_n_tiles;
-            const int s = cnt_item & 1;
-            mbar_arrive_expect_tx(&my_rfull[s], p.res_bytes);
-            tma_load_4d(slots + s * kSlotBytes, &tmRes, &my_rfull[s], n_tile * ncols + ci * CW,
-                        (m_tile % p.t1) * p.b1, ((m_tile / p.t1) % p.t2) * p.b2, (m_tile / (p.t1 * p.t2)) * p.b3);
+        // leader only: TMA-prefetch stream of residual chunks, kSlots - 2 work items ahead of the one being processed
+        int pf_tile = worker, pf_ci = grp;
+        uint32_t pf_cnt = 0;
+        auto prefetch_upto = [&](uint32_t last_cnt) {
+            while (pf_cnt <= last_cnt && pf_tile < num_tiles) {
+                const int m_tile = m_tile_of(pf_tile);
+                const int n_tile = pf_tile % p.num_n_tiles;
+                const int s = pf_cnt & (kSlots - 1);
+                mbar_arrive_expect_tx(&my_rfull[s], p.res_bytes);
+                tma_load_4d(slots + s * kSlotBytes, &tmRes, &my_rfull[s], n_tile * ncols + pf_ci * CW,
+                            (m_tile % p.t1) * p.b1, ((m_tile / p.t1) % p.t2) * p.b2, (m_tile / (p.t1 * p.t2)) * p.b3);
+                ++pf_cnt;
+                pf_ci += 2;
+                if (pf_ci >= nch) { pf_tile += nworkers; pf_ci = grp; }
+            }
         };
-        if (tma_res && leader && my_nch > 0 && worker < num_tiles)
-            prefetch_res(worker, grp, 0);
+        if (my_nch == 0) pf_tile = num_tiles;
         const uint32_t tempty_addr0 = k2 ? mapa_cluster(smem_u32(&tempty[0]), 0) : 0u;   // leader's ring barriers
 
         for (int tile = worker; tile < num_tiles; tile += nworkers, ++tc) {
@@ -251,7 +262,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t t_row = tmem_base + a * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 
             for (int ci = grp; ci < nch; ci += 2, ++cnt) {
-                const int s = cnt & 1;
+                const int s = cnt & (kSlots - 1);
                 uint8_t* slot = slots + s * kSlotBytes;
                 const int col0 = n_tile * ncols + ci * CW;              // first output column of this chunk
                 float o[CW];
@@ -279,17 +290,18 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 if (tma_res) {
                     if (leader) {
-                        // next work item of this group: next chunk of this tile, else first chunk of the next tile
-                        int ntile = tile, nci = ci + 2;
-                        if (nci >= nch) { ntile = tile + nworkers; nci = grp; }
-                        if (ntile < num_tiles) {
-                            tma_store_wait_read<0>();            // slot s^1 was last read by the previous store
-                            prefetch_res(ntile, nci, cnt + 1);
+                        if constexpr (kSlots > 2) {
+                            // slots of items <= cnt + kSlots - 2 were last read by stores of items <= cnt - 2
+                            tma_store_wait_read<1>();
+                            prefetch_upto(cnt + kSlots - 2);
+                        } else {
+                            tma_store_wait_read<0>();            // slot of item cnt + 1 was read by the latest store
+                            prefetch_upto(cnt + 1);
                         }
                     }
-                    mbar_wait(&my_rfull[s], (cnt >> 1) & 1);
+                    mbar_wait(&my_rfull[s], (cnt / kSlots) & 1);
                 } else {
-                    if (leader) tma_store_wait_read<1>();        // the store issued from this slot two chunks ago
+                    if (leader) tma_store_wait_read<kSlots - 1>();   // the store issued from this slot kSlots items ago
                     named_bar_sync(bar_id, 128);
                 }
                 // ---- accumulator chunk -> registers
@@ -447,9 +459,10 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
                   TapGemmParams& p, cudaStream_t stream) {
     constexpr int kBRows = k2 ? BN / 2 : BN;
     constexpr int kStageBytes = kABytes + kBRows * kBlockK * 2;
-    constexpr int smem_bytes = StageCount<BN, k2>::value * kStageBytes + kEpiBytes + 1024 + 256;
+    constexpr int smem_bytes = StageCount<BN, k2>::value * kStageBytes + StageCount<BN, k2>::epi_bytes + 1024 + 256;
     static_assert(smem_bytes <= 232448, "shared memory budget");
     static_assert(StageCount<BN, k2>::value >= 4, "pipeline depth");
+    static_assert((2 * StageCount<BN, k2>::value + 4 + 2 * EpiSlots<k2>::value) * 8 + 4 <= 256, "barrier area");
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BN, kF32, k2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
