@@ -18,6 +18,28 @@ __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f 
 
 struct GnPlan { int row_split, rows_per_chunk, nchunks; };
 
+// 4 / 8 consecutive channels of a row, fp32 or bf16 source
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+}
+
 static int gcd_i(int a, int b) { return b == 0 ? a : gcd_i(b, a % b); }
 
 // One work item = (128-channel block, row split); a block's 8 warps share Qb*row_split items evenly.
@@ -45,8 +67,9 @@ static GnPlan plan_stats(int C1, int C2, int S) {
 // (threadfence + counter) folds the per-chunk partials in double and writes (mean, rstd).
 // Bitwise reproducible: no floating-point atomics anywhere.
 // ---------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int S,
+gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int C2, int S,
                 int rows_per_chunk, int row_split, float* __restrict__ partial, unsigned* __restrict__ counters,
                 float* __restrict__ stats, float eps) {
     extern __shared__ float s_part[];       // [row_split][C][2]
@@ -61,20 +84,20 @@ gn_stats_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
     for (int item = warp; item < Qb * row_split; item += 8) {
         const int cb = item / row_split, split = item - cb * row_split;
         const bool second = cb >= Qb1;
-        const float* x = second ? x2 : x1;
+        const T* x = second ? x2 : x1;
         const int Cs = second ? C2 : C1;
         const int coff = second ? C1 : 0;
         const int q = (second ? cb - Qb1 : cb) * 32 + lane;
         if (q >= (Cs >> 2)) continue;
-        const float4* base = reinterpret_cast<const float4*>(x + (static_cast<size_t>(n) * S) * Cs) + q;
-        const size_t rs = static_cast<size_t>(Cs >> 2);       // row stride in float4
+        const T* base = x + (static_cast<size_t>(n) * S) * Cs + q * 4;
+        const size_t rs = static_cast<size_t>(Cs);            // row stride in elements
         float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
         for (int r = r0 + split; r < r1; r += 4 * row_split) {
             float4 v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int rr = r + u * row_split;
-                v[u] = rr < r1 ? __ldg(base + rr * rs) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[u] = rr < r1 ? ld4(base + rr * rs) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -161,8 +184,9 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
     return p;
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int S,
+gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int C2, int S,
                 int rows_per_chunk, const float* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int do_silu, __nv_bfloat16* __restrict__ y,
                 __nv_bfloat16* __restrict__ raw) {
@@ -188,10 +212,9 @@ gn_apply_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
     const int drr = 256 / O, dO = 256 - drr * O;          // idx += 256 without a division per item
     for (int idx = tid; idx < items; idx += 256) {
         const size_t row = static_cast<size_t>(n) * S + r0 + rr;
-        const float* src = (o < O1) ? (x1 + row * C1 + o * 8) : (x2 + row * C2 + (o - O1) * 8);
-        const float4 a = __ldg(reinterpret_cast<const float4*>(src));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const T* src = (o < O1) ? (x1 + row * C1 + o * 8) : (x2 + row * C2 + (o - O1) * 8);
+        float v[8];
+        ld8(src, v);
         const int c0 = o * 8;
         if (raw != nullptr) *reinterpret_cast<uint4*>(raw + row * C + c0) = pack8(v);
         if (y != nullptr) {
@@ -294,9 +317,23 @@ extern "C" int dcb_group_norm_stats(const float* x1, const float* x2, int C1, in
         return set_error(DCB_ERR_INVALID, "group_norm_stats: C1=%d C2=%d G=%d S=%d", C1, C2, G, S);
     const GnPlan pl = plan_stats(C1, C2, S);
     const size_t smem = static_cast<size_t>(pl.row_split) * C * 2 * sizeof(float);
-    gn_stats_kernel<<<dim3(pl.nchunks, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+    gn_stats_kernel<float><<<dim3(pl.nchunks, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         x1, x2, C1, C2, S, pl.rows_per_chunk, pl.row_split, static_cast<float*>(workspace), counters, stats, eps);
     return check_launch("group_norm_stats");
+}
+
+extern "C" int dcb_group_norm_stats_bf16(const void* x, int C, int G, int S, float eps, float* stats, void* workspace,
+                                         unsigned* counters, void* stream) {
+    if (x == nullptr || stats == nullptr || workspace == nullptr || counters == nullptr)
+        return set_error(DCB_ERR_INVALID, "group_norm_stats_bf16: null argument");
+    if (C % kGroups != 0 || (C & 7) || G < 1 || S < 1 || C > kMaxC)
+        return set_error(DCB_ERR_INVALID, "group_norm_stats_bf16: C=%d G=%d S=%d", C, G, S);
+    const GnPlan pl = plan_stats(C, 0, S);
+    const size_t smem = static_cast<size_t>(pl.row_split) * C * 2 * sizeof(float);
+    gn_stats_kernel<__nv_bfloat16><<<dim3(pl.nchunks, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), nullptr, C, 0, S, pl.rows_per_chunk, pl.row_split,
+        static_cast<float*>(workspace), counters, stats, eps);
+    return check_launch("group_norm_stats_bf16");
 }
 
 extern "C" int dcb_group_norm_apply(const float* x1, const float* x2, int C1, int C2, int G, int S,
@@ -313,10 +350,25 @@ extern "C" int dcb_group_norm_apply(const float* x1, const float* x2, int C1, in
     int nch = 1;
     const int rpc = apply_rows_per_chunk(G, S, C, &nch);
     const size_t smem = static_cast<size_t>(C) * 2 * sizeof(float);
-    gn_apply_kernel<<<dim3(nch, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+    gn_apply_kernel<float><<<dim3(nch, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         x1, x2, C1, C2, S, rpc, stats, gamma, beta, silu_act, static_cast<__nv_bfloat16*>(y_bf16),
         static_cast<__nv_bfloat16*>(raw_bf16));
     return check_launch("group_norm_apply");
+}
+
+extern "C" int dcb_group_norm_apply_bf16(const void* x, int C, int G, int S, const float* stats, const float* gamma,
+                                         const float* beta, int silu_act, void* y_bf16, void* stream) {
+    if (x == nullptr || y_bf16 == nullptr || stats == nullptr || gamma == nullptr || beta == nullptr)
+        return set_error(DCB_ERR_INVALID, "group_norm_apply_bf16: null argument");
+    if (C % kGroups != 0 || (C & 7) || G < 1 || S < 1 || C > kMaxC)
+        return set_error(DCB_ERR_INVALID, "group_norm_apply_bf16: C=%d G=%d S=%d", C, G, S);
+    int nch = 1;
+    const int rpc = apply_rows_per_chunk(G, S, C, &nch);
+    const size_t smem = static_cast<size_t>(C) * 2 * sizeof(float);
+    gn_apply_kernel<__nv_bfloat16><<<dim3(nch, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), nullptr, C, 0, S, rpc, stats, gamma, beta, silu_act,
+        static_cast<__nv_bfloat16*>(y_bf16), nullptr);
+    return check_launch("group_norm_apply_bf16");
 }
 
 extern "C" int dcb_layer_norm(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,

@@ -9,6 +9,17 @@ import torch.nn as nn
 
 BF16 = torch.bfloat16
 
+import os as _os
+
+# Block-internal activations that only feed a GroupNorm may be written by their producer GEMM as bf16 (the
+# GroupNorm output is a bf16 operand anyway; it halves the HBM traffic of the three kernels touching them).
+# DCB_BF16_INTERNAL: comma list of {tconv (TemporalConvBlock stages 1-3), res (ResBlock h after conv1),
+# vae (VAE ResnetBlock h after conv1)}; "0" = none.  Default: see DESIGN.md (precision budget).
+_LOWP = set(_os.environ.get("DCB_BF16_INTERNAL", "tconv,res").split(","))
+BF16_TCONV = "tconv" in _LOWP or "all" in _LOWP
+BF16_RES = "res" in _LOWP or "all" in _LOWP
+BF16_VAE = "vae" in _LOWP or "all" in _LOWP
+
 
 def _pad64(c):
     return (c + 63) // 64 * 64

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from dynamicrafter_b200 import ops
+from dynamicrafter_b200.lvdm import _packing
 from dynamicrafter_b200.lvdm._packing import PackedModule, Act, pack_linear, pack_conv3x3
 
 
@@ -89,7 +90,8 @@ class ResnetBlock(PackedModule):
         sc = "ws" in p
         res = ops.group_norm(h.x, nf, S, self.norm1.weight, self.norm1.bias, self.norm1.eps, silu=True, want_raw=sc)
         y, raw = res if sc else (res, None)
-        h1 = ops.conv3x3(y, nf, h.H, h.W, p["w1"], bias=p["b1"])
+        h1 = ops.conv3x3(y, nf, h.H, h.W, p["w1"], bias=p["b1"], f32=not _packing.BF16_VAE,
+                         bf16=_packing.BF16_VAE)
         y2 = ops.group_norm(h1, nf, S, self.norm2.weight, self.norm2.bias, self.norm2.eps, silu=True)
         xs = ops.linear(raw, p["ws"], bias=p["bs"], f32=True, bf16=False) if sc else h.x
         return h.like(ops.conv3x3(y2, nf, h.H, h.W, p["w2"], bias=p["b2"], residual=xs))

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from dynamicrafter_b200 import ops
+from dynamicrafter_b200.lvdm import _packing
 from dynamicrafter_b200.lvdm._packing import PackedModule, Act, pack_linear, pack_conv3x3, pack_tconv3
 from dynamicrafter_b200.lvdm.modules.attention import SpatialTransformer, TemporalTransformer, make_context, CrossAttentionContext, TEXT_CONTEXT_LEN
 
@@ -145,7 +146,10 @@ class TemporalConvBlock(PackedModule):
         for i, st in enumerate(self._stages()):
             gn = st[0]
             y = ops.group_norm(z, B, T * S, gn.weight, gn.bias, gn.eps, silu=True)
-            z = ops.tconv3(y, B, T, S, p["w"][i], bias=p["b"][i], residual=h.x if i == 3 else None)
+            last = i == 3
+            lowp = _packing.BF16_TCONV and not last
+            z = ops.tconv3(y, B, T, S, p["w"][i], bias=p["b"][i], residual=h.x if last else None,
+                           f32=not lowp, bf16=lowp)
         return h.like(z)
 
     def forward(self, x):
@@ -203,7 +207,8 @@ class ResBlock(PackedModule, TimestepBlock):
         has_skip_conv = "ws" in p
         res = ops.group_norm(h.x, nf, S, g1.weight, g1.bias, g1.eps, x2=skip, silu=True, want_raw=has_skip_conv)
         y, raw = res if has_skip_conv else (res, None)
-        h1 = ops.conv3x3(y, nf, h.H, h.W, p["w1"], bias=p["b1"], group_bias=emb_out, rows_per_group=rows_per_emb)
+        h1 = ops.conv3x3(y, nf, h.H, h.W, p["w1"], bias=p["b1"], group_bias=emb_out, rows_per_group=rows_per_emb,
+                         f32=not _packing.BF16_RES, bf16=_packing.BF16_RES)
         g2 = self.out_layers[0]
         y2 = ops.group_norm(h1, nf, S, g2.weight, g2.bias, g2.eps, silu=True)
         xs = ops.linear(raw, p["ws"], bias=p["bs"], f32=True, bf16=False) if has_skip_conv else h.x

@@ -181,6 +181,18 @@ def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False
     """x1: fp32 [G*S, C1] (+ x2 [G*S, C2] concatenated on channels) -> bf16 normalised operand
     (and/or bf16 raw copy of the concat)."""
     require_cuda(x1, x2, gamma, beta)
+    if x1.dtype == BF16:
+        # block-internal activation kept in bf16 by its producer: single source, normalised output only
+        assert x2 is None and not want_raw and x1.is_contiguous() and x1.shape[0] == G * S
+        C, dev, L = x1.shape[1], x1.device, _lib.lib()
+        ws, cnt = _gn_scratch(dev, G)
+        stats = torch.empty((G, 32, 2), dtype=F32, device=dev)
+        check(L.dcb_group_norm_stats_bf16(ptr(x1), _c_i(C), _c_i(G), _c_i(S), _c_f(eps), ptr(stats), ptr(ws), ptr(cnt),
+                                          _stream()), "dcb_group_norm_stats_bf16")
+        y = torch.empty((G * S, C), dtype=BF16, device=dev)
+        check(L.dcb_group_norm_apply_bf16(ptr(x1), _c_i(C), _c_i(G), _c_i(S), ptr(stats), ptr(gamma), ptr(beta),
+                                          _c_i(1 if silu else 0), ptr(y), _stream()), "dcb_group_norm_apply_bf16")
+        return y
     assert x1.dtype == F32 and x1.is_contiguous() and x1.shape[0] == G * S
     C1 = x1.shape[1]
     C2 = 0 if x2 is None else x2.shape[1]

@@ -103,6 +103,12 @@ int dcb_group_norm_stats(const float* x1, const float* x2, int C1, int C2, int G
 int dcb_group_norm_apply(const float* x1, const float* x2, int C1, int C2, int G, int S,
                          const float* stats, const float* gamma, const float* beta, int silu_act,
                          void* y_bf16, void* raw_bf16, void* stream);
+/* Same statistics / apply for a bf16 source (block-internal activations the producer GEMM wrote as bf16):
+ * single source, C % 8 == 0. */
+int dcb_group_norm_stats_bf16(const void* x, int C, int G, int S, float eps, float* stats, void* workspace,
+                              unsigned* counters, void* stream);
+int dcb_group_norm_apply_bf16(const void* x, int C, int G, int S, const float* stats, const float* gamma,
+                              const float* beta, int silu_act, void* y_bf16, void* stream);
 /* LayerNorm over the last dim (attention.py:225-227), fp32 in, bf16 out. C % 4 == 0, C <= 2560. */
 int dcb_layer_norm(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,
                    void* y_bf16, void* stream);

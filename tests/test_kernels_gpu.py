@@ -186,3 +186,13 @@ def test_ddim_update_matches_reference_arithmetic(is_v, gr, cfg):
         assert torch.equal(x0, p0) and torch.equal(xp, ref)         # bit exact: same fp32 ops in the same order
     else:
         assert _rel(x0, p0) < 1e-6 and _rel(xp, ref) < 1e-6
+
+
+@pytest.mark.parametrize("G,S,C", [(3, 40, 64), (2, 640, 320), (1, 4096, 1280)])
+def test_group_norm_bf16_source(G, S, C):
+    from dynamicrafter_b200 import ops
+    x = _randn((G * S, C), 41, 2.0, 0.7).to(torch.bfloat16)
+    gamma, beta = _randn((C,), 3, 0.2, 1.0), _randn((C,), 4, 0.1)
+    ref = F.silu(F.group_norm(x.float().reshape(G, S, C).permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(G * S, C)
+    y = ops.group_norm(x, G, S, gamma, beta, 1e-5, silu=True)
+    assert _rel(y, ref) < 4e-3
