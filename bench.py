@@ -283,6 +283,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line (NCCL prints its version at INFO/VERSION)
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.lib().dcb_check_device(), "dcb_check_device")
     peaks = load_peaks()
@@ -391,9 +392,9 @@ def main():
                                 guidance_rescale=sm["guidance_rescale"])
         torch.cuda.synchronize()
         t_s = time.perf_counter() - t0
-        if world > 1:
-            gathered = [torch.empty_like(samples) for _ in range(world)]
-            dist.all_gather(gathered, samples)        # the single collective of this mode
+        from dynamicrafter_b200.parallel import all_gather_latents
+        gathered = all_gather_latents(samples)        # the single collective of this mode
+        assert gathered.shape[0] == world * B
         t1 = time.perf_counter()
         frames = host.decode_first_stage(samples, frames_per_call=8)
         torch.cuda.synchronize()
