@@ -24,19 +24,20 @@ namespace dcb {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + kEpiWarps * 32;
+// epilogue groups of 4 warps (one warp per TMEM lane quarter): 4 groups in CTA-pair mode (576 threads), else 2
+template <bool k2> struct EpiGroups { static constexpr int value = k2 ? 4 : 2; };
+template <bool k2> struct Threads { static constexpr int value = 64 + 128 * EpiGroups<k2>::value; };
 constexpr int kABytes = kBlockM * kBlockK * 2;
 // epilogue chunk = 64-byte rows (SWIZZLE_64B): 16 fp32 or 32 bf16 output columns x 128 rows = 8 KB per slot
 constexpr int kSlotBytes = kBlockM * 64;
 // slots per epilogue group: depth of the TMA store / residual-prefetch ring (pairs are the HBM-heavy big launches)
-template <bool k2> struct EpiSlots { static constexpr int value = k2 ? 4 : 2; };
+template <bool k2> struct EpiSlots { static constexpr int value = 2; };
 
 // smem ring depth: {A 16 KB + B rows x 128 B} per stage, 32 KB of epilogue slots, <= 227 KB in total.
 // In CTA-pair mode (k2) each CTA stages only half of the B tile.
 template <int BN, bool k2> struct StageCount {
     static constexpr int stage_bytes = kABytes + (k2 ? BN / 2 : BN) * kBlockK * 2;
-    static constexpr int epi_bytes = 2 * EpiSlots<k2>::value * kSlotBytes;
+    static constexpr int epi_bytes = EpiGroups<k2>::value * EpiSlots<k2>::value * kSlotBytes;
     static constexpr int fit = (232448 - epi_bytes - 1024 - 256) / stage_bytes;
     static constexpr int value = fit > 8 ? 8 : fit;
 };
@@ -63,7 +64,8 @@ struct TapGemmParams {
 //   x >= 0: gelu = x - 0.5 x erfc(x/sqrt2)      x < 0: gelu = 0.5 x erfc(|x|/sqrt2)   (no cancellation)
 __device__ __forceinline__ float gelu_erf(float x) {
     const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));      // MUFU.RCP
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));      // MUFU.RCP, argument in [1, inf)
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
@@ -77,13 +79,15 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 
 template <int BN, bool kF32, bool k2>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(Threads<k2>::value, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                 const TapGemmParams p) {
     constexpr int kStages = StageCount<BN, k2>::value;
     constexpr int kSlots = EpiSlots<k2>::value;
-    constexpr int kEpiBytes = 2 * kSlots * kSlotBytes;
+    constexpr int kG = EpiGroups<k2>::value;
+    constexpr int kEpiWarps = 4 * kG;
+    constexpr int kEpiBytes = kG * kSlots * kSlotBytes;
     constexpr int kBRows = k2 ? BN / 2 : BN;               // B rows staged by this CTA
     constexpr int kBBytes = kBRows * kBlockK * 2;
     constexpr int kStageBytes = kABytes + kBBytes;
@@ -102,7 +106,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint64_t* tfull = bars + 2 * kStages;
     uint64_t* tempty = bars + 2 * kStages + 2;
     uint64_t* rfull = bars + 2 * kStages + 4;                         // [group][slot]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + 2 * kSlots);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + kG * kSlots);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -126,7 +130,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], k2 ? 2 * kEpiWarps : kEpiWarps);
         }
-        for (int i = 0; i < 2 * kSlots; ++i) mbar_init(&rfull[i], 1);
+        for (int i = 0; i < kG * kSlots; ++i) mbar_init(&rfull[i], 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -216,7 +220,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint64_t* my_rfull = rfull + grp * kSlots;
         const int ncols = p.geglu ? BN / 2 : BN;   // output columns per tile
         const int nch = ncols / CW;
-        const int my_nch = (nch - grp + 1) / 2;    // chunks grp, grp+2, ...
+        const int my_nch = grp < nch ? (nch - grp + kG - 1) / kG : 0;    // chunks grp, grp+kG, ...
         const bool tma_res = kF32 && p.has_residual;          // fp32 out: residual chunk prefetched in place by TMA
         const int swz = (r >> 1) & 3;              // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
         uint8_t* const row_base = nullptr;
@@ -235,7 +239,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tma_load_4d(slots + s * kSlotBytes, &tmRes, &my_rfull[s], n_tile * ncols + pf_ci * CW,
                             (m_tile % p.t1) * p.b1, ((m_tile / p.t1) % p.t2) * p.b2, (m_tile / (p.t1 * p.t2)) * p.b3);
                 ++pf_cnt;
-                pf_ci += 2;
+                pf_ci += kG;
                 if (pf_ci >= nch) { pf_tile += nworkers; pf_ci = grp; }
             }
         };
@@ -261,28 +265,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             bool acc_ready = false;
             const uint32_t t_row = tmem_base + a * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 
-            for (int ci = grp; ci < nch; ci += 2, ++cnt) {
+            for (int ci = grp; ci < nch; ci += kG, ++cnt) {
                 const int s = cnt & (kSlots - 1);
                 uint8_t* slot = slots + s * kSlotBytes;
                 const int col0 = n_tile * ncols + ci * CW;              // first output column of this chunk
-                float o[CW];
-                if (!kF32 && p.has_residual) {
-                    // issue the residual loads before waiting for the accumulator (fp32 rows, 128 B per chunk)
-                    if (res_row != nullptr && col0 + CW <= p.N_out) {
-#pragma unroll
-                        for (int j = 0; j < CW; j += 4) {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(res_row + col0 + j));
-                            o[j] = t.x; o[j + 1] = t.y; o[j + 2] = t.z; o[j + 3] = t.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < CW; ++j)
-                            o[j] = (res_row != nullptr && col0 + j < p.N_out) ? __ldg(res_row + col0 + j) : 0.f;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < CW; ++j) o[j] = 0.f;
-                }
                 if (!acc_ready) {
                     mbar_wait(&tfull[a], aph);
                     tc_fence_after();
@@ -290,107 +276,120 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 if (tma_res) {
                     if (leader) {
-                        if constexpr (kSlots > 2) {
-                            // slots of items <= cnt + kSlots - 2 were last read by stores of items <= cnt - 2
-                            tma_store_wait_read<1>();
-                            prefetch_upto(cnt + kSlots - 2);
-                        } else {
-                            tma_store_wait_read<0>();            // slot of item cnt + 1 was read by the latest store
-                            prefetch_upto(cnt + 1);
-                        }
+                        tma_store_wait_read<0>();                // slot of item cnt + 1 was read by the latest store
+                        prefetch_upto(cnt + 1);
                     }
                     mbar_wait(&my_rfull[s], (cnt / kSlots) & 1);
-                } else {
-                    if (leader) tma_store_wait_read<kSlots - 1>();   // the store issued from this slot kSlots items ago
-                    named_bar_sync(bar_id, 128);
                 }
-                // ---- accumulator chunk -> registers
-                uint32_t v[CW];
-                if constexpr (kF32) tmem_ld16(t_row + ci * CW, v); else tmem_ld32(t_row + ci * CW, v);
-                if constexpr (!kF32) {
-                    if (p.geglu) {
-                        uint32_t g[CW];
-                        tmem_ld32(t_row + BN / 2 + ci * CW, g);
-                        tmem_ld_wait();
-                        const int wn = n_tile * BN + ci * CW;           // packed weight column of the value half
+                // (no TMA residual: the slot was proven free before the previous chunk's barrier, see below)
+                uint8_t* orow = slot + r * 64;                          // 64-byte rows, SWIZZLE_64B
+                // 16 columns at a time (keeps the 576-thread CTA under 113 registers per thread)
 #pragma unroll
-                        for (int j = 0; j < CW; j += 4) {
+                for (int hf = 0; hf < CW / 16; ++hf) {
+                    const int cb = col0 + hf * 16;
+                    float o[16];
+                    if (!kF32 && p.has_residual) {
+                        if (res_row != nullptr && cb + 16 <= p.N_out) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(res_row + cb + j));
+                                o[j] = t.x; o[j + 1] = t.y; o[j + 2] = t.z; o[j + 3] = t.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                o[j] = (res_row != nullptr && cb + j < p.N_out) ? __ldg(res_row + cb + j) : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = 0.f;
+                    }
+                    uint32_t v[16];
+                    tmem_ld16(t_row + ci * CW + hf * 16, v);
+                    if (!kF32 && p.geglu) {
+                        uint32_t g[16];
+                        tmem_ld16(t_row + BN / 2 + ci * CW + hf * 16, g);
+                        tmem_ld_wait();
+                        const int wn = n_tile * BN + ci * CW + hf * 16;   // packed weight column of the value half
+                        const float s_ = p.out_scale;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
                             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
                             if (p.bias != nullptr) {
                                 bv = __ldg(reinterpret_cast<const float4*>(p.bias + wn + j));
                                 bg = __ldg(reinterpret_cast<const float4*>(p.bias + wn + BN / 2 + j));
                             }
-                            const float s_ = p.out_scale;
                             o[j] += (__uint_as_float(v[j]) * s_ + bv.x) * gelu_erf(__uint_as_float(g[j]) * s_ + bg.x);
                             o[j + 1] += (__uint_as_float(v[j + 1]) * s_ + bv.y) * gelu_erf(__uint_as_float(g[j + 1]) * s_ + bg.y);
                             o[j + 2] += (__uint_as_float(v[j + 2]) * s_ + bv.z) * gelu_erf(__uint_as_float(g[j + 2]) * s_ + bg.z);
                             o[j + 3] += (__uint_as_float(v[j + 3]) * s_ + bv.w) * gelu_erf(__uint_as_float(g[j + 3]) * s_ + bg.w);
                         }
-                    }
-                }
-                if (!p.geglu) {
-                    tmem_ld_wait();
-                    if (p.out_scale != 1.0f) {
-#pragma unroll
-                        for (int j = 0; j < CW; ++j) o[j] = fmaf(__uint_as_float(v[j]), p.out_scale, o[j]);
                     } else {
+                        tmem_ld_wait();
+                        if (p.out_scale != 1.0f) {
 #pragma unroll
-                        for (int j = 0; j < CW; ++j) o[j] += __uint_as_float(v[j]);
+                            for (int j = 0; j < 16; ++j) o[j] = fmaf(__uint_as_float(v[j]), p.out_scale, o[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) o[j] += __uint_as_float(v[j]);
+                        }
+                        if (p.bias != nullptr) {
+                            if (cb + 16 <= p.N_out) {
+#pragma unroll
+                                for (int j = 0; j < 16; j += 4) {
+                                    const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + cb + j));
+                                    o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (cb + j < p.N_out) o[j] += __ldg(p.bias + cb + j);
+                            }
+                        }
                     }
-                    if (p.bias != nullptr) {
-                        if (col0 + CW <= p.N_out) {
+                    if (gb != nullptr) {
+                        if (cb + 16 <= p.N_out && (reinterpret_cast<uintptr_t>(gb + cb) & 15) == 0) {
 #pragma unroll
-                            for (int j = 0; j < CW; j += 4) {
-                                const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(gb + cb + j));
                                 o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w;
                             }
                         } else {
 #pragma unroll
-                            for (int j = 0; j < CW; ++j)
-                                if (col0 + j < p.N_out) o[j] += __ldg(p.bias + col0 + j);
+                            for (int j = 0; j < 16; ++j)
+                                if (cb + j < p.N_out) o[j] += __ldg(gb + cb + j);
                         }
                     }
-                }
-                if (gb != nullptr) {
-                    if (col0 + CW <= p.N_out && (reinterpret_cast<uintptr_t>(gb + col0) & 15) == 0) {
+                    if constexpr (kF32) {
+                        if (tma_res) {
 #pragma unroll
-                        for (int j = 0; j < CW; j += 4) {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(gb + col0 + j));
-                            o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w;
+                            for (int c = 0; c < 4; ++c) {
+                                const float4 t = *reinterpret_cast<const float4*>(orow + ((c ^ swz) << 4));
+                                o[4 * c] += t.x; o[4 * c + 1] += t.y; o[4 * c + 2] += t.z; o[4 * c + 3] += t.w;
+                            }
                         }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            *reinterpret_cast<float4*>(orow + ((c ^ swz) << 4)) =
+                                make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < CW; ++j)
-                            if (col0 + j < p.N_out) o[j] += __ldg(gb + col0 + j);
-                    }
-                }
-                uint8_t* orow = slot + r * 64;                          // 64-byte rows, SWIZZLE_64B
-                if constexpr (kF32) {
-                    if (tma_res) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const float4 t = *reinterpret_cast<const float4*>(orow + ((c ^ swz) << 4));
-                            o[4 * c] += t.x; o[4 * c + 1] += t.y; o[4 * c + 2] += t.z; o[4 * c + 3] += t.w;
+                        for (int c = 0; c < 2; ++c) {
+                            uint4 pk;
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * c], o[8 * c + 1]);
+                            __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * c + 2], o[8 * c + 3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * c + 4], o[8 * c + 5]);
+                            __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * c + 6], o[8 * c + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(orow + (((hf * 2 + c) ^ swz) << 4)) = pk;
                         }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        *reinterpret_cast<float4*>(orow + ((c ^ swz) << 4)) =
-                            make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint4 pk;
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * c], o[8 * c + 1]);
-                        __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * c + 2], o[8 * c + 3]);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * c + 4], o[8 * c + 5]);
-                        __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * c + 6], o[8 * c + 7]);
-                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                        *reinterpret_cast<uint4*>(orow + ((c ^ swz) << 4)) = pk;
                     }
                 }
                 fence_proxy_async();                                     // generic-proxy writes -> visible to TMA
+                // the next chunk writes the other slot: its last store (issued one chunk ago) must have read it;
+                // checking before this barrier makes that visible to the whole group without a second barrier
+                if (!tma_res && leader) tma_store_wait_read<kSlots - 2>();
                 named_bar_sync(bar_id, 128);
                 if (leader) {
                     tma_store_4d(&tmOut, slot, col0, o1, o2, o3);
@@ -462,7 +461,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     constexpr int smem_bytes = StageCount<BN, k2>::value * kStageBytes + StageCount<BN, k2>::epi_bytes + 1024 + 256;
     static_assert(smem_bytes <= 232448, "shared memory budget");
     static_assert(StageCount<BN, k2>::value >= 4, "pipeline depth");
-    static_assert((2 * StageCount<BN, k2>::value + 4 + 2 * EpiSlots<k2>::value) * 8 + 4 <= 256, "barrier area");
+    static_assert((2 * StageCount<BN, k2>::value + 4 + EpiGroups<k2>::value * EpiSlots<k2>::value) * 8 + 4 <= 256, "barrier area");
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BN, kF32, k2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -474,7 +473,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     p.res_bytes = static_cast<uint32_t>(p.rows_per_tile * 64);
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(Threads<k2>::value);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     if (k2) {
@@ -544,7 +543,7 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
         // wider N tiles cut shared-memory bytes per MMA (the 1-CTA limiter) but need enough tiles to fill the SMs
         const long long m_tiles = static_cast<long long>((a->D1 + a->b1 - 1) / a->b1) * ((a->D2 + a->b2 - 1) / a->b2) *
                                   ((a->D3 + a->b3 - 1) / a->b3);
-        if (a->geglu) bn = 128;
+        if (a->geglu) bn = (a->N % 256 == 0) ? 256 : 128;
         else if (a->N % 256 == 0 && m_tiles * (a->N / 256) >= 2LL * num_sms()) bn = 256;
         else bn = (a->N % 160 == 0) ? 160 : 128;
     }
@@ -560,8 +559,8 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
         if (pair_mode_env() == 0) pair = false;
         if (pair_mode_env() == 1) pair = true;
     }
-    if (a->geglu && (bn != 128 || a->N % 128 != 0))
-        return set_error(DCB_ERR_INVALID, "tap_gemm: geglu needs block_n == 128 and N %% 128 == 0");
+    if (a->geglu && ((bn != 128 && bn != 256) || a->N % bn != 0))
+        return set_error(DCB_ERR_INVALID, "tap_gemm: geglu needs block_n in {128, 256} dividing N");
     if (a->group_bias != nullptr && a->rows_per_group < 1) return set_error(DCB_ERR_INVALID, "tap_gemm: rows_per_group");
     const bool obf = a->out_bf16 != nullptr;
     const void* outp = obf ? a->out_bf16 : static_cast<const void*>(a->out_f32);

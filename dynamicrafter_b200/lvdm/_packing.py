@@ -46,7 +46,9 @@ def pack_tconv3(w):
 
 
 def geglu_block_n(inner):
-    """The GEGLU epilogue pairs value/gate columns inside a 128-wide tile (64 values | 64 gates)."""
+    """The GEGLU epilogue pairs value/gate columns inside one N tile: (BN/2 values | BN/2 gates)."""
+    if inner % 128 == 0:
+        return 256
     if inner % 64 == 0:
         return 128
     raise ValueError(f"GEGLU inner dim {inner} must be a multiple of 64")

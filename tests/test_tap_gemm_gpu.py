@@ -50,7 +50,7 @@ def test_linear_strided_a_and_small_n():
     _close(out, ref, 1e-4)
 
 
-@pytest.mark.parametrize("K,inner,bn", [(128, 320, 128), (64, 256, 128), (320, 1280, 128)])
+@pytest.mark.parametrize("K,inner,bn", [(128, 320, 128), (64, 256, 128), (320, 1280, 128), (320, 1280, 256), (64, 256, 256)])
 def test_geglu(K, inner, bn):
     from dynamicrafter_b200 import ops
     M = 200
