@@ -10,11 +10,18 @@
 namespace dcb {
 
 constexpr int kGroups = 32;
-constexpr int kMaxChunks = 256;
+constexpr int kMaxChunks = 512;
 constexpr int kMaxC = 4096;
 constexpr int kMaxSplitC = 4096;          // row_split * C bound (dynamic smem of the stats kernel = 8 B each)
 
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// silu(x) = x / (1 + 2^(-x log2 e)) with the raw MUFU approximations (ex2.approx / rcp.approx, ~1 ulp each and no
+// range-fixup code: the apply kernel is close to issue-bound, not only HBM-bound)
+__device__ __forceinline__ float silu_fast(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
 
 struct GnPlan { int row_split, rows_per_chunk, nchunks; };
 
@@ -50,7 +57,7 @@ static GnPlan plan_stats(int C1, int C2, int S) {
     if (s > cap) s = cap;
     GnPlan p;
     p.row_split = s;
-    p.rows_per_chunk = 8 * s;                                   // 8 rows per item: 2 rounds of 4 loads in flight
+    p.rows_per_chunk = 8 * s;                                   // 8 rows per item, all 8 loads in flight
     p.nchunks = (S + p.rows_per_chunk - 1) / p.rows_per_chunk;
     if (p.nchunks > kMaxChunks) {
         p.rows_per_chunk = (S + kMaxChunks - 1) / kMaxChunks;
@@ -92,15 +99,15 @@ gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int 
         const T* base = x + (static_cast<size_t>(n) * S) * Cs + q * 4;
         const size_t rs = static_cast<size_t>(Cs);            // row stride in elements
         float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int r = r0 + split; r < r1; r += 4 * row_split) {
-            float4 v[4];
+        for (int r = r0 + split; r < r1; r += 8 * row_split) {
+            float4 v[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int rr = r + u * row_split;
                 v[u] = rr < r1 ? ld4(base + rr * rs) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
                 ss[0] += v[u].x * v[u].x; ss[1] += v[u].y * v[u].y; ss[2] += v[u].z * v[u].z; ss[3] += v[u].w * v[u].w;
             }
