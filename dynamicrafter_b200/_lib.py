@@ -27,6 +27,7 @@ class TapGemmArgs(ctypes.Structure):
         ("bias", c_vp), ("group_bias", c_vp), ("rows_per_group", c_int), ("ld_group_bias", c_int),
         ("residual", c_vp), ("ld_residual", c_int), ("geglu", c_int),
         ("out_f32", c_vp), ("out_bf16", c_vp), ("ld_out", c_int), ("out_scale", c_f),
+        ("colsum", c_vp), ("colsum_ld", c_int),
     ]
 
 
@@ -74,7 +75,7 @@ def lib():
 EXPORTS = [
     "dcb_last_error", "dcb_abi_version", "dcb_check_device", "dcb_tap_gemm",
     "dcb_group_norm_workspace_bytes", "dcb_group_norm_stats", "dcb_group_norm_apply", "dcb_layer_norm",
-    "dcb_group_norm_stats_bf16", "dcb_group_norm_apply_bf16",
+    "dcb_group_norm_stats_bf16", "dcb_group_norm_apply_bf16", "dcb_group_norm_finalize",
     "dcb_flash_attention", "dcb_temporal_attention", "dcb_softmax_rows",
     "dcb_nchw_to_rows", "dcb_rows_to_nchw", "dcb_upsample2x", "dcb_space_to_depth", "dcb_cast_bf16",
     "dcb_timestep_embedding", "dcb_small_linear", "dcb_ddim_update",

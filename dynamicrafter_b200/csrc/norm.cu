@@ -329,6 +329,58 @@ extern "C" int dcb_group_norm_stats(const float* x1, const float* x2, int C1, in
     return check_launch("group_norm_stats");
 }
 
+// (mean, rstd) of instance n / group g from the per-column (sum, sumsq) partial rows a tap_gemm epilogue wrote.
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float* __restrict__ colsum, int ld, int rows_per_instance, int C, double count, float eps,
+                   float* __restrict__ stats) {
+    __shared__ double red[2][256];
+    const int g = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+    const int cg = C / kGroups;
+    const float2* base = reinterpret_cast<const float2*>(colsum) + static_cast<size_t>(n) * rows_per_instance * ld + g * cg;
+    // thread (rsub, c): fixed column c of the group, rows rsub, rsub + R, ... with 8 independent loads in flight
+    const int tpr = cg <= 256 ? cg : 256;                 // threads along the columns of the group
+    const int R = 256 / tpr;                              // row lanes
+    const int c = tid % tpr, rsub = tid / tpr;
+    double s = 0.0, q = 0.0;
+    if (rsub < R) {
+        for (int cc = c; cc < cg; cc += tpr) {
+            for (int row = rsub; row < rows_per_instance; row += 8 * R) {
+                float2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int rr = row + u * R;
+                    v[u] = rr < rows_per_instance ? __ldcg(base + static_cast<size_t>(rr) * ld + cc) : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { s += static_cast<double>(v[u].x); q += static_cast<double>(v[u].y); }
+            }
+        }
+    }
+    red[0][tid] = s;
+    red[1][tid] = q;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {                 // fixed tree -> deterministic
+        if (tid < w) { red[0][tid] += red[0][tid + w]; red[1][tid] += red[1][tid + w]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const double mean = red[0][0] / count;
+        double var = red[1][0] / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stats[(static_cast<size_t>(n) * kGroups + g) * 2] = static_cast<float>(mean);
+        stats[(static_cast<size_t>(n) * kGroups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+}
+
+extern "C" int dcb_group_norm_finalize(const float* colsum, int colsum_ld, int rows_per_instance, int C, int G, double count,
+                                       float eps, float* stats, void* stream) {
+    if (colsum == nullptr || stats == nullptr || rows_per_instance < 1 || C % kGroups != 0 || G < 1 || colsum_ld < C || count <= 0)
+        return set_error(DCB_ERR_INVALID, "group_norm_finalize: bad argument");
+    gn_finalize_kernel<<<dim3(kGroups, G), 256, 0, static_cast<cudaStream_t>(stream)>>>(colsum, colsum_ld, rows_per_instance, C,
+                                                                                      count, eps, stats);
+    return check_launch("group_norm_finalize");
+}
+
 extern "C" int dcb_group_norm_stats_bf16(const void* x, int C, int G, int S, float eps, float* stats, void* workspace,
                                          unsigned* counters, void* stream) {
     if (x == nullptr || stats == nullptr || workspace == nullptr || counters == nullptr)

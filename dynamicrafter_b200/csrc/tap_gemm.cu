@@ -15,408 +15,15 @@
 //               the same slot (in place), so the epilogue issues no per-thread global loads or stores and
 //               all HBM traffic of the kernel is asynchronous and fully coalesced.  Out-of-range rows and
 //               columns (ragged tiles, N < 32) are clipped by the TMA unit.
-#include <cstdlib>
-
-#include "dcb_internal.h"
-#include "ptx.cuh"
+#include "tap_gemm_kernel.cuh"
 
 namespace dcb {
 
-constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;
-// epilogue groups of 4 warps (one warp per TMEM lane quarter): 4 groups in CTA-pair mode (576 threads), else 2
-template <bool k2> struct EpiGroups { static constexpr int value = k2 ? 4 : 2; };
-template <bool k2> struct Threads { static constexpr int value = 64 + 128 * EpiGroups<k2>::value; };
-constexpr int kABytes = kBlockM * kBlockK * 2;
-// epilogue chunk = 64-byte rows (SWIZZLE_64B): 16 fp32 or 32 bf16 output columns x 128 rows = 8 KB per slot
-constexpr int kSlotBytes = kBlockM * 64;
-// slots per epilogue group: depth of the TMA store / residual-prefetch ring (pairs are the HBM-heavy big launches)
-template <bool k2> struct EpiSlots { static constexpr int value = 2; };
+// statistics-emitting instantiations live in their own translation unit (tap_gemm_cs.cu): the plain kernels carry
+// no code or register cost for the fused GroupNorm statistics
+int tap_gemm_launch_cs(int bn, bool out_bf16, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                       const CUtensorMap& tmOut, const CUtensorMap& tmRes, TapGemmParams& p, cudaStream_t s);
 
-// smem ring depth: {A 16 KB + B rows x 128 B} per stage, 32 KB of epilogue slots, <= 227 KB in total.
-// In CTA-pair mode (k2) each CTA stages only half of the B tile.
-template <int BN, bool k2> struct StageCount {
-    static constexpr int stage_bytes = kABytes + (k2 ? BN / 2 : BN) * kBlockK * 2;
-    static constexpr int epi_bytes = EpiGroups<k2>::value * EpiSlots<k2>::value * kSlotBytes;
-    static constexpr int fit = (232448 - epi_bytes - 1024 - 256) / stage_bytes;
-    static constexpr int value = fit > 8 ? 8 : fit;
-};
-
-struct TapGemmParams {
-    int D1, D2, D3, b1, b2, b3, t1, t2, t3;
-    int num_m_tiles, num_n_tiles, rows_per_tile;
-    int kchunks, ntaps;
-    int taps[DCB_MAX_TAPS][3];
-    int N, N_out;
-    const float* bias;
-    const float* group_bias;
-    int rows_per_group, ld_group_bias;
-    int has_residual, geglu, out_bf16;
-    const float* residual;
-    int ld_residual;
-    float out_scale;
-    uint32_t stage_bytes, res_bytes;
-};
-
-// Exact (erf-based) GELU, attention.py:422.  erfc(z) via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, i.e.
-// fp32 round-off level): branch-free, ~16 instructions instead of libm erff's two divergent paths.  The epilogue
-// of the K=320 GEGLU GEMMs is issue-bound on this function, not on the tensor cores.
-//   x >= 0: gelu = x - 0.5 x erfc(x/sqrt2)      x < 0: gelu = 0.5 x erfc(|x|/sqrt2)   (no cancellation)
-__device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));      // MUFU.RCP, argument in [1, inf)
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    poly *= t;
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));   // MUFU.EX2
-    e *= poly;                                                                               // erfc(z)
-    const float h = 0.5f * x * e;
-    return x >= 0.f ? x - h : h;
-}
-
-template <int BN, bool kF32, bool k2>
-__global__ void __launch_bounds__(Threads<k2>::value, 1)
-tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
-                const TapGemmParams p) {
-    constexpr int kStages = StageCount<BN, k2>::value;
-    constexpr int kSlots = EpiSlots<k2>::value;
-    constexpr int kG = EpiGroups<k2>::value;
-    constexpr int kEpiWarps = 4 * kG;
-    constexpr int kEpiBytes = kG * kSlots * kSlotBytes;
-    constexpr int kBRows = k2 ? BN / 2 : BN;               // B rows staged by this CTA
-    constexpr int kBBytes = kBRows * kBlockK * 2;
-    constexpr int kStageBytes = kABytes + kBBytes;
-    constexpr int kAccStride = (BN <= 128) ? 128 : 256;
-    constexpr int kTmemCols = 2 * kAccStride;
-    constexpr uint32_t kIdesc = make_idesc_bf16(k2 ? 2 * kBlockM : kBlockM, BN);
-    // CTA pair: rank 0 (leader) issues tcgen05.mma.cta_group::2 for the 256 x BN tile; each CTA owns 128 of its rows
-    const uint32_t rank = k2 ? cluster_ctarank() : 0u;
-
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* epi = smem + kStages * kStageBytes;                      // 1024-aligned (stage sizes are multiples)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi + kEpiBytes);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + kStages;
-    uint64_t* tfull = bars + 2 * kStages;
-    uint64_t* tempty = bars + 2 * kStages + 2;
-    uint64_t* rfull = bars + 2 * kStages + 4;                         // [group][slot]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + kG * kSlots);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    // work item = (m tile [pair], n tile); workers = CTAs (or CTA pairs) striding over the items
-    const int num_tiles = (k2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
-    const int worker = k2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-    const int nworkers = k2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-    const int kblocks = p.ntaps * p.kchunks;
-    auto m_tile_of = [&](int tile) { const int mt = tile / p.num_n_tiles; return k2 ? 2 * mt + static_cast<int>(rank) : mt; };
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-        tma_prefetch_desc(&tmOut);
-        if (p.has_residual) tma_prefetch_desc(&tmRes);
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full[s], k2 ? 2 : 1);              // pair: both producers arrive on the leader's barrier
-            mbar_init(&empty[s], 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], k2 ? 2 * kEpiWarps : kEpiWarps);
-        }
-        for (int i = 0; i < kG * kSlots; ++i) mbar_init(&rfull[i], 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) {
-        if constexpr (k2) tmem_alloc_pair<kTmemCols>(tmem_slot); else tmem_alloc<kTmemCols>(tmem_slot);
-    }
-    tc_fence_before();
-    if constexpr (k2) cluster_sync_all(); else __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer (whole warp runs the loop with
-        // warp-uniform state; one elected lane issues, so operands stay in uniform registers)
-        uint32_t it = 0;
-        for (int tile = worker; tile < num_tiles; tile += nworkers) {
-            const int m_tile = m_tile_of(tile);
-            const int n_tile = tile % p.num_n_tiles;
-            const int i1 = (m_tile % p.t1) * p.b1;
-            const int i2 = ((m_tile / p.t1) % p.t2) * p.b2;
-            const int i3 = (m_tile / (p.t1 * p.t2)) * p.b3;
-            for (int tap = 0; tap < p.ntaps; ++tap) {
-                const int c1 = i1 + p.taps[tap][0], c2 = i2 + p.taps[tap][1], c3 = i3 + p.taps[tap][2];
-                for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-                    const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    if (elect_one()) {
-                        uint8_t* sa = smem + s * kStageBytes;
-                        if constexpr (k2) {
-                            const uint32_t lfull = mapa_cluster(smem_u32(&full[s]), 0);      // leader's barrier
-                            mbar_arrive_expect_tx_cluster(lfull, p.stage_bytes);
-                            tma_load_4d_pair(sa, &tmA, lfull, kc * kBlockK, c1, c2, c3);
-                            tma_load_2d_pair(sa + kABytes, &tmB, lfull, (tap * p.kchunks + kc) * kBlockK,
-                                             n_tile * BN + static_cast<int>(rank) * kBRows);
-                        } else {
-                            mbar_arrive_expect_tx(&full[s], p.stage_bytes);
-                            tma_load_4d(sa, &tmA, &full[s], kc * kBlockK, c1, c2, c3);
-                            tma_load_2d(sa + kABytes, &tmB, &full[s], (tap * p.kchunks + kc) * kBlockK, n_tile * BN);
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (leader CTA; one elected lane issues)
-        if (rank == 0) {
-            uint32_t it = 0, tc = 0;
-            for (int tile = worker; tile < num_tiles; tile += nworkers, ++tc) {
-                const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
-                mbar_wait(&tempty[a], aph ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + a * kAccStride;
-                for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                    const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                    mbar_wait(&full[s], ph);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t sa = smem_u32(smem + s * kStageBytes);
-                        const uint64_t adesc = make_sw128_kmajor_desc(sa);
-                        const uint64_t bdesc = make_sw128_kmajor_desc(sa + kABytes);
-#pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k) {
-                            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
-                            if constexpr (k2) umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
-                            else umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
-                        }
-                        // frees the smem stage (in both CTAs of a pair) when these MMAs retire
-                        if constexpr (k2) umma_commit_pair(&empty[s]); else umma_commit(&empty[s]);
-                        // accumulator complete -> epilogue (of both CTAs)
-                        if (kb == kblocks - 1) {
-                            if constexpr (k2) umma_commit_pair(&tfull[a]); else umma_commit(&tfull[a]);
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-    } else {
-        // ------------------------------------------------------------ epilogue: 2 groups x 4 warps
-        constexpr int CW = kF32 ? 16 : 32;         // output columns per chunk (64-byte smem rows)
-        const int q = warp & 3;                    // TMEM lane quarter this warp may access
-        const int grp = (warp - 2) >> 2;           // chunk parity handled by this group
-        const int r = q * 32 + lane;               // tile row owned by this thread
-        const bool leader = (q == 0 && lane == 0);
-        const int bar_id = 1 + grp;
-        uint8_t* slots = epi + grp * kSlots * kSlotBytes;
-        uint64_t* my_rfull = rfull + grp * kSlots;
-        const int ncols = p.geglu ? BN / 2 : BN;   // output columns per tile
-        const int nch = ncols / CW;
-        const int my_nch = grp < nch ? (nch - grp + kG - 1) / kG : 0;    // chunks grp, grp+kG, ...
-        const bool tma_res = kF32 && p.has_residual;          // fp32 out: residual chunk prefetched in place by TMA
-        const int swz = (r >> 1) & 3;              // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
-        uint8_t* const row_base = nullptr;
-        (void)row_base;
-        uint32_t tc = 0, cnt = 0;
-
-        // leader only: TMA-prefetch stream of residual chunks, kSlots - 2 work items ahead of the one being processed
-        int pf_tile = worker, pf_ci = grp;
-        uint32_t pf_cnt = 0;
-        auto prefetch_upto = [&](uint32_t last_cnt) {
-            while (pf_cnt <= last_cnt && pf_tile < num_tiles) {
-                const int m_tile = m_tile_of(pf_tile);
-                const int n_tile = pf_tile % p.num_n_tiles;
-                const int s = pf_cnt & (kSlots - 1);
-                mbar_arrive_expect_tx(&my_rfull[s], p.res_bytes);
-                tma_load_4d(slots + s * kSlotBytes, &tmRes, &my_rfull[s], n_tile * ncols + pf_ci * CW,
-                            (m_tile % p.t1) * p.b1, ((m_tile / p.t1) % p.t2) * p.b2, (m_tile / (p.t1 * p.t2)) * p.b3);
-                ++pf_cnt;
-                pf_ci += kG;
-                if (pf_ci >= nch) { pf_tile += nworkers; pf_ci = grp; }
-            }
-        };
-        if (my_nch == 0) pf_tile = num_tiles;
-        const uint32_t tempty_addr0 = k2 ? mapa_cluster(smem_u32(&tempty[0]), 0) : 0u;   // leader's ring barriers
-
-        for (int tile = worker; tile < num_tiles; tile += nworkers, ++tc) {
-            const int m_tile = m_tile_of(tile);
-            const int n_tile = tile % p.num_n_tiles;
-            const int o1 = (m_tile % p.t1) * p.b1, o2 = ((m_tile / p.t1) % p.t2) * p.b2;
-            const int o3 = (m_tile / (p.t1 * p.t2)) * p.b3;
-            const float* gb = nullptr;
-            const float* res_row = nullptr;        // bf16-out path: residual row read straight from global
-            if (p.group_bias != nullptr || (!kF32 && p.has_residual)) {
-                const int g1 = o1 + r % p.b1, g2 = o2 + (r / p.b1) % p.b2, g3 = o3 + r / (p.b1 * p.b2);
-                if (r < p.rows_per_tile && g1 < p.D1 && g2 < p.D2 && g3 < p.D3) {
-                    const long long grow = (static_cast<long long>(g3) * p.D2 + g2) * p.D1 + g1;
-                    if (p.group_bias != nullptr) gb = p.group_bias + (grow / p.rows_per_group) * p.ld_group_bias;
-                    if (!kF32 && p.has_residual) res_row = p.residual + grow * p.ld_residual;
-                }
-            }
-            const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
-            bool acc_ready = false;
-            const uint32_t t_row = tmem_base + a * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-
-            for (int ci = grp; ci < nch; ci += kG, ++cnt) {
-                const int s = cnt & (kSlots - 1);
-                uint8_t* slot = slots + s * kSlotBytes;
-                const int col0 = n_tile * ncols + ci * CW;              // first output column of this chunk
-                if (!acc_ready) {
-                    mbar_wait(&tfull[a], aph);
-                    tc_fence_after();
-                    acc_ready = true;
-                }
-                if (tma_res) {
-                    if (leader) {
-                        tma_store_wait_read<0>();                // slot of item cnt + 1 was read by the latest store
-                        prefetch_upto(cnt + 1);
-                    }
-                    mbar_wait(&my_rfull[s], (cnt / kSlots) & 1);
-                }
-                // (no TMA residual: the slot was proven free before the previous chunk's barrier, see below)
-                uint8_t* orow = slot + r * 64;                          // 64-byte rows, SWIZZLE_64B
-                // 16 columns at a time (keeps the 576-thread CTA under 113 registers per thread)
-#pragma unroll
-                for (int hf = 0; hf < CW / 16; ++hf) {
-                    const int cb = col0 + hf * 16;
-                    float o[16];
-                    if (!kF32 && p.has_residual) {
-                        if (res_row != nullptr && cb + 16 <= p.N_out) {
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
-                                const float4 t = __ldg(reinterpret_cast<const float4*>(res_row + cb + j));
-                                o[j] = t.x; o[j + 1] = t.y; o[j + 2] = t.z; o[j + 3] = t.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                o[j] = (res_row != nullptr && cb + j < p.N_out) ? __ldg(res_row + cb + j) : 0.f;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = 0.f;
-                    }
-                    uint32_t v[16];
-                    tmem_ld16(t_row + ci * CW + hf * 16, v);
-                    if (!kF32 && p.geglu) {
-                        uint32_t g[16];
-                        tmem_ld16(t_row + BN / 2 + ci * CW + hf * 16, g);
-                        tmem_ld_wait();
-                        const int wn = n_tile * BN + ci * CW + hf * 16;   // packed weight column of the value half
-                        const float s_ = p.out_scale;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
-                            if (p.bias != nullptr) {
-                                bv = __ldg(reinterpret_cast<const float4*>(p.bias + wn + j));
-                                bg = __ldg(reinterpret_cast<const float4*>(p.bias + wn + BN / 2 + j));
-                            }
-                            o[j] += (__uint_as_float(v[j]) * s_ + bv.x) * gelu_erf(__uint_as_float(g[j]) * s_ + bg.x);
-                            o[j + 1] += (__uint_as_float(v[j + 1]) * s_ + bv.y) * gelu_erf(__uint_as_float(g[j + 1]) * s_ + bg.y);
-                            o[j + 2] += (__uint_as_float(v[j + 2]) * s_ + bv.z) * gelu_erf(__uint_as_float(g[j + 2]) * s_ + bg.z);
-                            o[j + 3] += (__uint_as_float(v[j + 3]) * s_ + bv.w) * gelu_erf(__uint_as_float(g[j + 3]) * s_ + bg.w);
-                        }
-                    } else {
-                        tmem_ld_wait();
-                        if (p.out_scale != 1.0f) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) o[j] = fmaf(__uint_as_float(v[j]), p.out_scale, o[j]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) o[j] += __uint_as_float(v[j]);
-                        }
-                        if (p.bias != nullptr) {
-                            if (cb + 16 <= p.N_out) {
-#pragma unroll
-                                for (int j = 0; j < 16; j += 4) {
-                                    const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + cb + j));
-                                    o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w;
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j)
-                                    if (cb + j < p.N_out) o[j] += __ldg(p.bias + cb + j);
-                            }
-                        }
-                    }
-                    if (gb != nullptr) {
-                        if (cb + 16 <= p.N_out && (reinterpret_cast<uintptr_t>(gb + cb) & 15) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
-                                const float4 t = __ldg(reinterpret_cast<const float4*>(gb + cb + j));
-                                o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (cb + j < p.N_out) o[j] += __ldg(gb + cb + j);
-                        }
-                    }
-                    if constexpr (kF32) {
-                        if (tma_res) {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const float4 t = *reinterpret_cast<const float4*>(orow + ((c ^ swz) << 4));
-                                o[4 * c] += t.x; o[4 * c + 1] += t.y; o[4 * c + 2] += t.z; o[4 * c + 3] += t.w;
-                            }
-                        }
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            *reinterpret_cast<float4*>(orow + ((c ^ swz) << 4)) =
-                                make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            uint4 pk;
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * c], o[8 * c + 1]);
-                            __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * c + 2], o[8 * c + 3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * c + 4], o[8 * c + 5]);
-                            __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * c + 6], o[8 * c + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            *reinterpret_cast<uint4*>(orow + (((hf * 2 + c) ^ swz) << 4)) = pk;
-                        }
-                    }
-                }
-                fence_proxy_async();                                     // generic-proxy writes -> visible to TMA
-                // the next chunk writes the other slot: its last store (issued one chunk ago) must have read it;
-                // checking before this barrier makes that visible to the whole group without a second barrier
-                if (!tma_res && leader) tma_store_wait_read<kSlots - 2>();
-                named_bar_sync(bar_id, 128);
-                if (leader) {
-                    tma_store_4d(&tmOut, slot, col0, o1, o2, o3);
-                    tma_store_commit();
-                }
-            }
-            if (!acc_ready) {                                            // group without chunks still tracks the ring
-                mbar_wait(&tfull[a], aph);
-                tc_fence_after();
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if constexpr (k2) mbar_arrive_cluster(tempty_addr0 + a * 8); else mbar_arrive(&tempty[a]);
-            }
-        }
-        if (leader) tma_store_wait_all<0>();
-    }
-
-    tc_fence_before();
-    if constexpr (k2) cluster_sync_all(); else __syncthreads();
-    if (warp == 1) {
-        if constexpr (k2) tmem_dealloc_pair<kTmemCols>(tmem_base); else tmem_dealloc<kTmemCols>(tmem_base);
-    }
-}
-
-// ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -451,54 +58,6 @@ static int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, CU
                      promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return set_error(DCB_ERR_CUDA, "cuTensorMapEncodeTiled failed (rc=%d)", (int)rc);
     return DCB_OK;
-}
-
-template <int BN, bool kF32, bool k2>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
-                  TapGemmParams& p, cudaStream_t stream) {
-    constexpr int kBRows = k2 ? BN / 2 : BN;
-    constexpr int kStageBytes = kABytes + kBRows * kBlockK * 2;
-    constexpr int smem_bytes = StageCount<BN, k2>::value * kStageBytes + StageCount<BN, k2>::epi_bytes + 1024 + 256;
-    static_assert(smem_bytes <= 232448, "shared memory budget");
-    static_assert(StageCount<BN, k2>::value >= 4, "pipeline depth");
-    static_assert((2 * StageCount<BN, k2>::value + 4 + EpiGroups<k2>::value * EpiSlots<k2>::value) * 8 + 4 <= 256, "barrier area");
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BN, kF32, k2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             smem_bytes);
-        if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = true;
-    }
-    p.stage_bytes = static_cast<uint32_t>(p.rows_per_tile * kBlockK * 2 + kBRows * kBlockK * 2);
-    p.res_bytes = static_cast<uint32_t>(p.rows_per_tile * 64);
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
-    cfg.blockDim = dim3(Threads<k2>::value);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    if (k2) {
-        const int items = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
-        const int pairs = items < num_sms() / 2 ? items : num_sms() / 2;
-        cfg.gridDim = dim3(2 * pairs);
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-    } else {
-        const int tiles = p.num_m_tiles * p.num_n_tiles;
-        cfg.gridDim = dim3(tiles < num_sms() ? tiles : num_sms());
-    }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tap_gemm_kernel<BN, kF32, k2>, tmA, tmB, tmOut, tmRes, p);
-    if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "tap_gemm launch: %s", cudaGetErrorString(e));
-    return DCB_OK;
-}
-
-template <int BN, bool kF32>
-static int launch_mode(bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                       const CUtensorMap& tmRes, TapGemmParams& p, cudaStream_t s) {
-    return pair ? launch<BN, kF32, true>(tmA, tmB, tmOut, tmRes, p, s) : launch<BN, kF32, false>(tmA, tmB, tmOut, tmRes, p, s);
 }
 
 static int pair_mode_env() {       // DCB_GEMM_PAIR=0 forces single-CTA tiles, =1 forces CTA pairs, unset: heuristic
@@ -635,14 +194,18 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
     p.geglu = a->geglu;
     p.out_bf16 = obf ? 1 : 0;
     p.out_scale = a->out_scale;
+    p.colsum = a->colsum;
+    p.colsum_ld = a->colsum_ld;
+    p.seg_rows = a->b1 * a->b2;                                   // tile rows per D3 slice
+    p.seg_lw = p.seg_rows < 32 ? p.seg_rows : 32;                 // rows reduced inside one warp
+    p.seg_sub = p.seg_rows <= 32 ? 1 : p.seg_rows / 32;           // 32-row sub-partials per (slice, spatial tile)
+    if (a->colsum != nullptr) {
+        if (a->geglu || (p.seg_rows != 8 && p.seg_rows != 16 && p.seg_rows % 32 != 0) || p.seg_rows * a->b3 != p.rows_per_tile ||
+            a->colsum_ld < n_out)
+            return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: colsum needs b1*b2 in {8,16,32k} (got %d) and no geglu", p.seg_rows);
+    }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (a->geglu && !obf) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: geglu writes bf16 only");
-    if (obf) {
-        if (bn == 256) return launch_mode<256, false>(pair, tmA, tmB, tmOut, tmRes, p, s);
-        return bn == 160 ? launch_mode<160, false>(pair, tmA, tmB, tmOut, tmRes, p, s)
-                         : launch_mode<128, false>(pair, tmA, tmB, tmOut, tmRes, p, s);
-    }
-    if (bn == 256) return launch_mode<256, true>(pair, tmA, tmB, tmOut, tmRes, p, s);
-    return bn == 160 ? launch_mode<160, true>(pair, tmA, tmB, tmOut, tmRes, p, s)
-                     : launch_mode<128, true>(pair, tmA, tmB, tmOut, tmRes, p, s);
+    if (a->colsum != nullptr) return tap_gemm_launch_cs(bn, obf, pair, tmA, tmB, tmOut, tmRes, p, s);
+    return launch_all<false>(bn, obf, pair, tmA, tmB, tmOut, tmRes, p, s);
 }

@@ -19,6 +19,10 @@ _LOWP = set(_os.environ.get("DCB_BF16_INTERNAL", "tconv,res").split(","))
 BF16_TCONV = "tconv" in _LOWP or "all" in _LOWP
 BF16_RES = "res" in _LOWP or "all" in _LOWP
 BF16_VAE = "vae" in _LOWP or "all" in _LOWP
+# Fused GroupNorm statistics (conv / temporal-conv epilogues emit per-column sums, a tiny finalize kernel replaces the
+# statistics pass).  Measured on B200 at the 512 config: GroupNorm -0.9 ms but GEMM epilogues +1.3 ms per step, so it
+# is OFF by default (DCB_FUSED_GN_STATS=1 enables it); see DESIGN.md.
+FUSED_GN_STATS = _os.environ.get("DCB_FUSED_GN_STATS", "0") == "1"
 
 
 def _pad64(c):

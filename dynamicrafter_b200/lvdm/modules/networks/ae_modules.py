@@ -90,9 +90,10 @@ class ResnetBlock(PackedModule):
         sc = "ws" in p
         res = ops.group_norm(h.x, nf, S, self.norm1.weight, self.norm1.bias, self.norm1.eps, silu=True, want_raw=sc)
         y, raw = res if sc else (res, None)
-        h1 = ops.conv3x3(y, nf, h.H, h.W, p["w1"], bias=p["b1"], f32=not _packing.BF16_VAE,
-                         bf16=_packing.BF16_VAE)
-        y2 = ops.group_norm(h1, nf, S, self.norm2.weight, self.norm2.bias, self.norm2.eps, silu=True)
+        res1 = ops.conv3x3(y, nf, h.H, h.W, p["w1"], bias=p["b1"], f32=not _packing.BF16_VAE,
+                           bf16=_packing.BF16_VAE, stats=_packing.FUSED_GN_STATS)
+        h1, cs1 = res1 if _packing.FUSED_GN_STATS else (res1, None)
+        y2 = ops.group_norm(h1, nf, S, self.norm2.weight, self.norm2.bias, self.norm2.eps, silu=True, colsums=cs1)
         xs = ops.linear(raw, p["ws"], bias=p["bs"], f32=True, bf16=False) if sc else h.x
         return h.like(ops.conv3x3(y2, nf, h.H, h.W, p["w2"], bias=p["b2"], residual=xs))
 

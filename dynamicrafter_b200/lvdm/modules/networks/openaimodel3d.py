@@ -139,17 +139,20 @@ class TemporalConvBlock(PackedModule):
         return {"w": [pack_tconv3(s[-1].weight) for s in self._stages()],
                 "b": [_f32(s[-1].bias) for s in self._stages()]}
 
-    def _fwd(self, h):
+    def _fwd(self, h, colsums=None):
+        """colsums: fused statistics of h.x from the GEMM that produced it (per-frame slices), or None."""
         p = self.packed()
         B, T, S = h.B, h.T, h.H * h.W
         z = h.x
         for i, st in enumerate(self._stages()):
             gn = st[0]
-            y = ops.group_norm(z, B, T * S, gn.weight, gn.bias, gn.eps, silu=True)
+            y = ops.group_norm(z, B, T * S, gn.weight, gn.bias, gn.eps, silu=True, colsums=colsums)
             last = i == 3
             lowp = _packing.BF16_TCONV and not last
-            z = ops.tconv3(y, B, T, S, p["w"][i], bias=p["b"][i], residual=h.x if last else None,
-                           f32=not lowp, bf16=lowp)
+            want = _packing.FUSED_GN_STATS and not last          # also emit the next GroupNorm's column sums
+            res = ops.tconv3(y, B, T, S, p["w"][i], bias=p["b"][i], residual=h.x if last else None,
+                             f32=not lowp, bf16=lowp, stats=want)
+            z, colsums = res if want else (res, None)
         return h.like(z)
 
     def forward(self, x):
@@ -207,15 +210,20 @@ class ResBlock(PackedModule, TimestepBlock):
         has_skip_conv = "ws" in p
         res = ops.group_norm(h.x, nf, S, g1.weight, g1.bias, g1.eps, x2=skip, silu=True, want_raw=has_skip_conv)
         y, raw = res if has_skip_conv else (res, None)
-        h1 = ops.conv3x3(y, nf, h.H, h.W, p["w1"], bias=p["b1"], group_bias=emb_out, rows_per_group=rows_per_emb,
-                         f32=not _packing.BF16_RES, bf16=_packing.BF16_RES)
+        # each conv also emits the column sums its consumer GroupNorm needs (fused statistics, no extra pass)
+        fuse = _packing.FUSED_GN_STATS
+        res1 = ops.conv3x3(y, nf, h.H, h.W, p["w1"], bias=p["b1"], group_bias=emb_out, rows_per_group=rows_per_emb,
+                           f32=not _packing.BF16_RES, bf16=_packing.BF16_RES, stats=fuse)
+        h1, cs1 = res1 if fuse else (res1, None)
         g2 = self.out_layers[0]
-        y2 = ops.group_norm(h1, nf, S, g2.weight, g2.bias, g2.eps, silu=True)
+        y2 = ops.group_norm(h1, nf, S, g2.weight, g2.bias, g2.eps, silu=True, colsums=cs1)
         xs = ops.linear(raw, p["ws"], bias=p["bs"], f32=True, bf16=False) if has_skip_conv else h.x
-        h2 = ops.conv3x3(y2, nf, h.H, h.W, p["w2"], bias=p["b2"], residual=xs)
+        tconv = self.use_temporal_conv and temporal
+        res2 = ops.conv3x3(y2, nf, h.H, h.W, p["w2"], bias=p["b2"], residual=xs, stats=tconv and fuse)
+        h2, cs2 = res2 if (tconv and fuse) else (res2, None)
         out = h.like(h2)
-        if self.use_temporal_conv and temporal:
-            out = self.temopral_conv._fwd(out)
+        if tconv:
+            out = self.temopral_conv._fwd(out, colsums=cs2)
         return out
 
     def forward(self, x, emb, batch_size=None):

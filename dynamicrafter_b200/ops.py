@@ -48,9 +48,33 @@ def choose_box(D1, D2, D3):
     return best[1]
 
 
+class ColSums:
+    """Per-column (sum, sumsq) partials of a GEMM output, written by the GEMM epilogue (fused GroupNorm statistics).
+    partial: fp32 [D3 * rows_per_slice, C, 2]; slice_rows = activation rows per D3 slice."""
+    __slots__ = ("partial", "rows_per_slice", "slice_rows", "C")
+
+    def __init__(self, partial, rows_per_slice, slice_rows, C):
+        self.partial, self.rows_per_slice, self.slice_rows, self.C = partial, rows_per_slice, slice_rows, C
+
+
+def colsum_supported(dims):
+    b = choose_box(*dims)
+    seg = b[0] * b[1]
+    return seg in (8, 16) or seg % 32 == 0
+
+
+def _make_colsums(dims, N, dev):
+    b = choose_box(*dims)
+    seg = b[0] * b[1]
+    t12 = -(-dims[0] // b[0]) * -(-dims[1] // b[1])
+    rps = t12 * max(1, seg // 32)
+    part = torch.empty((dims[2] * rps, N, 2), dtype=F32, device=dev)
+    return ColSums(part, rps, dims[0] * dims[1], N)
+
+
 def tap_gemm(a, dims, strides, adims, taps, w, N, *, bias=None, group_bias=None, rows_per_group=0,
              residual=None, geglu=False, out_f32=None, out_bf16=None, ld_out=None, out_scale=1.0,
-             block_n=0, box=None):
+             block_n=0, box=None, colsum=None):
     """Raw launch.  a: bf16 tensor; dims=(D1,D2,D3) output domain; strides=(s1,s2,s3) element strides
     of A; adims=(A1,A2,A3) extents of A; taps=[(o1,o2,o3),...]; w: bf16 [N, ntaps*C]."""
     require_cuda(a, w, bias, group_bias, residual, out_f32, out_bf16)
@@ -83,6 +107,8 @@ def tap_gemm(a, dims, strides, adims, taps, w, N, *, bias=None, group_bias=None,
     args.out_bf16 = None if out_bf16 is None else out_bf16.data_ptr()
     args.ld_out = ld_out
     args.out_scale = out_scale
+    args.colsum = None if colsum is None else colsum.partial.data_ptr()
+    args.colsum_ld = 0 if colsum is None else colsum.C
     check(_lib.lib().dcb_tap_gemm(ctypes.byref(args), _stream()), "dcb_tap_gemm")
 
 
@@ -125,26 +151,30 @@ TAPS_T3 = [(0, dt, 0) for dt in (-1, 0, 1)]
 
 
 def conv3x3(a, nf, H, W, w, *, bias=None, residual=None, group_bias=None, rows_per_group=0,
-            f32=True, bf16=False, out=None, N=None):
+            f32=True, bf16=False, out=None, N=None, stats=False):
     """a: bf16 [nf*H*W, C] channels-last frames; w: bf16 [N, 9*C] ordered (ky, kx, c). Stride 1, pad 1."""
     C = a.shape[1]
     assert a.stride(1) == 1 and a.stride(0) == C and w.shape[1] == 9 * C
     N = N or w.shape[0]
     of, ob, ld = _outputs(nf * H * W, N, out, f32, bf16, a.device)
+    cs = _make_colsums((W, H, nf), N, a.device) if (stats and colsum_supported((W, H, nf))) else None
     tap_gemm(a, (W, H, nf), (C, C * W, C * W * H), (W, H, nf), TAPS_3X3, w, N, bias=bias, residual=residual,
-             group_bias=group_bias, rows_per_group=rows_per_group, out_f32=of, out_bf16=ob, ld_out=ld)
-    return of if (of is not None and ob is None) else (ob if of is None else (of, ob))
+             group_bias=group_bias, rows_per_group=rows_per_group, out_f32=of, out_bf16=ob, ld_out=ld, colsum=cs)
+    res = of if of is not None else ob
+    return (res, cs) if stats else res
 
 
-def tconv3(a, B, T, HW, w, *, bias=None, residual=None, f32=True, bf16=False, out=None):
+def tconv3(a, B, T, HW, w, *, bias=None, residual=None, f32=True, bf16=False, out=None, stats=False):
     """Temporal (3,1,1) conv.  a: bf16 [B*T*HW, C]; w: bf16 [N, 3*C] ordered (kt, c). Pad 1 frame."""
     C = a.shape[1]
     assert a.stride(1) == 1 and a.stride(0) == C and w.shape[1] == 3 * C
     N = w.shape[0]
     of, ob, ld = _outputs(B * T * HW, N, out, f32, bf16, a.device)
+    cs = _make_colsums((HW, T, B), N, a.device) if (stats and colsum_supported((HW, T, B))) else None
     tap_gemm(a, (HW, T, B), (C, C * HW, C * HW * T), (HW, T, B), TAPS_T3, w, N, bias=bias, residual=residual,
-             out_f32=of, out_bf16=ob, ld_out=ld)
-    return of if (of is not None and ob is None) else (ob if of is None else (of, ob))
+             out_f32=of, out_bf16=ob, ld_out=ld, colsum=cs)
+    res = of if of is not None else ob
+    return (res, cs) if stats else res
 
 
 # ------------------------------------------------------------------------------------------ norms
@@ -177,7 +207,19 @@ def _c_f(v):
     return ctypes.c_float(float(v))
 
 
-def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False, want_norm=True):
+def _stats_from_colsums(cs, G, S, C, eps, dev):
+    """Finalise fused statistics: instance g owns S / slice_rows consecutive D3 slices of the partial buffer."""
+    assert S % cs.slice_rows == 0 and cs.C == C
+    rpi = (S // cs.slice_rows) * cs.rows_per_slice
+    assert cs.partial.shape[0] == G * rpi, (cs.partial.shape, G, rpi)
+    stats = torch.empty((G, 32, 2), dtype=F32, device=dev)
+    check(_lib.lib().dcb_group_norm_finalize(ptr(cs.partial), _c_i(C), _c_i(rpi), _c_i(C), _c_i(G),
+                                             ctypes.c_double(float(S) * (C // 32)), _c_f(eps), ptr(stats), _stream()),
+          "dcb_group_norm_finalize")
+    return stats
+
+
+def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False, want_norm=True, colsums=None):
     """x1: fp32 [G*S, C1] (+ x2 [G*S, C2] concatenated on channels) -> bf16 normalised operand
     (and/or bf16 raw copy of the concat)."""
     require_cuda(x1, x2, gamma, beta)
@@ -185,10 +227,13 @@ def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False
         # block-internal activation kept in bf16 by its producer: single source, normalised output only
         assert x2 is None and not want_raw and x1.is_contiguous() and x1.shape[0] == G * S
         C, dev, L = x1.shape[1], x1.device, _lib.lib()
-        ws, cnt = _gn_scratch(dev, G)
-        stats = torch.empty((G, 32, 2), dtype=F32, device=dev)
-        check(L.dcb_group_norm_stats_bf16(ptr(x1), _c_i(C), _c_i(G), _c_i(S), _c_f(eps), ptr(stats), ptr(ws), ptr(cnt),
-                                          _stream()), "dcb_group_norm_stats_bf16")
+        if colsums is not None:
+            stats = _stats_from_colsums(colsums, G, S, C, eps, dev)
+        else:
+            ws, cnt = _gn_scratch(dev, G)
+            stats = torch.empty((G, 32, 2), dtype=F32, device=dev)
+            check(L.dcb_group_norm_stats_bf16(ptr(x1), _c_i(C), _c_i(G), _c_i(S), _c_f(eps), ptr(stats), ptr(ws), ptr(cnt),
+                                              _stream()), "dcb_group_norm_stats_bf16")
         y = torch.empty((G * S, C), dtype=BF16, device=dev)
         check(L.dcb_group_norm_apply_bf16(ptr(x1), _c_i(C), _c_i(G), _c_i(S), ptr(stats), ptr(gamma), ptr(beta),
                                           _c_i(1 if silu else 0), ptr(y), _stream()), "dcb_group_norm_apply_bf16")
@@ -201,7 +246,10 @@ def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False
     dev = x1.device
     L = _lib.lib()
     y = raw = stats = None
-    if want_norm:
+    if want_norm and colsums is not None and x2 is None:
+        stats = _stats_from_colsums(colsums, G, S, C1, eps, dev)
+        y = torch.empty((G * S, C1), dtype=BF16, device=dev)
+    elif want_norm:
         ws, cnt = _gn_scratch(dev, G)
         stats = torch.empty((G, 32, 2), dtype=F32, device=dev)
         check(L.dcb_group_norm_stats(ptr(x1), ptr(x2), _c_i(C1), _c_i(C2), _c_i(G), _c_i(S), _c_f(eps), ptr(stats),

@@ -82,6 +82,12 @@ typedef struct {
     void* out_bf16;
     int32_t ld_out;
     float out_scale;          /* applied to acc before bias (1.0 = none) */
+    /* Optional fused GroupNorm statistics of the OUTPUT (NULL = off): per (D3 slice d, spatial tile st of the t1*t2
+     * tiles of a slice, 32-row sub-tile u) the kernel writes (sum, sum of squares) of every output column to
+     * colsum[(((d * t1*t2 + st) * sub) + u) * colsum_ld + n] as float2, sub = max(1, b1*b2/32).  Requires
+     * b1*b2 in {8, 16, 32, 64, 96, 128}.  dcb_group_norm_finalize turns them into (mean, rstd). */
+    float* colsum;
+    int32_t colsum_ld;
 } dcb_tap_gemm_args;
 
 int dcb_tap_gemm(const dcb_tap_gemm_args* args, void* stream);
@@ -103,6 +109,10 @@ int dcb_group_norm_stats(const float* x1, const float* x2, int C1, int C2, int G
 int dcb_group_norm_apply(const float* x1, const float* x2, int C1, int C2, int G, int S,
                          const float* stats, const float* gamma, const float* beta, int silu_act,
                          void* y_bf16, void* raw_bf16, void* stream);
+/* (mean, rstd) from the column-sum partials a dcb_tap_gemm launch wrote (colsum): instance g owns
+ * `rows_per_instance` consecutive partial rows; count = elements per (instance, group). */
+int dcb_group_norm_finalize(const float* colsum, int colsum_ld, int rows_per_instance, int C, int G, double count,
+                            float eps, float* stats, void* stream);
 /* Same statistics / apply for a bf16 source (block-internal activations the producer GEMM wrote as bf16):
  * single source, C % 8 == 0. */
 int dcb_group_norm_stats_bf16(const void* x, int C, int G, int S, float eps, float* stats, void* workspace,

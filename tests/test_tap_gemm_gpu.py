@@ -111,3 +111,38 @@ def test_gemm_throughput_smoke():
     print(f"\ntap_gemm {M}x{N}x{K}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
     ref = a.float() @ w.float().t()
     _close(out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("nf,H,W,C,N,G", [(4, 40, 64, 64, 320, 4), (4, 10, 16, 64, 128, 4), (16, 5, 8, 64, 64, 16),
+                                          (16, 5, 8, 64, 64, 1), (32, 4, 4, 64, 96, 2), (3, 20, 32, 64, 160, 3)])
+def test_fused_groupnorm_statistics_conv(nf, H, W, C, N, G):
+    """Column sums written by the conv epilogue -> (mean, rstd) identical to statistics of the stored output."""
+    from dynamicrafter_b200 import ops
+    x = _mk((nf, H, W, C), 21)
+    wt = _mk((N, C, 3, 3), 22, (9 * C) ** -0.5)
+    wp = wt.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    bias = torch.randn(N, device="cuda")
+    for bf16 in (False, True):
+        out, cs = ops.conv3x3(x.reshape(-1, C), nf, H, W, wp, bias=bias, f32=not bf16, bf16=bf16, stats=True)
+        assert cs is not None
+        S = nf * H * W // G
+        stats = ops._stats_from_colsums(cs, G, S, N, 1e-5, out.device)
+        o = out.float().reshape(G, S, 32, N // 32).permute(0, 2, 1, 3).reshape(G, 32, -1)
+        mean, var = o.mean(-1), o.var(-1, unbiased=False)
+        tol = 2e-3 if bf16 else 2e-5          # bf16 output is rounded after the statistics were taken
+        assert (stats[:, :, 0] - mean).abs().max().item() < tol * (1 + mean.abs().max().item())
+        assert ((stats[:, :, 1] - (var + 1e-5).rsqrt()).abs() / (var + 1e-5).rsqrt()).max().item() < (5e-3 if bf16 else 1e-4)
+
+
+@pytest.mark.parametrize("B,T,HW,C,N", [(2, 16, 40, 64, 128), (1, 16, 2560, 64, 64), (2, 16, 160, 64, 320)])
+def test_fused_groupnorm_statistics_tconv(B, T, HW, C, N):
+    from dynamicrafter_b200 import ops
+    x = _mk((B * T * HW, C), 23)
+    wp = _mk((N, 3 * C), 24, (3 * C) ** -0.5)
+    out, cs = ops.tconv3(x, B, T, HW, wp, stats=True)
+    assert cs is not None
+    stats = ops._stats_from_colsums(cs, B, T * HW, N, 1e-5, out.device)
+    o = out.reshape(B, T * HW, 32, N // 32).permute(0, 2, 1, 3).reshape(B, 32, -1)
+    mean, var = o.mean(-1), o.var(-1, unbiased=False)
+    assert (stats[:, :, 0] - mean).abs().max().item() < 2e-5
+    assert ((stats[:, :, 1] - (var + 1e-5).rsqrt()).abs() / (var + 1e-5).rsqrt()).max().item() < 1e-4
