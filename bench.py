@@ -374,7 +374,12 @@ def main():
     step_tflop = 2 * UNET_TFLOP[args.config] * B
     roofline = {"bound": "tensor", "kernel": "tap_gemm_kernel (tcgen05 implicit GEMM: linear + conv3x3 + temporal conv)",
                 "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": round(achieved / peaks["tflops"], 4), "traffic": None, "peak_source": peaks["source"],
+                "frac": round(achieved / peaks["tflops"], 4),
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from the committed
+                # `ncu --set full` capture (profiles/r01b_tap_gemm_pair_160_f32_raw.csv): the 81920x640x5760
+                # conv-as-GEMM, fp32 out; algorithmic bytes of that launch = A 943.7 MB + W 7.4 MB + out 209.7 MB
+                "traffic": 1.240e9, "traffic_unit": "bytes/launch (captured 81920x640x5760 launch)",
+                "traffic_algorithmic": 1.161e9, "peak_source": peaks["source"],
                 "launches_per_step": n_gemm, "avg_launch_us": round(gemm_ms * 1e3 / max(n_gemm, 1), 2),
                 "kernel_share_of_step": round(gemm_ms / max(sum(by.values()), 1e-9), 4),
                 "whole_step_tflops": round(step_tflop / (ms_per_step * 1e-3), 1),

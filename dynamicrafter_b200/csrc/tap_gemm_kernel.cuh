@@ -6,15 +6,23 @@
 // (3 taps over frames): the A operand is fetched by TMA as a box of a 4-D channels-last tensor and a
 // tap is just a coordinate shift of that box; TMA's out-of-bounds zero fill is the conv padding.
 //
-// CTA = 320 threads, one CTA per SM, persistent over tiles (N fastest so an A tile is re-read from L2):
-//   warp 0      TMA producer: {A 128x64, B BNx64} bf16 stages, SWIZZLE_128B, full/empty mbarrier ring
-//   warp 1      TMEM owner + single-thread tcgen05.mma issuer (128 x BN x 16), 2-deep TMEM accumulator ring
-//   warps 2..9  epilogue, two groups of 4 warps (each group covers the 128 TMEM lanes and takes every other
-//               32-column chunk): tcgen05.ld -> fused bias / per-video embedding / exact-erf GEGLU / residual
-//               -> swizzled smem slot -> TMA tile store.  The fp32 residual chunk is PREFETCHED by TMA into
-//               the same slot (in place), so the epilogue issues no per-thread global loads or stores and
-//               all HBM traffic of the kernel is asynchronous and fully coalesced.  Out-of-range rows and
-//               columns (ragged tiles, N < 32) are clipped by the TMA unit.
+// Two launch modes of the same template (k2):
+//   single   one persistent CTA per SM, 320 threads, 128 x BN tile, cta_group::1.
+//   pair     clusters of 2 CTAs (cta_group::2), 576 threads each, one 256 x BN tile per pair: every CTA stages its own
+//            128 A rows and HALF of the B tile, the leader CTA issues the MMAs for both and multicasts the commit, so
+//            shared-memory operand traffic per FLOP halves (a single CTA at BN=128 is smem-bandwidth bound at ~50 %
+//            of the tensor pipe).  Persistent over tiles, N fastest so an A tile is re-read from L2.
+// Warp roles:
+//   warp 0      TMA producer: {A 128x64, B rows x 64} bf16 stages, SWIZZLE_128B, full/empty mbarrier ring
+//   warp 1      TMEM owner + tcgen05.mma issuer (the whole warp runs the loop, elect.sync picks the issuing lane so
+//               the loop stays warp-uniform), 2-deep TMEM accumulator ring
+//   warps 2..   epilogue, 2 (single) or 4 (pair) groups of 4 warps; a group covers the 128 TMEM lanes and takes
+//               every EpiGroups-th 16-column step: tcgen05.ld -> fused bias / per-video embedding / GEGLU /
+//               residual -> swizzled smem slot (64-byte rows) -> TMA tile store.  The fp32 residual chunk is
+//               PREFETCHED by TMA into the same slot (in place), so the epilogue issues no per-thread global loads
+//               or stores and all HBM traffic of the kernel is asynchronous and fully coalesced.  Out-of-range rows
+//               and columns (ragged tiles, N < 32) are clipped by the TMA unit.
+//   kCS         optional fused GroupNorm statistics (per-tile column sums of the stored values); separate TU.
 #pragma once
 #include <cstdlib>
 
