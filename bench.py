@@ -302,7 +302,9 @@ def main():
     smp.make_schedule(sm["S"], ddim_discretize=sm["timestep_spacing"], ddim_eta=sm["eta"], verbose=False)
     steps_desc = list(reversed(list(smp.ddim_timesteps)))
     total = len(steps_desc)
-    kw = dict(unconditional_guidance_scale=sm["cfg"], unconditional_conditioning=uc, fs=fs,
+    # DCB_BENCH_CFG: tuning-only override (1.0 = single-branch forward, to compare per-shape times at half the rows)
+    kw = dict(unconditional_guidance_scale=float(os.environ.get("DCB_BENCH_CFG", sm["cfg"])),
+              unconditional_conditioning=uc, fs=fs,
               guidance_rescale=sm["guidance_rescale"])
 
     def one_step(x, i, c=cond, extra=kw):

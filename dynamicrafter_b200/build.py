@@ -19,6 +19,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC",
          "-I", os.path.join(os.path.dirname(HERE), "include")]
+FLAGS += os.environ.get("DCB_NVCC_EXTRA", "").split()          # e.g. -DDCB_TRACE for tools/trace_gemm.py
 
 
 def _sources():

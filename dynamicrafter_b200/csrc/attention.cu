@@ -235,6 +235,182 @@ flash_attention_kernel(const FlashParams p) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// Cross-attention against SHORT key sets (text 77 + image 16 tokens, attention.py:89-94,129-142): the whole K/V of
+// both segments of one (batch, head) sits in shared memory (24 KB), so there is no online softmax and no block-level
+// synchronisation after the prologue: the job is a stream over Q and O (HBM bound, 4 * 64 * 93 FLOP per 256 bytes).
+// Each warp owns 16-row query tiles, prefetches them two tiles ahead with cp.async into a private 3-stage ring,
+// computes S for all keys of a segment in registers, normalises P before the P V product (so one accumulator
+// serves both segments) and writes O through its Q stage with 16-byte stores.
+// NT0 / NT1: 8-key tiles of the two segments (even; keys past nk are zero-filled and masked).
+// -------------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ void cross_segment(const __nv_bfloat16* tK, const __nv_bfloat16* tV, int nk, float scale_log2,
+                                              float seg_scale, const uint32_t (&qf)[4][4], float (&out)[8][4], int lane) {
+    const int t = lane & 3;
+    float s[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            uint32_t b0, b1, b2, b3;
+            const int r = nt * 8 + (lane & 7), c = kp * 4 + (lane >> 3);
+            ldsm_x4(smem_addr(tK + swz(r, c)), b0, b1, b2, b3);
+            mma_bf16(s[nt], qf[kp * 2], b0, b1);
+            mma_bf16(s[nt], qf[kp * 2 + 1], b2, b3);
+        }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int key = nt * 8 + 2 * t;
+        if (key >= nk) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+        if (key + 1 >= nk) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+        mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+    float rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+        mx[hh] *= scale_log2;
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = exp2f(s[nt][0] * scale_log2 - mx[0]);
+        s[nt][1] = exp2f(s[nt][1] * scale_log2 - mx[0]);
+        s[nt][2] = exp2f(s[nt][2] * scale_log2 - mx[1]);
+        s[nt][3] = exp2f(s[nt][3] * scale_log2 - mx[1]);
+        rs[0] += s[nt][0] + s[nt][1];
+        rs[1] += s[nt][2] + s[nt][3];
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        rs[hh] += __shfl_xor_sync(0xffffffffu, rs[hh], 1);
+        rs[hh] += __shfl_xor_sync(0xffffffffu, rs[hh], 2);
+        rs[hh] = seg_scale / rs[hh];
+    }
+    // O += (P / l * seg_scale) V : C fragments of S (n-tiles 2j, 2j+1) are the A fragment of key block j
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {
+        uint32_t pf[4];
+        pf[0] = pack_bf16(s[2 * kk][0] * rs[0], s[2 * kk][1] * rs[0]);
+        pf[1] = pack_bf16(s[2 * kk][2] * rs[1], s[2 * kk][3] * rs[1]);
+        pf[2] = pack_bf16(s[2 * kk + 1][0] * rs[0], s[2 * kk + 1][1] * rs[0]);
+        pf[3] = pack_bf16(s[2 * kk + 1][2] * rs[1], s[2 * kk + 1][3] * rs[1]);
+#pragma unroll
+        for (int ndp = 0; ndp < 4; ++ndp) {
+            uint32_t b0, b1, b2, b3;
+            const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, c = ndp * 2 + (lane >> 4);
+            ldsm_x4_t(smem_addr(tV + swz(r, c)), b0, b1, b2, b3);
+            mma_bf16(out[ndp * 2], pf, b0, b1);
+            mma_bf16(out[ndp * 2 + 1], pf, b2, b3);
+        }
+    }
+}
+
+constexpr int kCrossWarps = 8, kCrossStages = 3;
+
+template <int NT0, int NT1>
+__global__ void __launch_bounds__(kCrossWarps * 32, 2)
+cross_attention_kernel(const FlashParams p, int tiles_per_warp) {
+    static_assert(NT0 % 2 == 0 && NT1 % 2 == 0, "key tiles come in pairs (16-key P V steps)");
+    constexpr int K0 = NT0 * 8, K1 = NT1 * 8;
+    extern __shared__ __align__(128) uint8_t fa_smem[];
+    __nv_bfloat16* sK0 = reinterpret_cast<__nv_bfloat16*>(fa_smem);
+    __nv_bfloat16* sV0 = sK0 + K0 * kD;
+    __nv_bfloat16* sK1 = sV0 + K0 * kD;
+    __nv_bfloat16* sV1 = sK1 + K1 * kD;
+    __nv_bfloat16* sQ = sV1 + K1 * kD;                  // [warp][stage][16 * 64]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int g = lane >> 2, t = lane & 3;
+
+    // ---- K / V of both segments -> smem (rows past nk zero filled)
+    auto load_kv = [&](int seg, __nv_bfloat16* dK, __nv_bfloat16* dV, int rows) {
+        const int nk = p.nk[seg];
+        const long long kvb = b / p.kv_div[seg];
+        const __nv_bfloat16* kb = p.k[seg] + kvb * nk * p.ldk[seg] + h * kD;
+        const __nv_bfloat16* vb = p.v[seg] + kvb * nk * p.ldv[seg] + h * kD;
+        for (int i = tid; i < rows * 8; i += kCrossWarps * 32) {
+            const int r = i >> 3, c = i & 7;
+            const bool ok = r < nk;
+            const long long row = ok ? r : 0;
+            cp_async16(dK + swz(r, c), kb + row * p.ldk[seg] + c * 8, ok);
+            cp_async16(dV + swz(r, c), vb + row * p.ldv[seg] + c * 8, ok);
+        }
+    };
+    load_kv(0, sK0, sV0, K0);
+    load_kv(1, sK1, sV1, K1);
+    cp_async_commit();
+
+    // ---- this warp's query tiles: first + i * kCrossWarps, i < tiles_per_warp
+    const int ntiles = (p.nq + 15) / 16;
+    const int first = blockIdx.x * kCrossWarps * tiles_per_warp + warp;
+    __nv_bfloat16* myQ = sQ + warp * kCrossStages * 16 * kD;
+    const __nv_bfloat16* qb = p.q + (static_cast<long long>(b) * p.nq) * p.ldq + h * kD;
+    __nv_bfloat16* ob = p.o + (static_cast<long long>(b) * p.nq) * p.ldo + h * kD;
+    auto load_q = [&](int i) {              // always commits a group (possibly empty) so the wait counts stay fixed
+        const int tile = first + i * kCrossWarps;
+        if (i < tiles_per_warp && tile < ntiles) {
+            __nv_bfloat16* dst = myQ + (i % kCrossStages) * 16 * kD;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = lane + j * 32, r = idx >> 3, c = idx & 7;
+                const int row = tile * 16 + r;
+                const bool ok = row < p.nq;
+                cp_async16(dst + swz(r, c), qb + static_cast<long long>(ok ? row : 0) * p.ldq + c * 8, ok);
+            }
+        }
+        cp_async_commit();
+    };
+    load_q(0);
+    load_q(1);
+    cp_async_wait<2>();                     // this thread's share of K / V has landed
+    __syncthreads();
+
+    for (int i = 0; i < tiles_per_warp; ++i) {
+        const int tile = first + i * kCrossWarps;
+        if (tile >= ntiles) break;
+        load_q(i + 2);
+        cp_async_wait<2>();                 // tile i (two younger groups may still be in flight)
+        __syncwarp();
+        __nv_bfloat16* tQ = myQ + (i % kCrossStages) * 16 * kD;
+        uint32_t qf[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int r = (lane & 7) + ((lane >> 3) & 1) * 8, c = ks * 2 + (lane >> 4);
+            ldsm_x4(smem_addr(tQ + swz(r, c)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+        }
+        float out[8][4];
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) { out[nd][0] = out[nd][1] = out[nd][2] = out[nd][3] = 0.f; }
+        cross_segment<NT0>(sK0, sV0, p.nk[0], p.scale_log2, p.seg_scale[0], qf, out, lane);
+        cross_segment<NT1>(sK1, sV1, p.nk[1], p.scale_log2, p.seg_scale[1], qf, out, lane);
+        // ---- O -> bf16 through this tile's Q stage, then 16-byte stores
+        __syncwarp();
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) {
+            *reinterpret_cast<uint32_t*>(tQ + swz(g, nd) + 2 * t) = pack_bf16(out[nd][0], out[nd][1]);
+            *reinterpret_cast<uint32_t*>(tQ + swz(g + 8, nd) + 2 * t) = pack_bf16(out[nd][2], out[nd][3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int idx = lane + j * 32, r = idx >> 3, c = idx & 7;
+            const int row = tile * 16 + r;
+            if (row < p.nq)
+                *reinterpret_cast<uint4*>(ob + static_cast<long long>(row) * p.ldo + c * 8) =
+                    *reinterpret_cast<const uint4*>(tQ + swz(r, c));
+        }
+        __syncwarp();                       // stage is refilled by the prefetch of the next iteration
+    }
+    cp_async_wait<0>();
+}
+
+// -------------------------------------------------------------------------------------------------
 // Temporal self-attention: one warp per (batch, location, head); L <= 16 frames.
 // Row of frame f at location pix of batch b: ((b*L + f)*HW + pix); q/k/v/o are column slices (head h at
 // column h*64) of row-major buffers with leading dims ldq/ldk/ldv/ldo.
@@ -407,6 +583,24 @@ extern "C" int dcb_flash_attention(const dcb_attention_args* a, void* stream) {
     p.scale_log2 = a->softmax_scale * 1.4426950408889634f;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (a->heads > 65535 || a->batch > 65535) return set_error(DCB_ERR_INVALID, "flash_attention: grid too large");
+    static int use_cross = -1;                  // DCB_CROSS_ATTN=0 forces the tiled kernel (A/B testing)
+    if (use_cross < 0) { const char* e = getenv("DCB_CROSS_ATTN"); use_cross = (e == nullptr) ? 1 : atoi(e); }
+    if (use_cross && a->nseg == 2 && a->nk[0] <= 80 && a->nk[1] <= 16) {
+        // text + image cross-attention: all keys resident in shared memory, warps stream over the queries
+        constexpr int NT0 = 10, NT1 = 2;
+        constexpr int smem = (2 * (NT0 + NT1) * 8 + kCrossWarps * kCrossStages * 16) * kD * 2;
+        static bool cfg = false;
+        if (!cfg) {
+            cudaFuncSetAttribute(cross_attention_kernel<NT0, NT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cfg = true;
+        }
+        const int tiles = (a->nq + 15) / 16;
+        int tpw = (tiles + kCrossWarps - 1) / kCrossWarps;
+        tpw = tpw > 5 ? 5 : tpw;
+        dim3 grid((tiles + kCrossWarps * tpw - 1) / (kCrossWarps * tpw), a->heads, a->batch);
+        cross_attention_kernel<NT0, NT1><<<grid, kCrossWarps * 32, smem, st>>>(p, tpw);
+        return check_launch("cross_attention");
+    }
     if (a->nq >= 512) {
         constexpr int W = 8, smem = (W * 16 + 4 * 64) * kD * 2;
         static bool cfg = false;

@@ -6,15 +6,8 @@
 // (3 taps over frames): the A operand is fetched by TMA as a box of a 4-D channels-last tensor and a
 // tap is just a coordinate shift of that box; TMA's out-of-bounds zero fill is the conv padding.
 //
-// CTA = 320 threads, one CTA per SM, persistent over tiles (N fastest so an A tile is re-read from L2):
-//   warp 0      TMA producer: {A 128x64, B BNx64} bf16 stages, SWIZZLE_128B, full/empty mbarrier ring
-//   warp 1      TMEM owner + single-thread tcgen05.mma issuer (128 x BN x 16), 2-deep TMEM accumulator ring
-//   warps 2..9  epilogue, two groups of 4 warps (each group covers the 128 TMEM lanes and takes every other
-//               32-column chunk): tcgen05.ld -> fused bias / per-video embedding / exact-erf GEGLU / residual
-//               -> swizzled smem slot -> TMA tile store.  The fp32 residual chunk is PREFETCHED by TMA into
-//               the same slot (in place), so the epilogue issues no per-thread global loads or stores and
-//               all HBM traffic of the kernel is asynchronous and fully coalesced.  Out-of-range rows and
-//               columns (ragged tiles, N < 32) are clipped by the TMA unit.
+// Host entry point: argument validation, tensor maps, tile-shape / launch-mode heuristics.  The kernel and its warp
+// roles are described in tap_gemm_kernel.cuh.
 #include "tap_gemm_kernel.cuh"
 
 namespace dcb {
@@ -107,14 +100,17 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
         else bn = (a->N % 160 == 0) ? 160 : 128;
     }
     if (bn != 128 && bn != 160 && bn != 256) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: block_n must be 128, 160 or 256");
-    // CTA pairs (cta_group::2): each SM stages half of B, halving shared-memory traffic per MMA. Worth it when
-    // there is at least one 256-row work item per SM pair.
+    // CTA pairs (cta_group::2): each SM stages half of B, halving shared-memory traffic per MMA.  Measured on the
+    // UNet's shapes: pairs win down to ~24 work items of 256 rows (M = 1280 layers: 40 items, +10..20 %; whole step -0.5 ms); below that
+    // single 128-row tiles spread over more SMs.
     bool pair;
     {
         const long long m_tiles = static_cast<long long>((a->D1 + a->b1 - 1) / a->b1) * ((a->D2 + a->b2 - 1) / a->b2) *
                                   ((a->D3 + a->b3 - 1) / a->b3);
         const long long items = ((m_tiles + 1) / 2) * ((a->N + bn - 1) / bn);
-        pair = items >= num_sms() / 2;
+        static int min_items = -1;                   // DCB_GEMM_PAIR_MIN: tuning override
+        if (min_items < 0) { const char* e = getenv("DCB_GEMM_PAIR_MIN"); min_items = e ? atoi(e) : 24; }
+        pair = items >= min_items;
         if (pair_mode_env() == 0) pair = false;
         if (pair_mode_env() == 1) pair = true;
     }
@@ -209,3 +205,13 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
     if (a->colsum != nullptr) return tap_gemm_launch_cs(bn, obf, pair, tmA, tmB, tmOut, tmRes, p, s);
     return launch_all<false>(bn, obf, pair, tmA, tmB, tmOut, tmRes, p, s);
 }
+
+#ifdef DCB_TRACE
+// debug builds only (tools/trace_gemm.py): copy the CTA-0 event log (6 role regions of 4096 entries, entry 0 = count)
+extern "C" int dcb_debug_trace(unsigned long long* dst, int cap) {
+    cudaDeviceSynchronize();
+    if (cap < 6 * 4096) return -1;
+    cudaMemcpyFromSymbol(dst, dcb::g_tap_trace, 6 * 4096 * sizeof(unsigned long long));
+    return 6 * 4096;
+}
+#endif

@@ -51,6 +51,27 @@ template <int BN, bool k2> struct StageCount {
     static constexpr int value = fit > 8 ? 8 : fit;
 };
 
+// -DDCB_TRACE (DCB_NVCC_EXTRA=-DDCB_TRACE, tools/trace_gemm.py): six role lanes of CTA 0 (producer, mma, epilogue
+// leaders 0..3) log (clock, event, argument) into their own 4096-entry region with plain stores; entry 0 = count.
+#ifdef DCB_TRACE
+static __device__ unsigned long long g_tap_trace[6 * 4096];
+struct TraceLane {
+    unsigned n = 1;
+    __device__ __forceinline__ void ev(int role, unsigned code, unsigned arg) {
+        if (blockIdx.x == 0 && n < 4096u)
+            g_tap_trace[role * 4096 + n++] = (static_cast<unsigned long long>(clock64()) << 20) | (code << 12) | (arg & 0xfffu);
+    }
+    __device__ __forceinline__ void done(int role) { if (blockIdx.x == 0) g_tap_trace[role * 4096] = n; }
+};
+#define DCB_TR_DECL TraceLane trl;
+#define DCB_TR_DONE(role) trl.done(role)
+#define DCB_TR(role, code, arg) trl.ev(role, code, arg)
+#else
+#define DCB_TR_DECL
+#define DCB_TR_DONE(role)
+#define DCB_TR(role, code, arg)
+#endif
+
 struct TapGemmParams {
     int D1, D2, D3, b1, b2, b3, t1, t2, t3;
     int num_m_tiles, num_n_tiles, rows_per_tile;
@@ -172,6 +193,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    DCB_TR_DECL
     // work item = (m tile [pair], n tile); workers = CTAs (or CTA pairs) striding over the items
     const int num_tiles = (k2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
     const int worker = k2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
@@ -219,6 +241,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     if (elect_one()) {
+                        DCB_TR(0, 1, it);
                         uint8_t* sa = smem + s * kStageBytes;
                         if constexpr (k2) {
                             const uint32_t lfull = mapa_cluster(smem_u32(&full[s]), 0);      // leader's barrier
@@ -244,12 +267,14 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
                 mbar_wait(&tempty[a], aph ^ 1);
                 tc_fence_after();
+                if (lane == 0) DCB_TR(1, 2, tc);
                 const uint32_t d_tmem = tmem_base + a * kAccStride;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     if (elect_one()) {
+                        DCB_TR(1, 3, it);
                         const uint32_t sa = smem_u32(smem + s * kStageBytes);
                         const uint64_t adesc = make_sw128_kmajor_desc(sa);
                         const uint64_t bdesc = make_sw128_kmajor_desc(sa + kABytes);
@@ -352,6 +377,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     mbar_wait(&tfull[a], aph);
                     tc_fence_after();
                     acc_ready = true;
+                    if (leader) DCB_TR(2 + grp, 4 + grp, tc);
                 }
                 if (tma_res) {
                     if (leader) {
@@ -359,6 +385,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         prefetch_upto(cnt + 1);
                     }
                     mbar_wait(&my_rfull[s], (cnt / kSlots) & 1);
+                    if (leader) DCB_TR(2 + grp, 8 + grp, cnt);
                 }
                 // (no TMA residual: the slot was proven free before the previous chunk's barrier, see below)
                 uint8_t* orow = slot + r * 64;                          // 64-byte rows, SWIZZLE_64B
@@ -486,6 +513,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (leader) {
                     tma_store_4d(&tmOut, slot, col0, o1, o2, o3);
                     tma_store_commit();
+                    DCB_TR(2 + grp, 12 + grp, cnt);
                 }
             }
             if (!acc_ready) {                                            // group without chunks still tracks the ring
@@ -499,7 +527,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
         if (leader) tma_store_wait_all<0>();
+        if (leader) DCB_TR_DONE(2 + grp);
     }
+    if (warp == 0 && lane == 0) DCB_TR_DONE(0);
+    if (warp == 1 && lane == 0) DCB_TR_DONE(1);
 
     tc_fence_before();
     if constexpr (k2) cluster_sync_all(); else __syncthreads();

@@ -71,20 +71,22 @@ def test_flash_self_attention(B, H, N):
     assert _rel(out, ref) < 1e-2
 
 
-@pytest.mark.parametrize("B,T,H,N", [(1, 16, 2, 160), (2, 4, 1, 70)])
-def test_flash_dual_cross_attention(B, T, H, N):
-    """text keys shared by the T frames of a video + per-frame image keys, two independent softmaxes."""
+@pytest.mark.parametrize("B,T,H,N,NT,NI", [(1, 16, 2, 160, 77, 16), (2, 4, 1, 70, 77, 16), (1, 2, 5, 2560, 77, 16),
+                                           (1, 3, 2, 33, 77, 16), (2, 2, 2, 640, 50, 9), (1, 2, 2, 300, 100, 16)])
+def test_flash_dual_cross_attention(B, T, H, N, NT, NI):
+    """text keys shared by the T frames of a video + per-frame image keys, two independent softmaxes
+    (resident-key kernel when the keys fit 80 + 16, tiled kernel otherwise)."""
     from dynamicrafter_b200 import ops
     inner, nb = H * 64, B * T
     q = _randn((nb * N, inner), 9).to(torch.bfloat16)
-    kv_t = _randn((B * 77, 2 * inner), 10).to(torch.bfloat16)
-    kv_i = _randn((nb * 16, 2 * inner), 11).to(torch.bfloat16)
+    kv_t = _randn((B * NT, 2 * inner), 10).to(torch.bfloat16)
+    kv_i = _randn((nb * NI, 2 * inner), 11).to(torch.bfloat16)
     s_img = 1.37
-    out = ops.flash_attention(q, [(kv_t[:, :inner], kv_t[:, inner:], 77, T, 1.0),
-                                  (kv_i[:, :inner], kv_i[:, inner:], 16, 1, s_img)], nb, H, N, 0.125)
+    out = ops.flash_attention(q, [(kv_t[:, :inner], kv_t[:, inner:], NT, T, 1.0),
+                                  (kv_i[:, :inner], kv_i[:, inner:], NI, 1, s_img)], nb, H, N, 0.125)
     qf = q.float().reshape(nb, N, H, 64).permute(0, 2, 1, 3)
-    kt = kv_t.float().reshape(B, 77, 2, H, 64).permute(2, 0, 3, 1, 4).repeat_interleave(T, dim=1)
-    ki = kv_i.float().reshape(nb, 16, 2, H, 64).permute(2, 0, 3, 1, 4)
+    kt = kv_t.float().reshape(B, NT, 2, H, 64).permute(2, 0, 3, 1, 4).repeat_interleave(T, dim=1)
+    ki = kv_i.float().reshape(nb, NI, 2, H, 64).permute(2, 0, 3, 1, 4)
     ref = _sdpa(qf, kt[0], kt[1], 0.125) + s_img * _sdpa(qf, ki[0], ki[1], 0.125)
     assert _rel(out, ref.permute(0, 2, 1, 3).reshape(nb * N, inner)) < 1e-2
 
