@@ -47,11 +47,24 @@ __device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&v)[8]) {
     }
 }
 
+// 16 bytes -> 4 fp32 or 8 bf16 channels as floats (tag pointer selects the source type)
+__device__ __forceinline__ void unpack16(const uint4& u, float (&v)[4], const float*) {
+    v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+}
+__device__ __forceinline__ void unpack16(const uint4& u, float (&v)[8], const __nv_bfloat16*) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+}
+
 static int gcd_i(int a, int b) { return b == 0 ? a : gcd_i(b, a % b); }
 
 // One work item = (128-channel block, row split); a block's 8 warps share Qb*row_split items evenly.
-static GnPlan plan_stats(int C1, int C2, int S) {
-    const int Qb = ((C1 >> 2) + 31) / 32 + ((C2 >> 2) + 31) / 32;
+static GnPlan plan_stats(int C1, int C2, int S, int vec = 4) {
+    const int Qb = (C1 / vec + 31) / 32 + (C2 / vec + 31) / 32;
     int s = 8 / gcd_i(Qb, 8);
     const int cap = kMaxSplitC / (C1 + C2) > 0 ? kMaxSplitC / (C1 + C2) : 1;
     if (s > cap) s = cap;
@@ -243,6 +256,197 @@ gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused statistics + apply in ONE cooperative launch: grid = (nchunks, G) with every block resident.  A block
+// reduces its rows of instance n (same item scheme as gn_stats_kernel), publishes 64 partial sums, waits on the
+// per-instance arrival counter (the only inter-block dependency), folds all partials of its instance in the same
+// fixed order as every other block (bitwise identical statistics everywhere, no broadcast needed) and normalises
+// the rows it has just read -- they come back from L1 / L2 instead of HBM.  Saves a launch, the serial last-block
+// finalisation and one HBM pass for every tensor that fits in L2.  counters: [2 * G] (arrive, leave), self-cleaning.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+#ifndef DCB_GN_U
+#define DCB_GN_U 4          // phase 2: rows in flight per thread
+#endif
+#ifndef DCB_GN_P1
+#define DCB_GN_P1 8         // phase 1: rows in flight per lane
+#endif
+#ifndef DCB_GN_OCC
+#define DCB_GN_OCC 3        // resident blocks per SM the register allocation must allow
+#endif
+template <typename T>
+__global__ void __launch_bounds__(256, DCB_GN_OCC)
+gn_fused_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int C2, int S, int rows_per_chunk,
+                int row_split, float* __restrict__ partial, unsigned* __restrict__ counters, float eps,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
+                __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ raw) {
+    extern __shared__ float s_mem[];        // phase 1: [row_split][C][2] partial slots; phase 2: A[C] | B[C]
+    __shared__ double s_fold[4][kGroups * 2];
+    __shared__ float s_mr[kGroups * 2];
+    const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x, G = gridDim.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int C = C1 + C2, cg = C / kGroups;
+    const int r0 = chunk * rows_per_chunk;
+    const int r1 = min(S, r0 + rows_per_chunk);
+    constexpr int kV = 16 / sizeof(T);        // channels per 16-byte load: 4 (fp32) or 8 (bf16)
+    const int Qb1 = (C1 / kV + 31) >> 5, Qb2 = (C2 / kV + 31) >> 5, Qb = Qb1 + Qb2;
+
+    // ---- phase 1: per-(row split, channel) sums of this block's rows; an item = (32 lanes x 16 bytes of channels,
+    // row split), 8 rows in flight per lane
+    for (int item = warp; item < Qb * row_split; item += 8) {
+        const int cb = item / row_split, split = item - cb * row_split;
+        const bool second = cb >= Qb1;
+        const T* x = second ? x2 : x1;
+        const int Cs = second ? C2 : C1;
+        const int coff = second ? C1 : 0;
+        const int q = (second ? cb - Qb1 : cb) * 32 + lane;
+        if (q >= Cs / kV) continue;
+        const T* base = x + (static_cast<size_t>(n) * S) * Cs + q * kV;
+        const size_t rs = static_cast<size_t>(Cs);
+        float s[kV], ss[kV];
+#pragma unroll
+        for (int e = 0; e < kV; ++e) { s[e] = 0.f; ss[e] = 0.f; }
+        constexpr int kR = DCB_GN_P1;         // rows in flight per lane
+        for (int r = r0 + split; r < r1; r += kR * row_split) {
+            uint4 raw16[kR];
+#pragma unroll
+            for (int u = 0; u < kR; ++u) {
+                const int rr = r + u * row_split;
+                raw16[u] = rr < r1 ? __ldg(reinterpret_cast<const uint4*>(base + rr * rs)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < kR; ++u) {
+                float v[kV];
+                unpack16(raw16[u], v, static_cast<const T*>(nullptr));
+#pragma unroll
+                for (int e = 0; e < kV; ++e) { s[e] += v[e]; ss[e] = fmaf(v[e], v[e], ss[e]); }
+            }
+        }
+        float* dst = s_mem + (static_cast<size_t>(split) * C + coff + q * kV) * 2;
+#pragma unroll
+        for (int e = 0; e < kV; ++e) { dst[2 * e] = s[e]; dst[2 * e + 1] = ss[e]; }
+    }
+    __syncthreads();
+    {
+        float* pbase = partial + (static_cast<size_t>(n) * nchunks + chunk) * (kGroups * 2);
+        const int g = tid >> 3, sub = tid & 7;
+        float a = 0.f, b = 0.f;
+        const int slots = row_split * cg;
+        for (int i = sub; i < slots; i += 8) {
+            const int sp = i / cg, c = g * cg + (i - sp * cg);
+            a += s_mem[(static_cast<size_t>(sp) * C + c) * 2];
+            b += s_mem[(static_cast<size_t>(sp) * C + c) * 2 + 1];
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (sub == 0) {
+            pbase[g * 2] = a;
+            pbase[g * 2 + 1] = b;
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    // ---- instance barrier (all blocks are resident: cooperative launch)
+    if (tid == 0) {
+        atomicAdd(&counters[n], 1u);
+        unsigned spins = 0;
+        while (ld_acquire_u32(&counters[n]) < static_cast<unsigned>(nchunks)) {
+            __nanosleep(40);
+            if (++spins > (1u << 24)) __trap();          // watchdog: never hang the GPU on a protocol bug
+        }
+    }
+    __syncthreads();
+    // ---- every block folds the [nchunks][64] partials of its instance in the same fixed order
+    {
+        const int col = tid & 63, crow = tid >> 6;
+        const float* pp = partial + static_cast<size_t>(n) * nchunks * (kGroups * 2) + col;
+        double acc = 0.0;
+        for (int c = crow; c < nchunks; c += 64) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (c + 4 * u < nchunks) ? __ldcg(pp + static_cast<size_t>(c + 4 * u) * (kGroups * 2)) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc += static_cast<double>(v[u]);
+        }
+        s_fold[crow][col] = acc;
+        __syncthreads();
+        if (tid < kGroups) {
+            const int g = tid;
+            const double sum = ((s_fold[0][2 * g] + s_fold[1][2 * g]) + s_fold[2][2 * g]) + s_fold[3][2 * g];
+            const double sq = ((s_fold[0][2 * g + 1] + s_fold[1][2 * g + 1]) + s_fold[2][2 * g + 1]) + s_fold[3][2 * g + 1];
+            const double cnt = static_cast<double>(S) * cg;
+            const double mean = sum / cnt;
+            double var = sq / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            s_mr[2 * g] = static_cast<float>(mean);
+            s_mr[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {          // leave counter: the last block out re-arms both counters for the next launch
+        const unsigned prev = atomicAdd(&counters[G + n], 1u);
+        if (prev == static_cast<unsigned>(nchunks - 1)) { counters[n] = 0; counters[G + n] = 0; }
+    }
+    // ---- phase 2: y = silu?(x * A + B) on the rows this block has just read
+    for (int c = tid; c < C; c += 256) {
+        const int g = c / cg;
+        const float a = s_mr[2 * g + 1] * gamma[c];
+        s_mem[c] = a;
+        s_mem[C + c] = beta[c] - s_mr[2 * g] * a;
+    }
+    __syncthreads();
+    // a thread owns one 8-channel column (its affine coefficients live in registers) and walks down the rows of the
+    // chunk with a constant pointer stride, U rows in flight
+    const int O = C >> 3, O1 = C1 >> 3, nrows = r1 - r0;
+    constexpr int U = DCB_GN_U;
+    for (int o0 = 0; o0 < O; o0 += 256) {
+        const int ow = min(256, O - o0);               // columns of this pass
+        const int rpp = 256 / ow;                      // rows covered by the block per step
+        const int my_r = tid / ow, my_o = o0 + tid - my_r * ow;
+        if (my_r >= rpp) continue;
+        const int c0 = my_o * 8;
+        float am[8], bm[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { am[e] = s_mem[c0 + e]; bm[e] = s_mem[C + c0 + e]; }
+        const size_t row0 = static_cast<size_t>(n) * S + r0 + my_r;
+        const bool first = my_o < O1;
+        const T* src = first ? (x1 + row0 * C1 + c0) : (x2 + row0 * C2 + (c0 - C1));
+        const size_t sstep = static_cast<size_t>(rpp) * (first ? C1 : C2);
+        const size_t dstep = static_cast<size_t>(rpp) * C;
+        __nv_bfloat16* dst = y + row0 * C + c0;
+        __nv_bfloat16* rdst = raw != nullptr ? raw + row0 * C + c0 : nullptr;
+        for (int r = my_r; r < nrows; r += rpp * U) {
+            float v[U][8];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (r + u * rpp < nrows) ld8(src + u * sstep, v[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (r + u * rpp < nrows) {
+                    if (rdst != nullptr) *reinterpret_cast<uint4*>(rdst + u * dstep) = pack8(v[u]);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float t = fmaf(v[u][e], am[e], bm[e]);
+                        v[u][e] = do_silu ? silu_fast(t) : t;
+                    }
+                    *reinterpret_cast<uint4*>(dst + u * dstep) = pack8(v[u]);
+                }
+            }
+            src += U * sstep;
+            dst += U * dstep;
+            if (rdst != nullptr) rdst += U * dstep;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // LayerNorm over the last dim (C <= 1280*... kMaxQuads*128), one warp per row, values kept in
 // registers (two-pass variance), bf16 out.
 // ---------------------------------------------------------------------------------------------
@@ -428,6 +632,74 @@ extern "C" int dcb_group_norm_apply_bf16(const void* x, int C, int G, int S, con
         static_cast<const __nv_bfloat16*>(x), nullptr, C, 0, S, rpc, stats, gamma, beta, silu_act,
         static_cast<__nv_bfloat16*>(y_bf16), nullptr);
     return check_launch("group_norm_apply_bf16");
+}
+
+template <typename T>
+static int launch_gn_fused(const T* x1, const T* x2, int C1, int C2, int G, int S, float eps, const float* gamma,
+                           const float* beta, int silu_act, void* y, void* raw, void* workspace, unsigned* counters,
+                           cudaStream_t stream) {
+    const int C = C1 + C2;
+    const GnPlan pl = plan_stats(C1, C2, S, static_cast<int>(16 / sizeof(T)));
+    static int per_sm = -1;                                   // resident blocks per SM at the largest smem request
+    if (per_sm < 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gn_fused_kernel<T>, 256, kMaxSplitC * 2 * sizeof(float)) !=
+            cudaSuccess || n < 1)
+            return set_error(DCB_ERR_CUDA, "group_norm_fused: occupancy query failed");
+        per_sm = n > 6 ? 6 : n;
+    }
+    const int capacity = per_sm * num_sms();
+    if (G > capacity) return set_error(DCB_ERR_UNSUPPORTED, "group_norm_fused: G=%d exceeds %d resident blocks", G, capacity);
+    // fill the resident capacity: small tensors get few-row chunks (row_split 1: an item = one 128-channel block
+    // over all rows of the chunk, every load in flight at once), large ones the streaming plan of the stats kernel
+    int nch = capacity / G;
+    if (nch > kMaxChunks) nch = kMaxChunks;
+    int rpc = (S + nch - 1) / nch;
+    int split = 1;
+    if (rpc > 8) {
+        split = pl.row_split;
+        rpc = (rpc + split - 1) / split * split;
+    }
+    nch = (S + rpc - 1) / rpc;
+    size_t smem = static_cast<size_t>(split) * C * 2 * sizeof(float);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.gridDim = dim3(nch, G);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gn_fused_kernel<T>, x1, x2, C1, C2, S, rpc, split,
+                                       static_cast<float*>(workspace), counters, eps, gamma, beta, silu_act,
+                                       static_cast<__nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(raw));
+    if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "group_norm_fused launch: %s", cudaGetErrorString(e));
+    return DCB_OK;
+}
+
+extern "C" int dcb_group_norm_fused(const float* x1, const float* x2, int C1, int C2, int G, int S, float eps,
+                                    const float* gamma, const float* beta, int silu_act, void* y_bf16, void* raw_bf16,
+                                    void* workspace, unsigned* counters, void* stream) {
+    const int C = C1 + C2;
+    if (x1 == nullptr || y_bf16 == nullptr || gamma == nullptr || beta == nullptr || workspace == nullptr || counters == nullptr)
+        return set_error(DCB_ERR_INVALID, "group_norm_fused: null argument");
+    if (C % kGroups != 0 || (C1 & 7) || (C2 & 7) || G < 1 || S < 1 || (C2 > 0 && x2 == nullptr) || C > kMaxC)
+        return set_error(DCB_ERR_INVALID, "group_norm_fused: C1=%d C2=%d G=%d S=%d", C1, C2, G, S);
+    return launch_gn_fused<float>(x1, x2, C1, C2, G, S, eps, gamma, beta, silu_act, y_bf16, raw_bf16, workspace, counters,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dcb_group_norm_fused_bf16(const void* x, int C, int G, int S, float eps, const float* gamma,
+                                         const float* beta, int silu_act, void* y_bf16, void* workspace,
+                                         unsigned* counters, void* stream) {
+    if (x == nullptr || y_bf16 == nullptr || gamma == nullptr || beta == nullptr || workspace == nullptr || counters == nullptr)
+        return set_error(DCB_ERR_INVALID, "group_norm_fused_bf16: null argument");
+    if (C % kGroups != 0 || (C & 7) || G < 1 || S < 1 || C > kMaxC)
+        return set_error(DCB_ERR_INVALID, "group_norm_fused_bf16: C=%d G=%d S=%d", C, G, S);
+    return launch_gn_fused<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), nullptr, C, 0, G, S, eps, gamma, beta,
+                                          silu_act, y_bf16, nullptr, workspace, counters, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dcb_layer_norm(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,

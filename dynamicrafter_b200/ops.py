@@ -5,6 +5,7 @@ Tensors are torch CUDA tensors used purely as device-memory handles; every op ru
 """
 import ctypes
 import functools
+import os
 
 import torch
 
@@ -181,6 +182,11 @@ def tconv3(a, B, T, HW, w, *, bias=None, residual=None, f32=True, bf16=False, ou
 _GN_SCRATCH = {}
 
 
+# GroupNorm inputs up to this many bytes take the single cooperative launch (statistics + apply, second read from
+# L2); larger ones keep the two streaming kernels.  DCB_GN_FUSED_MB overrides (0 = never).
+_GN_FUSED_MAX_BYTES = int(float(os.environ.get("DCB_GN_FUSED_MB", "4096")) * (1 << 20))
+
+
 def _gn_scratch(dev, G):
     """(workspace, counters) reused by every GroupNorm launch on this device (stream ordered)."""
     key = (dev.index, )
@@ -189,7 +195,7 @@ def _gn_scratch(dev, G):
         cap = max(G, 64)
         nbytes = _lib.lib().dcb_group_norm_workspace_bytes(cap)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        cnt = torch.zeros(cap, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(2 * cap, dtype=torch.int32, device=dev)     # fused kernel: arrive + leave counters
         ent = (ws, cnt, cap)
         _GN_SCRATCH[key] = ent
     return ent[0], ent[1]
@@ -227,6 +233,13 @@ def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False
         # block-internal activation kept in bf16 by its producer: single source, normalised output only
         assert x2 is None and not want_raw and x1.is_contiguous() and x1.shape[0] == G * S
         C, dev, L = x1.shape[1], x1.device, _lib.lib()
+        if colsums is None and x1.numel() * 2 <= _GN_FUSED_MAX_BYTES:
+            ws, cnt = _gn_scratch(dev, G)
+            y = torch.empty((G * S, C), dtype=BF16, device=dev)
+            check(L.dcb_group_norm_fused_bf16(ptr(x1), _c_i(C), _c_i(G), _c_i(S), _c_f(eps), ptr(gamma), ptr(beta),
+                                              _c_i(1 if silu else 0), ptr(y), ptr(ws), ptr(cnt), _stream()),
+                  "dcb_group_norm_fused_bf16")
+            return y
         if colsums is not None:
             stats = _stats_from_colsums(colsums, G, S, C, eps, dev)
         else:
@@ -246,6 +259,16 @@ def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False
     dev = x1.device
     L = _lib.lib()
     y = raw = stats = None
+    if want_norm and colsums is None and (x1.numel() + (0 if x2 is None else x2.numel())) * 4 <= _GN_FUSED_MAX_BYTES \
+            and C1 % 8 == 0 and C2 % 8 == 0:
+        ws, cnt = _gn_scratch(dev, G)
+        y = torch.empty((G * S, C1 + C2), dtype=BF16, device=dev)
+        if want_raw:
+            raw = torch.empty((G * S, C1 + C2), dtype=BF16, device=dev)
+        check(L.dcb_group_norm_fused(ptr(x1), ptr(x2), _c_i(C1), _c_i(C2), _c_i(G), _c_i(S), _c_f(eps), ptr(gamma),
+                                     ptr(beta), _c_i(1 if silu else 0), ptr(y), ptr(raw), ptr(ws), ptr(cnt), _stream()),
+              "dcb_group_norm_fused")
+        return (y, raw) if want_raw else y
     if want_norm and colsums is not None and x2 is None:
         stats = _stats_from_colsums(colsums, G, S, C1, eps, dev)
         y = torch.empty((G * S, C1), dtype=BF16, device=dev)

@@ -119,6 +119,15 @@ int dcb_group_norm_stats_bf16(const void* x, int C, int G, int S, float eps, flo
                               unsigned* counters, void* stream);
 int dcb_group_norm_apply_bf16(const void* x, int C, int G, int S, const float* stats, const float* gamma,
                               const float* beta, int silu_act, void* y_bf16, void* stream);
+/* Statistics + apply in one cooperative launch (every block resident; blocks of an instance meet at a counter):
+ * same results as stats + apply, one HBM pass less for tensors that stay in L2.  counters: 2 * G unsigned, zero
+ * before the first launch (self-cleaning); workspace as for dcb_group_norm_stats.  C1, C2 multiples of 8. */
+int dcb_group_norm_fused(const float* x1, const float* x2, int C1, int C2, int G, int S, float eps,
+                         const float* gamma, const float* beta, int silu_act, void* y_bf16, void* raw_bf16,
+                         void* workspace, unsigned* counters, void* stream);
+int dcb_group_norm_fused_bf16(const void* x, int C, int G, int S, float eps, const float* gamma,
+                              const float* beta, int silu_act, void* y_bf16, void* workspace,
+                              unsigned* counters, void* stream);
 /* LayerNorm over the last dim (attention.py:225-227), fp32 in, bf16 out. C % 4 == 0, C <= 2560. */
 int dcb_layer_norm(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,
                    void* y_bf16, void* stream);
