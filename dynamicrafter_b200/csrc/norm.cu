@@ -454,49 +454,66 @@ template <int kMaxQuads>
 __global__ void __launch_bounds__(256)
 layer_norm_kernel(const float* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= rows) return;
+    // persistent warps: row, row + W, row + 2W, ... with the next row's loads issued before the current row's
+    // arithmetic (two rows in flight per warp)
+    const int lane = threadIdx.x & 31;
+    const int W = gridDim.x * (blockDim.x >> 5);
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
     const int Q = C >> 2;
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * C);
-    float4 v[kMaxQuads];
-    float sum = 0.f;
+    const float inv_c = 1.0f / C;
+    float4 v[kMaxQuads], nx[kMaxQuads];
+    {
+        const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * C);
 #pragma unroll
-    for (int i = 0; i < kMaxQuads; ++i) {
-        const int q = lane + i * 32;
-        if (q < Q) {
-            v[i] = __ldg(xr + q);
-            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-        }
+        for (int i = 0; i < kMaxQuads; ++i)
+            if (lane + i * 32 < Q) v[i] = __ldg(xr + lane + i * 32);
     }
+    while (true) {
+        const int next = row + W;
+        if (next < rows) {
+            const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(next) * C);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / C;
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < kMaxQuads; ++i) {
-        const int q = lane + i * 32;
-        if (q < Q) {
-            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-            sq += (a * a + b * b) + (c * c + d * d);
+            for (int i = 0; i < kMaxQuads; ++i)
+                if (lane + i * 32 < Q) nx[i] = __ldg(xr + lane + i * 32);
         }
-    }
+        float sum = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = rsqrtf(sq / C + eps);
-    __nv_bfloat16* yr = y + static_cast<size_t>(warp) * C;
+        for (int i = 0; i < kMaxQuads; ++i)
+            if (lane + i * 32 < Q) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
 #pragma unroll
-    for (int i = 0; i < kMaxQuads; ++i) {
-        const int q = lane + i * 32;
-        if (q < Q) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
-            const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + q);
-            __nv_bfloat162 lo = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
-            __nv_bfloat162 hi = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
-            uint2 p;
-            p.x = *reinterpret_cast<uint32_t*>(&lo);
-            p.y = *reinterpret_cast<uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(yr + q * 4) = p;
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum * inv_c;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxQuads; ++i) {
+            if (lane + i * 32 < Q) {
+                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                sq += (a * a + b * b) + (c * c + d * d);
+            }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = rsqrtf(sq * inv_c + eps);
+        __nv_bfloat16* yr = y + static_cast<size_t>(row) * C;
+#pragma unroll
+        for (int i = 0; i < kMaxQuads; ++i) {
+            const int q = lane + i * 32;
+            if (q < Q) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + q);
+                __nv_bfloat162 lo = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+                __nv_bfloat162 hi = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+                uint2 p;
+                p.x = *reinterpret_cast<uint32_t*>(&lo);
+                p.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(yr + q * 4) = p;
+            }
+        }
+        if (next >= rows) break;
+        row = next;
+#pragma unroll
+        for (int i = 0; i < kMaxQuads; ++i) v[i] = nx[i];
     }
 }
 
@@ -708,11 +725,16 @@ extern "C" int dcb_layer_norm(const float* x, int rows, int C, const float* gamm
         return set_error(DCB_ERR_INVALID, "layer_norm: null argument");
     if (rows < 1 || C < 4 || (C & 3) || C > 20 * 128)
         return set_error(DCB_ERR_INVALID, "layer_norm: rows=%d C=%d (C %% 4 == 0, C <= 2560)", rows, C);
-    const int blocks = (rows + 7) / 8;
+    // persistent warps: as many blocks as stay resident (register-limited per variant)
+    const int kq = C <= 3 * 128 ? 3 : (C <= 5 * 128 ? 5 : (C <= 10 * 128 ? 10 : 20));
+    const int per_sm = kq == 3 ? 4 : (kq == 5 ? 3 : (kq == 10 ? 2 : 1));
+    int blocks = (rows + 7) / 8;
+    if (blocks > num_sms() * per_sm) blocks = num_sms() * per_sm;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     __nv_bfloat16* y = static_cast<__nv_bfloat16*>(y_bf16);
-    if (C <= 5 * 128) layer_norm_kernel<5><<<blocks, 256, 0, s>>>(x, rows, C, gamma, beta, eps, y);
-    else if (C <= 10 * 128) layer_norm_kernel<10><<<blocks, 256, 0, s>>>(x, rows, C, gamma, beta, eps, y);
+    if (kq == 3) layer_norm_kernel<3><<<blocks, 256, 0, s>>>(x, rows, C, gamma, beta, eps, y);
+    else if (kq == 5) layer_norm_kernel<5><<<blocks, 256, 0, s>>>(x, rows, C, gamma, beta, eps, y);
+    else if (kq == 10) layer_norm_kernel<10><<<blocks, 256, 0, s>>>(x, rows, C, gamma, beta, eps, y);
     else layer_norm_kernel<20><<<blocks, 256, 0, s>>>(x, rows, C, gamma, beta, eps, y);
     return check_launch("layer_norm");
 }

@@ -33,7 +33,7 @@ def graph_ms(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
-for G, S, C in SHAPES:
+for G, S, C in (SHAPES if __name__ == "__main__" else []):
     src = torch.randn(G * S, C, device=dev).to(dt)
     xs = [torch.empty_like(src) for _ in range(N)]
     gam, bet = torch.ones(C, device=dev), torch.zeros(C, device=dev)
