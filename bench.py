@@ -267,6 +267,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-video", action="store_true")
+    ap.add_argument("--frame-shard", action="store_true",
+                    help="N>1: ONE video, its 16 frames sharded over the ranks (all-to-all around the temporal blocks); "
+                         "strong scaling of single-video latency (BASELINE.json configs[3])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -283,13 +286,30 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line (NCCL prints its version at INFO/VERSION)
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the first communicator comes up: keep stdout to the single
+        # JSON line by pointing fd 1 at stderr until that has happened
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     _lib.check(_lib.lib().dcb_check_device(), "dcb_check_device")
     peaks = load_peaks()
 
     host, mp = build_host(args.config, dev, with_vae=not args.no_video)
     host.unet.use_cuda_graph = not args.no_graph
+    fshard = args.frame_shard and world > 1
+    if fshard:
+        from dynamicrafter_b200.parallel import FrameShard
+        host.unet.frame_shard = FrameShard()
+    units = 1 if fshard else world          # videos in flight over the whole job
     sm = SAMPLER[args.config]
     B, T = 1, 16
     h, w = mp["image_size"]
@@ -338,7 +358,7 @@ def main():
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(t_ms) / args.steps
-    value = world * B / (ms_per_step * 1e-3)
+    value = units * B / (ms_per_step * 1e-3)
     assert torch.isfinite(x).all(), "non-finite latents"
 
     # ---------------- end-to-end through the public API from HOST buffers (pinned), result read back every step
@@ -360,7 +380,7 @@ def main():
     e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * B / (float(e2e_ms) / args.steps * 1e-3)
+    e2e_value = units * B / (float(e2e_ms) / args.steps * 1e-3)
 
     # ---------------- instrumented eager step: per-launch CUDA events -> roofline of the tcgen05 kernel + breakdown
     host.unet.use_cuda_graph = False
@@ -373,7 +393,7 @@ def main():
     launches_per_step = _lib.CALLS[0] - calls0
     host.unet.use_cuda_graph = not args.no_graph
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    step_tflop = 2 * UNET_TFLOP[args.config] * B
+    step_tflop = 2 * UNET_TFLOP[args.config] * B / (world if fshard else 1)      # per-GPU share of one step
     roofline = {"bound": "tensor", "kernel": "tap_gemm_kernel (tcgen05 implicit GEMM: linear + conv3x3 + temporal conv)",
                 "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": round(achieved / peaks["tflops"], 4),
@@ -400,10 +420,15 @@ def main():
         torch.cuda.synchronize()
         t_s = time.perf_counter() - t0
         from dynamicrafter_b200.parallel import all_gather_latents
-        gathered = all_gather_latents(samples)        # the single collective of this mode
-        assert gathered.shape[0] == world * B
-        t1 = time.perf_counter()
-        frames = host.decode_first_stage(samples, frames_per_call=8)
+        if fshard:                                    # every rank holds the whole video: decode own frames only
+            f0, f1 = host.unet.frame_shard.frames(T)
+            t1 = time.perf_counter()
+            frames = host.decode_first_stage(samples[:, :, f0:f1].contiguous(), frames_per_call=8)
+        else:
+            gathered = all_gather_latents(samples)        # the single collective of this mode
+            assert gathered.shape[0] == world * B
+            t1 = time.perf_counter()
+            frames = host.decode_first_stage(samples, frames_per_call=8)
         torch.cuda.synchronize()
         t_d = time.perf_counter() - t1
         tv = torch.tensor([t_s + t_d, t_s, t_d], device=dev, dtype=torch.float64)
@@ -411,7 +436,7 @@ def main():
             dist.all_reduce(tv, op=dist.ReduceOp.MAX)
         vid_tflop = 100 * UNET_TFLOP[args.config] + VAE_TFLOP[args.config]
         video = {"s_per_video": round(float(tv[0]), 3), "sample_s": round(float(tv[1]), 3), "decode_s": round(float(tv[2]), 3),
-                 "videos_per_s_all_gpus": round(world / float(tv[0]), 4), "tflops": round(vid_tflop / float(tv[0]), 1),
+                 "videos_per_s_all_gpus": round(units / float(tv[0]), 4), "tflops": round(vid_tflop / float(tv[0]), 1),
                  "frac_of_peak": round(vid_tflop / float(tv[0]) / peaks["tflops"], 4),
                  "finite": bool(torch.isfinite(frames).all())}
 
@@ -430,12 +455,15 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 4), "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
+                "scaling": "strong" if fshard else "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"DynamiCrafter {args.config} ({h * 8}x{w * 8}x16f, latent {h}x{w}), DDIM {sm['S']} "
                                        f"{sm['timestep_spacing']} eta {sm['eta']}, CFG {sm['cfg']}, guidance_rescale "
                                        f"{sm['guidance_rescale']}; 1 video per GPU; random-init weights (1.44 B params)",
-                           "videos_per_gpu": B, "cuda_graph": not args.no_graph,
+                           "videos_per_gpu": B, "cuda_graph": (not args.no_graph) and not fshard,
+                           "parallelism": (f"frame-sharded x{world}: one video, {T // world} frames per GPU, all-to-all "
+                                           "around the temporal blocks") if fshard else f"one video per GPU x{world}",
                            "l2": "not flushed: per-step working set (2.9 GB bf16 weights + activations) >> 126 MB L2"},
                 "s_per_video_unet_only": round(sm["S"] * ms_per_step * 1e-3, 3),
                 "e2e": {"value": round(e2e_value, 4), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -91,7 +91,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int C2, int S,
                 int rows_per_chunk, int row_split, float* __restrict__ partial, unsigned* __restrict__ counters,
-                float* __restrict__ stats, float eps) {
+                float* __restrict__ stats, float eps, double* __restrict__ sums) {
     extern __shared__ float s_part[];       // [row_split][C][2]
     __shared__ bool s_last;
     const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
@@ -183,8 +183,14 @@ gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int 
             const double mean = sum / cnt;
             double var = sq / cnt - mean * mean;
             if (var < 0.0) var = 0.0;
-            stats[(static_cast<size_t>(n) * kGroups + g) * 2] = static_cast<float>(mean);
-            stats[(static_cast<size_t>(n) * kGroups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+            if (stats != nullptr) {
+                stats[(static_cast<size_t>(n) * kGroups + g) * 2] = static_cast<float>(mean);
+                stats[(static_cast<size_t>(n) * kGroups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+            }
+            if (sums != nullptr) {           // raw (sum, sum of squares): partial statistics of a sharded instance
+                sums[(static_cast<size_t>(n) * kGroups + g) * 2] = sum;
+                sums[(static_cast<size_t>(n) * kGroups + g) * 2 + 1] = sq;
+            }
         }
         if (tid == 0) counters[n] = 0;   // self-cleaning: ready for the next launch
     }
@@ -546,8 +552,57 @@ extern "C" int dcb_group_norm_stats(const float* x1, const float* x2, int C1, in
     const GnPlan pl = plan_stats(C1, C2, S);
     const size_t smem = static_cast<size_t>(pl.row_split) * C * 2 * sizeof(float);
     gn_stats_kernel<float><<<dim3(pl.nchunks, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-        x1, x2, C1, C2, S, pl.rows_per_chunk, pl.row_split, static_cast<float*>(workspace), counters, stats, eps);
+        x1, x2, C1, C2, S, pl.rows_per_chunk, pl.row_split, static_cast<float*>(workspace), counters, stats, eps, nullptr);
     return check_launch("group_norm_stats");
+}
+
+extern "C" int dcb_group_norm_sums(const float* x1, const float* x2, int C1, int C2, int G, int S, double* sums,
+                                   void* workspace, unsigned* counters, void* stream) {
+    const int C = C1 + C2;
+    if (x1 == nullptr || sums == nullptr || workspace == nullptr || counters == nullptr)
+        return set_error(DCB_ERR_INVALID, "group_norm_sums: null argument");
+    if (C % kGroups != 0 || (C1 & 3) || (C2 & 3) || G < 1 || S < 1 || (C2 > 0 && x2 == nullptr) || C > kMaxC)
+        return set_error(DCB_ERR_INVALID, "group_norm_sums: C1=%d C2=%d G=%d S=%d", C1, C2, G, S);
+    const GnPlan pl = plan_stats(C1, C2, S);
+    const size_t smem = static_cast<size_t>(pl.row_split) * C * 2 * sizeof(float);
+    gn_stats_kernel<float><<<dim3(pl.nchunks, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        x1, x2, C1, C2, S, pl.rows_per_chunk, pl.row_split, static_cast<float*>(workspace), counters, nullptr, 0.f, sums);
+    return check_launch("group_norm_sums");
+}
+
+extern "C" int dcb_group_norm_sums_bf16(const void* x, int C, int G, int S, double* sums, void* workspace,
+                                        unsigned* counters, void* stream) {
+    if (x == nullptr || sums == nullptr || workspace == nullptr || counters == nullptr)
+        return set_error(DCB_ERR_INVALID, "group_norm_sums_bf16: null argument");
+    if (C % kGroups != 0 || (C & 7) || G < 1 || S < 1 || C > kMaxC)
+        return set_error(DCB_ERR_INVALID, "group_norm_sums_bf16: C=%d G=%d S=%d", C, G, S);
+    const GnPlan pl = plan_stats(C, 0, S);
+    const size_t smem = static_cast<size_t>(pl.row_split) * C * 2 * sizeof(float);
+    gn_stats_kernel<__nv_bfloat16><<<dim3(pl.nchunks, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), nullptr, C, 0, S, pl.rows_per_chunk, pl.row_split,
+        static_cast<float*>(workspace), counters, nullptr, 0.f, sums);
+    return check_launch("group_norm_sums_bf16");
+}
+
+// (mean, rstd) from (all-reduced) raw sums: count = elements per (instance, group) over ALL shards.
+__global__ void gn_stats_from_sums_kernel(const double* __restrict__ sums, int n, double count, float eps,
+                                          float* __restrict__ stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double mean = sums[2 * i] / count;
+    double var = sums[2 * i + 1] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[2 * i] = static_cast<float>(mean);
+    stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+extern "C" int dcb_group_norm_stats_from_sums(const double* sums, int G, double count, float eps, float* stats,
+                                              void* stream) {
+    if (sums == nullptr || stats == nullptr || G < 1 || count <= 0.0)
+        return set_error(DCB_ERR_INVALID, "group_norm_stats_from_sums: bad argument");
+    const int n = G * kGroups;
+    gn_stats_from_sums_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(sums, n, count, eps, stats);
+    return check_launch("group_norm_stats_from_sums");
 }
 
 // (mean, rstd) of instance n / group g from the per-column (sum, sumsq) partial rows a tap_gemm epilogue wrote.
@@ -612,7 +667,7 @@ extern "C" int dcb_group_norm_stats_bf16(const void* x, int C, int G, int S, flo
     const size_t smem = static_cast<size_t>(pl.row_split) * C * 2 * sizeof(float);
     gn_stats_kernel<__nv_bfloat16><<<dim3(pl.nchunks, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), nullptr, C, 0, S, pl.rows_per_chunk, pl.row_split,
-        static_cast<float*>(workspace), counters, stats, eps);
+        static_cast<float*>(workspace), counters, stats, eps, nullptr);
     return check_launch("group_norm_stats_bf16");
 }
 

@@ -373,16 +373,30 @@ class UNetModel(PackedModule):
             return CrossAttentionContext(text, TEXT_CONTEXT_LEN, t, image, IMG_TOKENS_PER_FRAME, 1)
         return make_context(context, t, self.image_cross_attention)
 
-    def _run(self, layers, h, emb_all, pk, ctx, skip=None):
+    @staticmethod
+    def _temporal(mod, h, shard):
+        """Frame-sharded mode: a temporal block needs every frame of a pixel -> transpose the residual stream
+        frames -> pixels (all-to-all), run the block on this rank's pixel columns with its 5-D GroupNorm statistics
+        all-reduced, transpose back."""
+        from dynamicrafter_b200.parallel import frames_to_pixels, pixels_to_frames
+        hw = h.H * h.W
+        hp = Act(frames_to_pixels(h.x, h.B, h.T, hw, shard), h.B, h.T * shard.world, 1, hw // shard.world)
+        with ops.sharded_group_norm(shard):
+            op = mod._fwd(hp)
+        return h.like(pixels_to_frames(op.x, h.B, hp.T, hp.W, shard))
+
+    def _run(self, layers, h, emb_all, pk, ctx, skip=None, shard=None):
         for layer in layers:
             if isinstance(layer, ResBlock):
                 off, n = pk["emb_off"][id(layer)]
-                h = layer._fwd(h, emb_all[:, off:off + n], h.T * h.H * h.W, skip=skip)
+                h = layer._fwd(h, emb_all[:, off:off + n], h.T * h.H * h.W, skip=skip, temporal=shard is None)
+                if shard is not None and layer.use_temporal_conv:
+                    h = self._temporal(layer.temopral_conv, h, shard)
                 skip = None
             elif isinstance(layer, SpatialTransformer):
                 h = layer._fwd(h, ctx)
             elif isinstance(layer, TemporalTransformer):
-                h = layer._fwd(h)
+                h = layer._fwd(h) if shard is None else self._temporal(layer, h, shard)
             elif isinstance(layer, (Downsample, Upsample)):
                 h = layer._fwd(h)
             else:
@@ -406,8 +420,8 @@ class UNetModel(PackedModule):
             fs = torch.full((b,), self.default_fs, dtype=torch.long, device=dev) if fs is None \
                 else fs.to(device=dev, dtype=torch.long)
         context = context.to(device=dev, dtype=torch.float32)
-        if not getattr(self, "use_cuda_graph", False):
-            return self._forward_impl(x, timesteps, context, fs)
+        if not getattr(self, "use_cuda_graph", False) or getattr(self, "frame_shard", None) is not None:
+            return self._forward_impl(x, timesteps, context, fs)       # collectives are not captured
         return self._forward_graphed(x, timesteps, context, fs)
 
     def _forward_graphed(self, x, timesteps, context, fs):
@@ -444,6 +458,15 @@ class UNetModel(PackedModule):
 
     def _forward_impl(self, x, timesteps, context, fs):
         pk = self.packed()
+        shard = getattr(self, "frame_shard", None)      # parallel.FrameShard: this rank denoises frames t0..t1 only
+        if shard is not None:
+            t_full = x.shape[2]
+            t0, t1 = shard.frames(t_full)
+            x = x[:, :, t0:t1].contiguous()
+            if context.shape[1] == TEXT_CONTEXT_LEN + t_full * IMG_TOKENS_PER_FRAME:
+                i0 = TEXT_CONTEXT_LEN + t0 * IMG_TOKENS_PER_FRAME
+                i1 = TEXT_CONTEXT_LEN + t1 * IMG_TOKENS_PER_FRAME
+                context = torch.cat([context[:, :TEXT_CONTEXT_LEN], context[:, i0:i1]], 1)
         b, cin, t, hh, ww = x.shape
         mc = self.model_channels
         dev = x.device
@@ -465,14 +488,18 @@ class UNetModel(PackedModule):
         hs = []
         for i, module in enumerate(self.input_blocks):
             if i > 0:
-                h = self._run(module, h, emb_all, pk, ctx)
+                h = self._run(module, h, emb_all, pk, ctx, shard=shard)
             if i == 0 and self.addition_attention:
-                h = self.init_attn[0]._fwd(h)
+                h = self.init_attn[0]._fwd(h) if shard is None else self._temporal(self.init_attn[0], h, shard)
             hs.append(h)
-        h = self._run(self.middle_block, h, emb_all, pk, ctx)
+        h = self._run(self.middle_block, h, emb_all, pk, ctx, shard=shard)
         for module in self.output_blocks:
-            h = self._run(module, h, emb_all, pk, ctx, skip=hs.pop().x)
+            h = self._run(module, h, emb_all, pk, ctx, skip=hs.pop().x, shard=shard)
         g = self.out[0]
         y = ops.group_norm(h.x, b * t, hh * ww, g.weight, g.bias, g.eps, silu=True)
         o = ops.conv3x3(y, b * t, hh, ww, pk["w_out"], bias=pk["b_out"])
-        return ops.rows_to_nchw(o, b, self.out_channels, t, hh, ww).to(x.dtype)
+        out = ops.rows_to_nchw(o, b, self.out_channels, t, hh, ww)
+        if shard is not None:
+            from dynamicrafter_b200.parallel import all_gather_frames
+            out = all_gather_frames(out, shard)          # every rank applies the (tiny) DDIM update to all frames
+        return out.to(x.dtype)

@@ -225,10 +225,57 @@ def _stats_from_colsums(cs, G, S, C, eps, dev):
     return stats
 
 
+_SHARDED_GN = [None]      # FrameShard while the instances of group_norm calls are spread over ranks
+
+
+class sharded_group_norm:
+    """Context: every group_norm inside normalises instances whose rows are split over the ranks of `shard`
+    (the 5-D GroupNorms of the temporal blocks in frame-sharded mode): local raw sums -> all-reduce -> apply."""
+
+    def __init__(self, shard):
+        self.shard = shard
+
+    def __enter__(self):
+        self.prev, _SHARDED_GN[0] = _SHARDED_GN[0], self.shard
+
+    def __exit__(self, *exc):
+        _SHARDED_GN[0] = self.prev
+
+
+def _group_norm_sharded(x1, G, S, gamma, beta, eps, silu, shard):
+    from .parallel import all_reduce_sums
+    L, dev, C = _lib.lib(), x1.device, x1.shape[1]
+    assert x1.is_contiguous() and x1.shape[0] == G * S
+    ws, cnt = _gn_scratch(dev, G)
+    sums = torch.empty((G, 32, 2), dtype=torch.float64, device=dev)
+    if x1.dtype == BF16:
+        check(L.dcb_group_norm_sums_bf16(ptr(x1), _c_i(C), _c_i(G), _c_i(S), ptr(sums), ptr(ws), ptr(cnt), _stream()),
+              "dcb_group_norm_sums_bf16")
+    else:
+        check(L.dcb_group_norm_sums(ptr(x1), None, _c_i(C), _c_i(0), _c_i(G), _c_i(S), ptr(sums), ptr(ws), ptr(cnt),
+                                    _stream()), "dcb_group_norm_sums")
+    all_reduce_sums(sums, shard)
+    stats = torch.empty((G, 32, 2), dtype=F32, device=dev)
+    count = float(S) * shard.world * (C // 32)
+    check(L.dcb_group_norm_stats_from_sums(ptr(sums), _c_i(G), ctypes.c_double(count), _c_f(eps), ptr(stats), _stream()),
+          "dcb_group_norm_stats_from_sums")
+    y = torch.empty((G * S, C), dtype=BF16, device=dev)
+    if x1.dtype == BF16:
+        check(L.dcb_group_norm_apply_bf16(ptr(x1), _c_i(C), _c_i(G), _c_i(S), ptr(stats), ptr(gamma), ptr(beta),
+                                          _c_i(1 if silu else 0), ptr(y), _stream()), "dcb_group_norm_apply_bf16")
+    else:
+        check(L.dcb_group_norm_apply(ptr(x1), None, _c_i(C), _c_i(0), _c_i(G), _c_i(S), ptr(stats), ptr(gamma),
+                                     ptr(beta), _c_i(1 if silu else 0), ptr(y), None, _stream()), "dcb_group_norm_apply")
+    return y
+
+
 def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False, want_norm=True, colsums=None):
     """x1: fp32 [G*S, C1] (+ x2 [G*S, C2] concatenated on channels) -> bf16 normalised operand
     (and/or bf16 raw copy of the concat)."""
     require_cuda(x1, x2, gamma, beta)
+    if _SHARDED_GN[0] is not None:
+        assert x2 is None and not want_raw and want_norm and colsums is None
+        return _group_norm_sharded(x1, G, S, gamma, beta, eps, silu, _SHARDED_GN[0])
     if x1.dtype == BF16:
         # block-internal activation kept in bf16 by its producer: single source, normalised output only
         assert x2 is None and not want_raw and x1.is_contiguous() and x1.shape[0] == G * S

@@ -36,3 +36,60 @@ def all_gather_latents(local, counts=None, group=None):
 def frame_shard(n_frames, rank, world):
     """Frames of the gathered latents this rank decodes with the VAE (decode is per frame)."""
     return shard_range(n_frames, rank, world)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Frame-sharded single video (576x1024 latency mode, SURVEY.md 8(e) row 2).  Per-frame work (ResBlock 2-D part,
+# SpatialTransformer, up / down sampling) runs on the rank's own frames; the temporal blocks (TemporalConvBlock,
+# TemporalTransformer: attention.py:365-412, openaimodel3d.py:272-279) need every frame of a pixel, so the residual
+# stream is transposed frames <-> pixels with one all-to-all on each side of them, and the 5-D GroupNorms of those
+# blocks all-reduce their 64 partial sums per video.
+# ------------------------------------------------------------------------------------------------------------
+class FrameShard:
+    """Which frames / pixels of the video this rank owns.  T and every level's H*W must divide by the world size."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def frames(self, T):
+        if T % self.world:
+            raise ValueError(f"frame sharding needs T={T} divisible by the {self.world} ranks")
+        n = T // self.world
+        return self.rank * n, (self.rank + 1) * n
+
+
+def frames_to_pixels(x, B, T_loc, HW, shard):
+    """x: [B*T_loc*HW, C] rows (b, t_loc, p) of this rank's frames -> [B*T*HW_loc, C] rows (b, t, p_loc): every frame
+    of this rank's pixel block.  One all-to-all of the whole tensor minus the diagonal block."""
+    N, C = shard.world, x.shape[1]
+    if HW % N:
+        raise ValueError(f"frame sharding needs H*W={HW} divisible by the {N} ranks")
+    send = x.reshape(B, T_loc, N, HW // N, C).permute(2, 0, 1, 3, 4).contiguous()        # [dst, b, t_loc, p, c]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=shard.group)                                 # [src, b, t_loc, p, c]
+    return recv.permute(1, 0, 2, 3, 4).reshape(B * N * T_loc * (HW // N), C)              # (b, (src t_loc), p_loc)
+
+
+def pixels_to_frames(x, B, T, HW_loc, shard):
+    """Inverse of frames_to_pixels: [B*T*HW_loc, C] rows (b, t, p_loc) -> [B*T_loc*HW, C] rows (b, t_loc, p)."""
+    N, C = shard.world, x.shape[1]
+    T_loc = T // N
+    send = x.reshape(B, N, T_loc, HW_loc, C).permute(1, 0, 2, 3, 4).contiguous()          # [dst, b, t_loc, p_loc, c]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=shard.group)                                 # [src = pixel block, ...]
+    return recv.permute(1, 2, 0, 3, 4).reshape(B * T_loc * N * HW_loc, C)                 # (b, t_loc, (src p_loc))
+
+
+def all_gather_frames(local, shard):
+    """local: [B, C, T_loc, H, W] (this rank's frames) -> [B, C, T, H, W] on every rank."""
+    bufs = [torch.empty_like(local) for _ in range(shard.world)]
+    dist.all_gather(bufs, local.contiguous(), group=shard.group)
+    return torch.cat(bufs, dim=2)
+
+
+def all_reduce_sums(sums, shard):
+    """In-place SUM of the GroupNorm partial (sum, sum of squares) over the ranks holding the instance."""
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=shard.group)
+    return sums

@@ -1,0 +1,68 @@
+"""Frame-sharded UNet forward vs the same forward on one GPU (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/frame_shard_check.py
+
+Every rank builds the same tiny UNet (reference-generated golden fixture unet_tiny512.pt: weights / inputs from
+dynamicrafter_b200.synth), runs the unsharded forward locally, then the frame-sharded forward across the ranks, and
+checks (i) the sharded output is within the bf16 bar (rel-L2 <= 2e-2) of the REFERENCE golden, like the unsharded one,
+(ii) every rank ends with the identical full tensor, (iii) sharded vs unsharded differ by no more than two independent
+bf16 evaluations do (the GroupNorm partial sums are reduced in a different order, which re-rolls the bf16 roundings
+downstream; on this random-weight tiny model that alone moves the output by ~1.7e-2)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from conftest import load_golden, rel_l2                                             # noqa: E402
+from dynamicrafter_b200.synth import synth_state_dict, synth_input                   # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ["NCCL_DEBUG"] = "WARN"
+    dist.init_process_group("nccl", device_id=dev)
+    from dynamicrafter_b200.lvdm.modules.networks.openaimodel3d import UNetModel
+    from dynamicrafter_b200.parallel import FrameShard
+    g = load_golden("unet_tiny512.pt")
+    cfg, h, w, seed = g["cfg"], g["h"], g["w"], g["seed"]
+    T = cfg["temporal_length"]
+    m = UNetModel(**cfg)
+    m.load_state_dict(synth_state_dict(g["shapes"], seed), strict=True)
+    m = m.cuda().eval()
+    ok = True
+    for b in (1, 2):
+        x = torch.cat([synth_input("x", (1, cfg["in_channels"], T, h, w), seed + i) for i in range(b)])
+        ctx = torch.cat([synth_input("context", (1, 77 + 16 * T, cfg["context_dim"]), seed + i) for i in range(b)])
+        ts = torch.tensor([g["t_val"] - 7 * i for i in range(b)], dtype=torch.long)
+        fs = torch.tensor([cfg["default_fs"] + 2 * i for i in range(b)], dtype=torch.long) if g["with_fs"] else None
+        args = (x.cuda(), ts.cuda())
+        kw = dict(context=ctx.cuda(), fs=None if fs is None else fs.cuda())
+        m.frame_shard = None
+        y_one = m(*args, **kw)
+        m.frame_shard = FrameShard()
+        y_sh = m(*args, **kw)
+        torch.cuda.synchronize()
+        e_pair = rel_l2(y_sh.cpu(), y_one.cpu())
+        e_gold = rel_l2(y_sh[:1].cpu(), g["y"]) if g["b"] == 1 else float("nan")
+        same = [torch.empty_like(y_sh) for _ in range(world)]
+        dist.all_gather(same, y_sh)
+        identical = all(torch.equal(s, same[0]) for s in same)
+        if rank == 0:
+            print(f"b={b} world={world}: sharded vs single rel-L2 {e_pair:.3e}, sharded vs reference golden {e_gold:.3e}, "
+                  f"ranks identical: {identical}", flush=True)
+        ok = ok and e_pair < 2.5e-2 and e_gold < 2e-2 and identical and y_sh.shape == y_one.shape
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if float(flag) == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()

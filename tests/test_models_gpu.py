@@ -246,3 +246,20 @@ def test_unet_full_512_config_vs_oracle_reduced_frames():
     err = rel_l2(y, ref)
     print(f"\nfull 512-config UNet (2 frames, 16x24 latent): rel-L2 vs oracle {err:.3e}")
     assert err < BF16_TOL
+
+
+def test_frame_sharded_unet_matches_single_gpu():
+    """frames sharded over 2 GPUs, all-to-all around the temporal blocks (needs >= 2 GPUs)."""
+    import os, socket, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(here, "frame_shard_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0
