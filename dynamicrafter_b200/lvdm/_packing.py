@@ -23,6 +23,9 @@ BF16_VAE = "vae" in _LOWP or "all" in _LOWP
 # statistics pass).  Measured on B200 at the 512 config: GroupNorm -0.9 ms but GEMM epilogues +1.3 ms per step, so it
 # is OFF by default (DCB_FUSED_GN_STATS=1 enables it); see DESIGN.md.
 FUSED_GN_STATS = _os.environ.get("DCB_FUSED_GN_STATS", "0") == "1"
+# frame-sharded mode: also capture the NCCL calls of a forward in the CUDA graph.  Works (94.4 vs 97.7 ms/step at the
+# 1024 config on 2 GPUs) but process-group teardown then hangs with torch 2.11 / NCCL 2.28 -> off by default.
+GRAPH_COLLECTIVES = _os.environ.get("DCB_GRAPH_COLLECTIVES", "0") == "1"
 
 
 def _pad64(c):

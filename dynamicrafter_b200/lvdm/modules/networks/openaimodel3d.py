@@ -420,8 +420,9 @@ class UNetModel(PackedModule):
             fs = torch.full((b,), self.default_fs, dtype=torch.long, device=dev) if fs is None \
                 else fs.to(device=dev, dtype=torch.long)
         context = context.to(device=dev, dtype=torch.float32)
-        if not getattr(self, "use_cuda_graph", False) or getattr(self, "frame_shard", None) is not None:
-            return self._forward_impl(x, timesteps, context, fs)       # collectives are not captured
+        if not getattr(self, "use_cuda_graph", False) or \
+                (getattr(self, "frame_shard", None) is not None and not _packing.GRAPH_COLLECTIVES):
+            return self._forward_impl(x, timesteps, context, fs)
         return self._forward_graphed(x, timesteps, context, fs)
 
     def _forward_graphed(self, x, timesteps, context, fs):
