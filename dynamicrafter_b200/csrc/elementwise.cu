@@ -18,8 +18,16 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
 }
 
 // [B, C, T, HW] fp32 (the reference's NCTHW, openaimodel3d.py:566) -> rows (b,t,p) x Cpad bf16, zero padded.
+__device__ __forceinline__ void put8(__nv_bfloat16* p, const float* v) { *reinterpret_cast<uint4*>(p) = pack8_bf16(v); }
+__device__ __forceinline__ void put8(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// TOut = bf16 (operand) or float (fp32 parity mode) for the three conv-input layout kernels below
+template <typename TOut>
 __global__ void nchw_to_rows_kernel(const float* __restrict__ src, int B, int C, int T, int HW, int Cpad,
-                                    __nv_bfloat16* __restrict__ dst) {
+                                    TOut* __restrict__ dst) {
     const long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long rows = static_cast<long long>(B) * T * HW;
     if (row >= rows) return;
@@ -31,7 +39,7 @@ __global__ void nchw_to_rows_kernel(const float* __restrict__ src, int B, int C,
             const int c = c0 + e;
             v[e] = c < C ? __ldg(src + ((static_cast<long long>(b) * C + c) * T + t) * HW + p) : 0.f;
         }
-        *reinterpret_cast<uint4*>(dst + row * Cpad + c0) = pack8_bf16(v);
+        put8(dst + row * Cpad + c0, v);
     }
 }
 
@@ -46,8 +54,9 @@ __global__ void rows_to_nchw_kernel(const float* __restrict__ src, int ld, int B
 }
 
 // nearest x2 (openaimodel3d.py:103, ae_modules.py:124): fp32 [nf,H,W,C] -> bf16 [nf,2H,2W,C]
+template <typename TOut>
 __global__ void upsample2x_kernel(const float* __restrict__ src, int nf, int H, int W, int C,
-                                  __nv_bfloat16* __restrict__ dst) {
+                                  TOut* __restrict__ dst) {
     const int O = C >> 3;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(nf) * 4 * H * W * O;
@@ -59,13 +68,14 @@ __global__ void upsample2x_kernel(const float* __restrict__ src, int nf, int H, 
     const float* s = src + ((f * H + (y >> 1)) * W + (x >> 1)) * C + o * 8;
     const float4 a = __ldg(reinterpret_cast<const float4*>(s)), b = __ldg(reinterpret_cast<const float4*>(s) + 1);
     const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    *reinterpret_cast<uint4*>(dst + pix * C + o * 8) = pack8_bf16(v);
+    put8(dst + pix * C + o * 8, v);
 }
 
 // 2x2 phase split for the stride-2 conv (openaimodel3d.py:68): fp32 [nf,H,W,C] -> bf16 [4,nf,Hp,Wp,C],
 // plane (py*2+px)[f, i, j] = src[f, 2i+py, 2j+px] (zero where outside).
+template <typename TOut>
 __global__ void space_to_depth_kernel(const float* __restrict__ src, int nf, int H, int W, int C, int Hp, int Wp,
-                                      __nv_bfloat16* __restrict__ dst) {
+                                      TOut* __restrict__ dst) {
     const int O = C >> 3;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = 4LL * nf * Hp * Wp * O;
@@ -82,7 +92,7 @@ __global__ void space_to_depth_kernel(const float* __restrict__ src, int nf, int
         const float4 a = __ldg(reinterpret_cast<const float4*>(s)), b = __ldg(reinterpret_cast<const float4*>(s) + 1);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
-    *reinterpret_cast<uint4*>(dst + pix * C + o * 8) = pack8_bf16(v);
+    put8(dst + pix * C + o * 8, v);
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, long long n8, __nv_bfloat16* __restrict__ dst) {
@@ -248,9 +258,35 @@ extern "C" int dcb_nchw_to_rows(const float* src, int B, int C, int T, int HW, i
     if (!src || !dst_bf16 || B < 1 || C < 1 || T < 1 || HW < 1 || Cpad < C || (Cpad & 7))
         return set_error(DCB_ERR_INVALID, "nchw_to_rows: bad argument");
     const long long rows = static_cast<long long>(B) * T * HW;
-    nchw_to_rows_kernel<<<blocks_for(rows, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    nchw_to_rows_kernel<__nv_bfloat16><<<blocks_for(rows, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         src, B, C, T, HW, Cpad, static_cast<__nv_bfloat16*>(dst_bf16));
     return check_launch("nchw_to_rows");
+}
+
+// fp32-output variants of the three conv-input layout kernels (fp32 parity mode)
+extern "C" int dcb_nchw_to_rows_f32out(const float* src, int B, int C, int T, int HW, int Cpad, float* dst, void* stream) {
+    if (!src || !dst || B < 1 || C < 1 || T < 1 || HW < 1 || Cpad < C || (Cpad & 7))
+        return set_error(DCB_ERR_INVALID, "nchw_to_rows_f32out: bad argument");
+    const long long rows = static_cast<long long>(B) * T * HW;
+    nchw_to_rows_kernel<float><<<blocks_for(rows, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(src, B, C, T, HW, Cpad, dst);
+    return check_launch("nchw_to_rows_f32out");
+}
+
+extern "C" int dcb_upsample2x_f32out(const float* src, int nf, int H, int W, int C, float* dst, void* stream) {
+    if (!src || !dst || nf < 1 || H < 1 || W < 1 || C < 8 || (C & 7))
+        return set_error(DCB_ERR_INVALID, "upsample2x_f32out: bad argument");
+    const long long total = static_cast<long long>(nf) * 4 * H * W * (C >> 3);
+    upsample2x_kernel<float><<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, nf, H, W, C, dst);
+    return check_launch("upsample2x_f32out");
+}
+
+extern "C" int dcb_space_to_depth_f32out(const float* src, int nf, int H, int W, int C, float* dst, void* stream) {
+    if (!src || !dst || nf < 1 || H < 1 || W < 1 || C < 8 || (C & 7))
+        return set_error(DCB_ERR_INVALID, "space_to_depth_f32out: bad argument");
+    const int Hp = (H + 1) / 2, Wp = (W + 1) / 2;
+    const long long total = 4LL * nf * Hp * Wp * (C >> 3);
+    space_to_depth_kernel<float><<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, nf, H, W, C, Hp, Wp, dst);
+    return check_launch("space_to_depth_f32out");
 }
 
 extern "C" int dcb_rows_to_nchw(const float* src, int ld, int B, int C, int T, int HW, float* dst, void* stream) {
@@ -265,7 +301,7 @@ extern "C" int dcb_upsample2x(const float* src, int nf, int H, int W, int C, voi
     if (!src || !dst_bf16 || nf < 1 || H < 1 || W < 1 || C < 8 || (C & 7))
         return set_error(DCB_ERR_INVALID, "upsample2x: bad argument");
     const long long total = static_cast<long long>(nf) * 4 * H * W * (C >> 3);
-    upsample2x_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    upsample2x_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         src, nf, H, W, C, static_cast<__nv_bfloat16*>(dst_bf16));
     return check_launch("upsample2x");
 }
@@ -275,7 +311,7 @@ extern "C" int dcb_space_to_depth(const float* src, int nf, int H, int W, int C,
         return set_error(DCB_ERR_INVALID, "space_to_depth: bad argument");
     const int Hp = (H + 1) / 2, Wp = (W + 1) / 2;
     const long long total = 4LL * nf * Hp * Wp * (C >> 3);
-    space_to_depth_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    space_to_depth_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         src, nf, H, W, C, Hp, Wp, static_cast<__nv_bfloat16*>(dst_bf16));
     return check_launch("space_to_depth");
 }

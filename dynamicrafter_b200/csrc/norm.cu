@@ -284,12 +284,19 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 #ifndef DCB_GN_OCC
 #define DCB_GN_OCC 3        // resident blocks per SM the register allocation must allow
 #endif
-template <typename T>
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* v) { *reinterpret_cast<uint4*>(p) = pack8(v); }
+__device__ __forceinline__ void store8(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// TOut = bf16 (tensor-core operand) or float (fp32 parity mode, fp32_mode.cu)
+template <typename T, typename TOut = __nv_bfloat16>
 __global__ void __launch_bounds__(256, DCB_GN_OCC)
 gn_fused_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int C2, int S, int rows_per_chunk,
                 int row_split, float* __restrict__ partial, unsigned* __restrict__ counters, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
-                __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ raw) {
+                TOut* __restrict__ y, TOut* __restrict__ raw) {
     extern __shared__ float s_mem[];        // phase 1: [row_split][C][2] partial slots; phase 2: A[C] | B[C]
     __shared__ double s_fold[4][kGroups * 2];
     __shared__ float s_mr[kGroups * 2];
@@ -426,8 +433,8 @@ gn_fused_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int 
         const T* src = first ? (x1 + row0 * C1 + c0) : (x2 + row0 * C2 + (c0 - C1));
         const size_t sstep = static_cast<size_t>(rpp) * (first ? C1 : C2);
         const size_t dstep = static_cast<size_t>(rpp) * C;
-        __nv_bfloat16* dst = y + row0 * C + c0;
-        __nv_bfloat16* rdst = raw != nullptr ? raw + row0 * C + c0 : nullptr;
+        TOut* dst = y + row0 * C + c0;
+        TOut* rdst = raw != nullptr ? raw + row0 * C + c0 : nullptr;
         for (int r = my_r; r < nrows; r += rpp * U) {
             float v[U][8];
 #pragma unroll
@@ -436,13 +443,13 @@ gn_fused_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int 
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (r + u * rpp < nrows) {
-                    if (rdst != nullptr) *reinterpret_cast<uint4*>(rdst + u * dstep) = pack8(v[u]);
+                    if (rdst != nullptr) store8(rdst + u * dstep, v[u]);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const float t = fmaf(v[u][e], am[e], bm[e]);
-                        v[u][e] = do_silu ? silu_fast(t) : t;
+                        v[u][e] = do_silu ? (sizeof(TOut) == 4 ? t / (1.0f + expf(-t)) : silu_fast(t)) : t;
                     }
-                    *reinterpret_cast<uint4*>(dst + u * dstep) = pack8(v[u]);
+                    store8(dst + u * dstep, v[u]);
                 }
             }
             src += U * sstep;
@@ -456,10 +463,10 @@ gn_fused_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int 
 // LayerNorm over the last dim (C <= 1280*... kMaxQuads*128), one warp per row, values kept in
 // registers (two-pass variance), bf16 out.
 // ---------------------------------------------------------------------------------------------
-template <int kMaxQuads>
+template <int kMaxQuads, typename TOut = __nv_bfloat16>
 __global__ void __launch_bounds__(256)
 layer_norm_kernel(const float* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
-                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y) {
+                  const float* __restrict__ beta, float eps, TOut* __restrict__ y) {
     // persistent warps: row, row + W, row + 2W, ... with the next row's loads issued before the current row's
     // arithmetic (two rows in flight per warp)
     const int lane = threadIdx.x & 31;
@@ -501,19 +508,25 @@ layer_norm_kernel(const float* __restrict__ x, int rows, int C, const float* __r
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
         const float rstd = rsqrtf(sq * inv_c + eps);
-        __nv_bfloat16* yr = y + static_cast<size_t>(row) * C;
+        TOut* yr = y + static_cast<size_t>(row) * C;
 #pragma unroll
         for (int i = 0; i < kMaxQuads; ++i) {
             const int q = lane + i * 32;
             if (q < Q) {
                 const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
                 const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + q);
-                __nv_bfloat162 lo = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
-                __nv_bfloat162 hi = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
-                uint2 p;
-                p.x = *reinterpret_cast<uint32_t*>(&lo);
-                p.y = *reinterpret_cast<uint32_t*>(&hi);
-                *reinterpret_cast<uint2*>(yr + q * 4) = p;
+                const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
+                const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
+                if constexpr (sizeof(TOut) == 4) {
+                    *reinterpret_cast<float4*>(yr + q * 4) = make_float4(o0, o1, o2, o3);
+                } else {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1);
+                    __nv_bfloat162 hi = __floats2bfloat162_rn(o2, o3);
+                    uint2 p;
+                    p.x = *reinterpret_cast<uint32_t*>(&lo);
+                    p.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(yr + q * 4) = p;
+                }
             }
         }
         if (next >= rows) break;
@@ -706,7 +719,7 @@ extern "C" int dcb_group_norm_apply_bf16(const void* x, int C, int G, int S, con
     return check_launch("group_norm_apply_bf16");
 }
 
-template <typename T>
+template <typename T, typename TOut = __nv_bfloat16>
 static int launch_gn_fused(const T* x1, const T* x2, int C1, int C2, int G, int S, float eps, const float* gamma,
                            const float* beta, int silu_act, void* y, void* raw, void* workspace, unsigned* counters,
                            cudaStream_t stream) {
@@ -715,7 +728,7 @@ static int launch_gn_fused(const T* x1, const T* x2, int C1, int C2, int G, int 
     static int per_sm = -1;                                   // resident blocks per SM at the largest smem request
     if (per_sm < 0) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gn_fused_kernel<T>, 256, kMaxSplitC * 2 * sizeof(float)) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gn_fused_kernel<T, TOut>, 256, kMaxSplitC * 2 * sizeof(float)) !=
             cudaSuccess || n < 1)
             return set_error(DCB_ERR_CUDA, "group_norm_fused: occupancy query failed");
         per_sm = n > 6 ? 6 : n;
@@ -744,9 +757,9 @@ static int launch_gn_fused(const T* x1, const T* x2, int C1, int C2, int G, int 
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gn_fused_kernel<T>, x1, x2, C1, C2, S, rpc, split,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gn_fused_kernel<T, TOut>, x1, x2, C1, C2, S, rpc, split,
                                        static_cast<float*>(workspace), counters, eps, gamma, beta, silu_act,
-                                       static_cast<__nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(raw));
+                                       static_cast<TOut*>(y), static_cast<TOut*>(raw));
     if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "group_norm_fused launch: %s", cudaGetErrorString(e));
     return DCB_OK;
 }
@@ -761,6 +774,18 @@ extern "C" int dcb_group_norm_fused(const float* x1, const float* x2, int C1, in
         return set_error(DCB_ERR_INVALID, "group_norm_fused: C1=%d C2=%d G=%d S=%d", C1, C2, G, S);
     return launch_gn_fused<float>(x1, x2, C1, C2, G, S, eps, gamma, beta, silu_act, y_bf16, raw_bf16, workspace, counters,
                                   static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dcb_group_norm_fused_f32out(const float* x1, const float* x2, int C1, int C2, int G, int S, float eps,
+                                           const float* gamma, const float* beta, int silu_act, float* y, float* raw,
+                                           void* workspace, unsigned* counters, void* stream) {
+    const int C = C1 + C2;
+    if (x1 == nullptr || y == nullptr || gamma == nullptr || beta == nullptr || workspace == nullptr || counters == nullptr)
+        return set_error(DCB_ERR_INVALID, "group_norm_fused_f32out: null argument");
+    if (C % kGroups != 0 || (C1 & 7) || (C2 & 7) || G < 1 || S < 1 || (C2 > 0 && x2 == nullptr) || C > kMaxC)
+        return set_error(DCB_ERR_INVALID, "group_norm_fused_f32out: C1=%d C2=%d G=%d S=%d", C1, C2, G, S);
+    return launch_gn_fused<float, float>(x1, x2, C1, C2, G, S, eps, gamma, beta, silu_act, y, raw, workspace, counters,
+                                         static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dcb_group_norm_fused_bf16(const void* x, int C, int G, int S, float eps, const float* gamma,
@@ -792,4 +817,18 @@ extern "C" int dcb_layer_norm(const float* x, int rows, int C, const float* gamm
     else if (kq == 10) layer_norm_kernel<10><<<blocks, 256, 0, s>>>(x, rows, C, gamma, beta, eps, y);
     else layer_norm_kernel<20><<<blocks, 256, 0, s>>>(x, rows, C, gamma, beta, eps, y);
     return check_launch("layer_norm");
+}
+
+extern "C" int dcb_layer_norm_f32out(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,
+                                     float* y, void* stream) {
+    if (x == nullptr || y == nullptr || gamma == nullptr || beta == nullptr)
+        return set_error(DCB_ERR_INVALID, "layer_norm_f32out: null argument");
+    if (rows < 1 || C < 4 || (C & 3) || C > 10 * 128)
+        return set_error(DCB_ERR_INVALID, "layer_norm_f32out: rows=%d C=%d (C %% 4 == 0, C <= 1280)", rows, C);
+    int blocks = (rows + 7) / 8;
+    if (blocks > num_sms() * 2) blocks = num_sms() * 2;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (C <= 5 * 128) layer_norm_kernel<5, float><<<blocks, 256, 0, s>>>(x, rows, C, gamma, beta, eps, y);
+    else layer_norm_kernel<10, float><<<blocks, 256, 0, s>>>(x, rows, C, gamma, beta, eps, y);
+    return check_launch("layer_norm_f32out");
 }

@@ -28,12 +28,26 @@ FUSED_GN_STATS = _os.environ.get("DCB_FUSED_GN_STATS", "0") == "1"
 GRAPH_COLLECTIVES = _os.environ.get("DCB_GRAPH_COLLECTIVES", "0") == "1"
 
 
+from dynamicrafter_b200.precision import fp32_mode, get_precision
+
+
 def _pad64(c):
     return (c + 63) // 64 * 64
 
 
+def _split_w(w):
+    """fp32 parity mode: fp32 [N, taps, C] -> bf16 [N, taps * 3C], per tap (hi | hi | lo); pairs with the
+    (hi | lo | hi) split of the activations so that one GEMM sums a_hi w_hi + a_lo w_hi + a_hi w_lo."""
+    w = w.float()
+    hi = w.to(BF16)
+    lo = (w - hi.float()).to(BF16)
+    return torch.cat([hi, hi, lo], dim=-1).reshape(w.shape[0], -1).contiguous()
+
+
 def pack_linear(w):
     """[N, K] (or Conv1d/Conv2d k=1 [N, K, 1(,1)]) -> bf16 [N, K]."""
+    if fp32_mode():
+        return _split_w(w.detach().reshape(w.shape[0], 1, w.shape[1]))
     return w.detach().reshape(w.shape[0], w.shape[1]).to(BF16).contiguous()
 
 
@@ -41,6 +55,10 @@ def pack_conv3x3(w):
     """[N, C, 3, 3] -> bf16 [N, 9*Cpad] ordered (ky, kx, c); input channels zero-padded to 64."""
     N, C = w.shape[0], w.shape[1]
     Cp = _pad64(C)
+    if fp32_mode():
+        full = torch.zeros((N, 3, 3, Cp), dtype=torch.float32, device=w.device)
+        full[..., :C] = w.detach().permute(0, 2, 3, 1).float()
+        return _split_w(full.reshape(N, 9, Cp))
     out = torch.zeros((N, 3, 3, Cp), dtype=BF16, device=w.device)
     out[..., :C] = w.detach().permute(0, 2, 3, 1).to(BF16)
     return out.reshape(N, 9 * Cp).contiguous()
@@ -49,6 +67,8 @@ def pack_conv3x3(w):
 def pack_tconv3(w):
     """[N, C, 3, 1, 1] -> bf16 [N, 3*C] ordered (kt, c)."""
     N, C = w.shape[0], w.shape[1]
+    if fp32_mode():
+        return _split_w(w.detach().reshape(N, C, 3).permute(0, 2, 1))
     return w.detach().reshape(N, C, 3).permute(0, 2, 1).to(BF16).reshape(N, 3 * C).contiguous()
 
 
@@ -64,6 +84,8 @@ def geglu_block_n(inner):
 def pack_geglu(w, b):
     """[2*inner, K] -> rows interleaved per output tile: (BN/2 value rows, BN/2 gate rows) * tiles."""
     inner = w.shape[0] // 2
+    if fp32_mode():             # plain GEMM + separate exact gate: rows stay in (value..., gate...) order
+        return _split_w(w.detach().reshape(w.shape[0], 1, w.shape[1])), b.detach().float().contiguous(), 0
     bn = geglu_block_n(inner)
     half = bn // 2
     idx = torch.arange(inner, device=w.device).reshape(inner // half, half)
@@ -92,7 +114,7 @@ class PackedModule(nn.Module):
         if p0 is None or not p0.is_cuda:
             raise RuntimeError(f"{type(self).__name__}: parameters must live on a CUDA device "
                                "(dcb200 has no CPU path)")
-        key = (p0.device, self._own_version())
+        key = (p0.device, self._own_version(), get_precision())
         cache = self.__dict__.get("_packed_cache")
         if cache is None or cache[0] != key:
             with torch.no_grad():

@@ -11,6 +11,7 @@ import torch
 
 from . import _lib
 from ._lib import TapGemmArgs, check, ptr
+from .precision import fp32_mode
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -79,6 +80,17 @@ def tap_gemm(a, dims, strides, adims, taps, w, N, *, bias=None, group_bias=None,
     """Raw launch.  a: bf16 tensor; dims=(D1,D2,D3) output domain; strides=(s1,s2,s3) element strides
     of A; adims=(A1,A2,A3) extents of A; taps=[(o1,o2,o3),...]; w: bf16 [N, ntaps*C]."""
     require_cuda(a, w, bias, group_bias, residual, out_f32, out_bf16)
+    if a.dtype == F32:
+        # fp32 parity mode: A -> [hi | lo | hi] (3C bf16 columns per row); w was packed as [hi | hi | lo] per tap
+        assert fp32_mode() and a.stride(1) == 1 and a.dim() == 2 and out_bf16 is None
+        C0, pitch = a.shape[1], a.stride(0)
+        assert w.shape[1] == 3 * C0 * len(taps), "weights are not packed for the fp32 mode"
+        assert all(s_ % pitch == 0 for s_ in strides)
+        a3 = torch.empty((a.shape[0], 3 * C0), dtype=BF16, device=a.device)
+        check(_lib.lib().dcb_split_bf16x3(ptr(a), _c_ll(a.shape[0]), _c_i(C0), _c_ll(pitch), ptr(a3), _stream()),
+              "dcb_split_bf16x3")
+        strides = tuple(s_ // pitch * 3 * C0 for s_ in strides)
+        a = a3
     assert a.dtype == BF16 and w.dtype == BF16 and w.stride(1) == 1
     C = w.shape[1] // len(taps)
     args = TapGemmArgs()
@@ -115,6 +127,8 @@ def tap_gemm(a, dims, strides, adims, taps, w, N, *, bias=None, group_bias=None,
 
 def _outputs(rows, n_out, out, want_f32, want_bf16, dev):
     of = ob = None
+    if fp32_mode() and out is None:
+        want_f32, want_bf16 = True, False
     if out is not None:
         if out.dtype == F32:
             of = out
@@ -136,6 +150,21 @@ def linear(a, w, *, bias=None, residual=None, geglu=False, f32=False, bf16=True,
            group_bias=None, rows_per_group=0, out_scale=1.0, block_n=0):
     """a: bf16 [M, K] (row stride may exceed K); w: bf16 [N, K] -> [M, N] (or N/2 for geglu)."""
     M, K = a.shape
+    if a.dtype == F32:                      # fp32 parity mode
+        assert a.stride(1) == 1 and w.shape[1] == 3 * K
+        N = N or w.shape[0]
+        if geglu:                           # plain GEMM (weights not interleaved) + exact-erf gate on the CUDA cores
+            assert residual is None and out is None
+            both = linear(a, w, bias=bias, N=N, out_scale=out_scale)
+            o = torch.empty((M, N // 2), dtype=F32, device=a.device)
+            check(_lib.lib().dcb_geglu_f32(ptr(both), _c_ll(M), _c_i(N // 2), _c_ll(both.stride(0)), ptr(o), _stream()),
+                  "dcb_geglu_f32")
+            return o
+        of, ob, ld = _outputs(M, N, out, True, False, a.device)
+        s1 = a.stride(0)
+        tap_gemm(a, (M, 1, 1), (s1, s1 * M, s1 * M), (M, 1, 1), [(0, 0, 0)], w, N, bias=bias, residual=residual,
+                 out_f32=of, ld_out=ld, group_bias=group_bias, rows_per_group=rows_per_group, out_scale=out_scale)
+        return of
     assert a.stride(1) == 1 and w.shape[1] == K
     N = N or w.shape[0]
     n_out = N // 2 if geglu else N
@@ -155,7 +184,7 @@ def conv3x3(a, nf, H, W, w, *, bias=None, residual=None, group_bias=None, rows_p
             f32=True, bf16=False, out=None, N=None, stats=False):
     """a: bf16 [nf*H*W, C] channels-last frames; w: bf16 [N, 9*C] ordered (ky, kx, c). Stride 1, pad 1."""
     C = a.shape[1]
-    assert a.stride(1) == 1 and a.stride(0) == C and w.shape[1] == 9 * C
+    assert a.stride(1) == 1 and a.stride(0) == C and w.shape[1] == (27 if a.dtype == F32 else 9) * C
     N = N or w.shape[0]
     of, ob, ld = _outputs(nf * H * W, N, out, f32, bf16, a.device)
     cs = _make_colsums((W, H, nf), N, a.device) if (stats and colsum_supported((W, H, nf))) else None
@@ -168,7 +197,7 @@ def conv3x3(a, nf, H, W, w, *, bias=None, residual=None, group_bias=None, rows_p
 def tconv3(a, B, T, HW, w, *, bias=None, residual=None, f32=True, bf16=False, out=None, stats=False):
     """Temporal (3,1,1) conv.  a: bf16 [B*T*HW, C]; w: bf16 [N, 3*C] ordered (kt, c). Pad 1 frame."""
     C = a.shape[1]
-    assert a.stride(1) == 1 and a.stride(0) == C and w.shape[1] == 3 * C
+    assert a.stride(1) == 1 and a.stride(0) == C and w.shape[1] == (9 if a.dtype == F32 else 3) * C
     N = w.shape[0]
     of, ob, ld = _outputs(B * T * HW, N, out, f32, bf16, a.device)
     cs = _make_colsums((HW, T, B), N, a.device) if (stats and colsum_supported((HW, T, B))) else None
@@ -273,6 +302,17 @@ def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False
     """x1: fp32 [G*S, C1] (+ x2 [G*S, C2] concatenated on channels) -> bf16 normalised operand
     (and/or bf16 raw copy of the concat)."""
     require_cuda(x1, x2, gamma, beta)
+    if fp32_mode():
+        assert _SHARDED_GN[0] is None, "the fp32 parity mode is single-GPU"
+        assert x1.dtype == F32 and x1.is_contiguous() and x1.shape[0] == G * S and want_norm
+        C1, C2, dev, L = x1.shape[1], (0 if x2 is None else x2.shape[1]), x1.device, _lib.lib()
+        ws, cnt = _gn_scratch(dev, G)
+        y = torch.empty((G * S, C1 + C2), dtype=F32, device=dev)
+        raw = torch.empty((G * S, C1 + C2), dtype=F32, device=dev) if want_raw else None
+        check(L.dcb_group_norm_fused_f32out(ptr(x1), ptr(x2), _c_i(C1), _c_i(C2), _c_i(G), _c_i(S), _c_f(eps), ptr(gamma),
+                                            ptr(beta), _c_i(1 if silu else 0), ptr(y), ptr(raw), ptr(ws), ptr(cnt),
+                                            _stream()), "dcb_group_norm_fused_f32out")
+        return (y, raw) if want_raw else y
     if _SHARDED_GN[0] is not None:
         assert x2 is None and not want_raw and want_norm and colsums is None
         return _group_norm_sharded(x1, G, S, gamma, beta, eps, silu, _SHARDED_GN[0])
@@ -339,6 +379,11 @@ def layer_norm(x, gamma, beta, eps=1e-5):
     require_cuda(x, gamma, beta)
     assert x.dtype == F32 and x.is_contiguous()
     rows, C = x.shape
+    if fp32_mode():
+        y = torch.empty((rows, C), dtype=F32, device=x.device)
+        check(_lib.lib().dcb_layer_norm_f32out(ptr(x), _c_i(rows), _c_i(C), ptr(gamma), ptr(beta), _c_f(eps), ptr(y),
+                                               _stream()), "dcb_layer_norm_f32out")
+        return y
     y = torch.empty((rows, C), dtype=BF16, device=x.device)
     check(_lib.lib().dcb_layer_norm(ptr(x), _c_i(rows), _c_i(C), ptr(gamma), ptr(beta), _c_f(eps), ptr(y), _stream()),
           "dcb_layer_norm")
@@ -350,20 +395,25 @@ def flash_attention(q, segments, batch, heads, nq, scale, out=None):
     """q: bf16 2-D view [batch*nq, >= heads*64]; segments: list of (k, v, nk, kv_batch_div, seg_scale) with
     k/v 2-D views [kv_batches*nk, >= heads*64].  Returns bf16 [batch*nq, heads*64]."""
     require_cuda(q)
+    f32 = q.dtype == F32                    # fp32 parity mode: CUDA-core attention on fp32 q / k / v
     a = _lib.AttentionArgs()
     a.q, a.ldq = q.data_ptr(), q.stride(0)
     a.nseg = len(segments)
     for i, (k, v, nk, div, sc) in enumerate(segments):
         require_cuda(k, v)
-        assert k.dtype == BF16 and v.dtype == BF16 and k.stride(1) == 1 and v.stride(1) == 1
+        assert k.dtype == q.dtype and v.dtype == q.dtype and k.stride(1) == 1 and v.stride(1) == 1
         a.k[i], a.v[i] = k.data_ptr(), v.data_ptr()
         a.ldk[i], a.ldv[i] = k.stride(0), v.stride(0)
         a.nk[i], a.kv_batch_div[i], a.seg_scale[i] = nk, div, sc
     a.batch, a.heads, a.nq, a.head_dim = batch, heads, nq, 64
     if out is None:
-        out = torch.empty((batch * nq, heads * 64), dtype=BF16, device=q.device)
+        out = torch.empty((batch * nq, heads * 64), dtype=q.dtype, device=q.device)
     a.o, a.ldo = out.data_ptr(), out.stride(0)
     a.softmax_scale = scale
+    if f32:
+        assert fp32_mode() and out.dtype == F32
+        check(_lib.lib().dcb_attention_f32(ctypes.byref(a), _c_i(1), _stream()), "dcb_attention_f32")
+        return out
     check(_lib.lib().dcb_flash_attention(ctypes.byref(a), _stream()), "dcb_flash_attention")
     return out
 
@@ -371,6 +421,19 @@ def flash_attention(q, segments, batch, heads, nq, scale, out=None):
 def temporal_attention(q, k, v, B, L, HW, heads, scale, out=None):
     """q/k/v: bf16 2-D views [B*L*HW, >= heads*64] (rows ordered b, frame, pixel)."""
     require_cuda(q, k, v)
+    if q.dtype == F32:                      # fp32 parity mode: B*HW interleaved sequences of L tokens
+        assert fp32_mode() and out is None
+        out = torch.empty((B * L * HW, heads * 64), dtype=F32, device=q.device)
+        a = _lib.AttentionArgs()
+        a.q, a.ldq = q.data_ptr(), q.stride(0)
+        a.nseg = 1
+        a.k[0], a.v[0], a.ldk[0], a.ldv[0] = k.data_ptr(), v.data_ptr(), k.stride(0), v.stride(0)
+        a.nk[0], a.kv_batch_div[0], a.seg_scale[0] = L, 1, 1.0
+        a.batch, a.heads, a.nq, a.head_dim = B * HW, heads, L, 64
+        a.o, a.ldo = out.data_ptr(), out.stride(0)
+        a.softmax_scale = scale
+        check(_lib.lib().dcb_attention_f32(ctypes.byref(a), _c_i(HW), _stream()), "dcb_attention_f32")
+        return out
     if out is None:
         out = torch.empty((B * L * HW, heads * 64), dtype=BF16, device=q.device)
     check(_lib.lib().dcb_temporal_attention(ptr(q), ptr(k), ptr(v), ptr(out), _c_ll(q.stride(0)), _c_ll(k.stride(0)),
@@ -398,6 +461,11 @@ def nchw_to_rows(x, Cpad):
         T = 1
     else:
         B, C, T, H, W = x.shape
+    if fp32_mode():
+        out = torch.empty((B * T * H * W, Cpad), dtype=F32, device=x.device)
+        check(_lib.lib().dcb_nchw_to_rows_f32out(ptr(x), _c_i(B), _c_i(C), _c_i(T), _c_i(H * W), _c_i(Cpad), ptr(out),
+                                                 _stream()), "dcb_nchw_to_rows_f32out")
+        return out
     out = torch.empty((B * T * H * W, Cpad), dtype=BF16, device=x.device)
     check(_lib.lib().dcb_nchw_to_rows(ptr(x), _c_i(B), _c_i(C), _c_i(T), _c_i(H * W), _c_i(Cpad), ptr(out), _stream()),
           "dcb_nchw_to_rows")
@@ -416,6 +484,11 @@ def rows_to_nchw(rows, B, C, T, H, W, five_d=True):
 def upsample2x(x, nf, H, W):
     require_cuda(x)
     C = x.shape[1]
+    if fp32_mode():
+        out = torch.empty((nf * 4 * H * W, C), dtype=F32, device=x.device)
+        check(_lib.lib().dcb_upsample2x_f32out(ptr(x), _c_i(nf), _c_i(H), _c_i(W), _c_i(C), ptr(out), _stream()),
+              "dcb_upsample2x_f32out")
+        return out
     out = torch.empty((nf * 4 * H * W, C), dtype=BF16, device=x.device)
     check(_lib.lib().dcb_upsample2x(ptr(x), _c_i(nf), _c_i(H), _c_i(W), _c_i(C), ptr(out), _stream()), "dcb_upsample2x")
     return out
@@ -425,6 +498,11 @@ def space_to_depth(x, nf, H, W):
     require_cuda(x)
     C = x.shape[1]
     Hp, Wp = (H + 1) // 2, (W + 1) // 2
+    if fp32_mode():
+        out = torch.empty((4 * nf * Hp * Wp, C), dtype=F32, device=x.device)
+        check(_lib.lib().dcb_space_to_depth_f32out(ptr(x), _c_i(nf), _c_i(H), _c_i(W), _c_i(C), ptr(out), _stream()),
+              "dcb_space_to_depth_f32out")
+        return out
     out = torch.empty((4 * nf * Hp * Wp, C), dtype=BF16, device=x.device)
     check(_lib.lib().dcb_space_to_depth(ptr(x), _c_i(nf), _c_i(H), _c_i(W), _c_i(C), ptr(out), _stream()),
           "dcb_space_to_depth")
@@ -455,6 +533,8 @@ def conv3x3_s2(planes, nf, H, W, w, *, bias=None, f32=True, bf16=False):
 
 def cast_bf16(x):
     require_cuda(x)
+    if fp32_mode():
+        return x                            # operands stay fp32; the GEMM splits them
     assert x.dtype == F32 and x.is_contiguous() and x.numel() % 8 == 0
     out = torch.empty(x.shape, dtype=BF16, device=x.device)
     check(_lib.lib().dcb_cast_bf16(ptr(x), _c_ll(x.numel()), ptr(out), _stream()), "dcb_cast_bf16")

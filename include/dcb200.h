@@ -183,6 +183,26 @@ int dcb_small_linear(const float* a, int lda, const float* w, const float* bias,
                      int silu_in, int silu_out, int accumulate, float* out, int ldo, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * fp32 parity mode (north_star: per-step eps within rel-L2 <= 1e-3 of the fp32 reference; csrc/fp32_mode.cu).
+ * Contractions stay on the tensor cores: an fp32 operand becomes three bf16 columns blocks [hi | lo | hi]
+ * (dcb_split_bf16x3), the weights [hi | hi | lo], and dcb_tap_gemm runs over the 3x longer K.  Everything else
+ * stays fp32: *_f32out variants of the operand producers, exact-erf GEGLU and CUDA-core attention.
+ * dcb_attention_f32: same argument block as dcb_flash_attention with float q/k/v/o; inner > 1 selects
+ * `inner` interleaved sequences (token stride = inner rows: temporal attention over '(b hw) t c').
+ * ------------------------------------------------------------------------------------------ */
+int dcb_split_bf16x3(const float* x, long long rows, int C, long long ldx, void* out_bf16, void* stream);
+int dcb_geglu_f32(const float* x, long long rows, int inner, long long ldx, float* out, void* stream);
+int dcb_attention_f32(const dcb_attention_args* args, int inner, void* stream);
+int dcb_group_norm_fused_f32out(const float* x1, const float* x2, int C1, int C2, int G, int S, float eps,
+                                const float* gamma, const float* beta, int silu_act, float* y, float* raw,
+                                void* workspace, unsigned* counters, void* stream);
+int dcb_layer_norm_f32out(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,
+                          float* y, void* stream);
+int dcb_nchw_to_rows_f32out(const float* src, int B, int C, int T, int HW, int Cpad, float* dst, void* stream);
+int dcb_upsample2x_f32out(const float* src, int nf, int H, int W, int C, float* dst, void* stream);
+int dcb_space_to_depth_f32out(const float* src, int nf, int H, int W, int C, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused classifier-free guidance + guidance rescale + v/eps conversion + DDIM x_{t-1} update.
  * Replaces ~25 pointwise launches of DDIMSampler.p_sample_ddim (ddim.py:226-277),
  * rescale_noise_cfg (utils_diffusion.py:147-158), predict_*_from_z_and_v (ddpm3d.py:239-251).

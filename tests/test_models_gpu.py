@@ -263,3 +263,23 @@ def test_frame_sharded_unet_matches_single_gpu():
                        capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0
+
+
+FP32_TOL = 1e-3
+
+
+@pytest.mark.parametrize("name", ["unet_tiny512.pt", "unet_tiny512_b2.pt", "unet_tiny256.pt"])
+def test_unet_forward_fp32_mode(name):
+    """north_star: per-step eps within rel-L2 <= 1e-3 of the fp32 reference in fp32 mode (hi/lo-split bf16 operands on
+    the tensor cores, everything else fp32; csrc/fp32_mode.cu)."""
+    from dynamicrafter_b200.precision import set_precision
+    g, cfg, x, ts, ctx, fs = _unet_case(name)
+    set_precision("fp32")
+    try:
+        m = _build_unet(cfg, g["shapes"], g["seed"])
+        y = m(x.cuda(), ts.cuda(), context=ctx.cuda(), fs=None if fs is None else fs.cuda()).cpu()
+    finally:
+        set_precision("bf16")
+    err = rel_l2(y, g["y"])
+    print(f"\n{name}: fp32 mode rel-L2 vs reference golden {err:.3e}")
+    assert err < FP32_TOL
