@@ -47,13 +47,15 @@ class AutoencoderKL(PackedModule):
         """z: [n, embed_dim, h, w] fp32 (already divided by scale_factor) -> [n, 3, 8h, 8w]."""
         if not z.is_cuda:
             raise RuntimeError("dcb200 AutoencoderKL.decode runs on CUDA tensors only (no CPU path)")
-        p = self.packed()
-        n, c, hh, ww = z.shape
-        zr = ops.nchw_to_rows(z, 64)
-        pq = torch.zeros((n * hh * ww, 64), dtype=torch.bfloat16, device=z.device)
-        ops.linear(zr, p["w"], bias=p["b"], out=pq)          # 1x1 post_quant_conv, written into the padded operand
-        o, H, W = self.decoder._fwd_rows(pq, n, hh, ww)
-        return ops.rows_to_nchw(o, n, self.decoder.out_ch, 1, H, W, five_d=False).to(z.dtype)
+        from dynamicrafter_b200.precision import use_precision
+        with use_precision("bf16"):                             # the decoder has no fp32 parity mode (PSNR bar)
+            p = self.packed()
+            n, c, hh, ww = z.shape
+            zr = ops.nchw_to_rows(z, 64)
+            pq = torch.zeros((n * hh * ww, 64), dtype=torch.bfloat16, device=z.device)
+            ops.linear(zr, p["w"], bias=p["b"], out=pq)      # 1x1 post_quant_conv, written into the padded operand
+            o, H, W = self.decoder._fwd_rows(pq, n, hh, ww)
+            return ops.rows_to_nchw(o, n, self.decoder.out_ch, 1, H, W, five_d=False).to(z.dtype)
 
     def forward(self, input, sample_posterior=True):
         raise NotImplementedError("training forward is outside the dcb200 hot path")

@@ -23,3 +23,19 @@ def get_precision():
 
 def fp32_mode():
     return _MODE[0] == "fp32"
+
+
+class use_precision:
+    """Context manager: run a region in the given mode (the VAE decode always runs in bf16: its parity bar is a
+    PSNR bar and its attention / 1x1 paths are not built for the fp32 mode)."""
+
+    def __init__(self, mode):
+        if mode not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev, _MODE[0] = _MODE[0], self.mode
+
+    def __exit__(self, *exc):
+        _MODE[0] = self.prev
