@@ -158,8 +158,9 @@ class OpTimer:
             flops, key = 0, name
             if name == "tap_gemm":
                 dims, taps, w, N = a[1], a[4], a[5], a[6]
-                flops = 2.0 * dims[0] * dims[1] * dims[2] * N * w.shape[1]
-                key = (f"gemm M={dims[0] * dims[1] * dims[2]} N={N} K={w.shape[1]} taps={len(taps)} "
+                kdim = w.shape[1] // (3 if a[0].dtype == torch.float32 else 1)     # fp32 mode: algorithmic K, not 3K
+                flops = 2.0 * dims[0] * dims[1] * dims[2] * N * kdim
+                key = (f"gemm M={dims[0] * dims[1] * dims[2]} N={N} K={kdim} taps={len(taps)} "
                        f"f32={kw.get('out_f32') is not None} bf16={kw.get('out_bf16') is not None} "
                        f"res={kw.get('residual') is not None} geglu={bool(kw.get('geglu'))}")
             elif name == "group_norm":
@@ -267,6 +268,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-video", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="fp32 = the <=1e-3 parity mode (hi/lo-split operands, 3x GEMM work, CUDA-core attention); "
+                         "the headline numbers are the bf16 mode")
     ap.add_argument("--frame-shard", action="store_true",
                     help="N>1: ONE video, its 16 frames sharded over the ranks (all-to-all around the temporal blocks); "
                          "strong scaling of single-video latency (BASELINE.json configs[3])")
@@ -277,6 +281,8 @@ def main():
 
     import torch.distributed as dist
     from dynamicrafter_b200 import _lib, ops
+    from dynamicrafter_b200.precision import set_precision
+    set_precision(args.precision)
     from dynamicrafter_b200.configs import SAMPLER, UNET_TFLOP, VAE_TFLOP
     from dynamicrafter_b200.lvdm.models.samplers.ddim import DDIMSampler
 
@@ -457,7 +463,9 @@ def main():
         line = {"metric": METRIC, "value": round(value, 4), "unit": "steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
                 "scaling": "strong" if fshard else "weak",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "fp32 (bf16 hi/lo split x3 on tensor cores)",
+                "data": "synthetic",
                 "config": {"workload": f"DynamiCrafter {args.config} ({h * 8}x{w * 8}x16f, latent {h}x{w}), DDIM {sm['S']} "
                                        f"{sm['timestep_spacing']} eta {sm['eta']}, CFG {sm['cfg']}, guidance_rescale "
                                        f"{sm['guidance_rescale']}; 1 video per GPU; random-init weights (1.44 B params)",

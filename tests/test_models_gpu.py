@@ -12,6 +12,7 @@ from dynamicrafter_b200.synth import synth_state_dict, synth_input
 
 pytestmark = pytest.mark.gpu
 BF16_TOL = 2e-2
+FP32_TOL = 1e-3
 
 
 def _unet_case(name):
@@ -253,6 +254,14 @@ def test_unet_full_512_config_vs_oracle_reduced_frames():
     err = rel_l2(y, ref)
     print(f"\nfull 512-config UNet (2 frames, 16x24 latent): rel-L2 vs oracle {err:.3e}")
     assert err < BF16_TOL
+    # the same forward in the fp32 parity mode (weights re-packed as hi/lo splits)
+    from dynamicrafter_b200.precision import use_precision
+    m.use_cuda_graph = False
+    with use_precision("fp32"):
+        y32 = m(x.cuda(), ts.cuda(), context=ctx.cuda()).cpu()
+    err32 = rel_l2(y32, ref)
+    print(f"full 512-config UNet, fp32 mode: rel-L2 vs oracle {err32:.3e}")
+    assert err32 < FP32_TOL
 
 
 def test_frame_sharded_unet_matches_single_gpu():
@@ -271,8 +280,6 @@ def test_frame_sharded_unet_matches_single_gpu():
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0
 
-
-FP32_TOL = 1e-3
 
 
 @pytest.mark.parametrize("name", ["unet_tiny512.pt", "unet_tiny512_b2.pt", "unet_tiny256.pt"])
