@@ -163,21 +163,29 @@ struct DdimParams {
     float sqrt_a_prev, dir_coef, sigma_t, temperature, x0_rescale;
 };
 
+// three-branch guidance of the multi-condition sampler (ddim_multiplecond.py:234), in the reference's order:
+// (e_u + cfg_img * (e_ui - e_u)) + s * (e_c - e_ui)
+__device__ __forceinline__ float cfg3(float c, float u, float ui, float s, float cfg_img) {
+    return __fadd_rn(__fadd_rn(u, __fmul_rn(cfg_img, __fsub_rn(ui, u))), __fmul_rn(s, __fsub_rn(c, ui)));
+}
+
 // per-sample unbiased std of e_cond and of the CFG combination (utils_diffusion.py:152-153); one block per sample.
 __global__ void __launch_bounds__(1024)
-cfg_std_kernel(const float* __restrict__ e_c, const float* __restrict__ e_u, long long per_sample, float cfg_scale,
-               float* __restrict__ stds) {
+cfg_std_kernel(const float* __restrict__ e_c, const float* __restrict__ e_u, const float* __restrict__ e_ui,
+               long long per_sample, float cfg_scale, float cfg_img, float* __restrict__ stds) {
     __shared__ double red[2][32];
     __shared__ double s_mean[2];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* pc = e_c + b * per_sample;
     const float* pu = e_u + b * per_sample;
+    const float* pi = e_ui != nullptr ? e_ui + b * per_sample : nullptr;
     for (int pass = 0; pass < 2; ++pass) {
         double a0 = 0.0, a1 = 0.0;
         const double m0 = pass ? s_mean[0] : 0.0, m1 = pass ? s_mean[1] : 0.0;
         for (long long i = tid; i < per_sample; i += blockDim.x) {
             const float c = pc[i], u = pu[i];
-            const float cfg = __fadd_rn(u, __fmul_rn(cfg_scale, __fsub_rn(c, u)));
+            const float cfg = pi == nullptr ? __fadd_rn(u, __fmul_rn(cfg_scale, __fsub_rn(c, u)))
+                                            : cfg3(c, u, pi[i], cfg_scale, cfg_img);
             if (pass == 0) { a0 += c; a1 += cfg; }
             else { a0 += (c - m0) * (c - m0); a1 += (cfg - m1) * (cfg - m1); }
         }
@@ -205,6 +213,7 @@ cfg_std_kernel(const float* __restrict__ e_c, const float* __restrict__ e_u, lon
 // torch bit for bit when guidance_rescale == 0.
 __global__ void __launch_bounds__(256)
 ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ e_c, const float* __restrict__ e_u,
+                   const float* __restrict__ e_ui, float cfg_img,
                    const float* __restrict__ noise, const float* __restrict__ stds, long long per_sample,
                    long long total, DdimParams p, float* __restrict__ x_prev, float* __restrict__ pred_x0) {
     const long long i4 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4;
@@ -217,6 +226,9 @@ ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ e_c, c
     float4 uv = cv;
     if (p.use_cfg) uv = *reinterpret_cast<const float4*>(e_u + i4);
     const float4 nv = *reinterpret_cast<const float4*>(noise + i4);
+    float4 iv = uv;
+    if (p.use_cfg && e_ui != nullptr) iv = *reinterpret_cast<const float4*>(e_ui + i4);
+    const float is[4] = {iv.x, iv.y, iv.z, iv.w};
     const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, cs[4] = {cv.x, cv.y, cv.z, cv.w};
     const float us[4] = {uv.x, uv.y, uv.z, uv.w}, ns[4] = {nv.x, nv.y, nv.z, nv.w};
     float xp[4], x0[4];
@@ -224,7 +236,8 @@ ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ e_c, c
     for (int e = 0; e < 4; ++e) {
         float mo = cs[e];
         if (p.use_cfg) {
-            mo = __fadd_rn(us[e], __fmul_rn(p.cfg_scale, __fsub_rn(cs[e], us[e])));
+            mo = e_ui == nullptr ? __fadd_rn(us[e], __fmul_rn(p.cfg_scale, __fsub_rn(cs[e], us[e])))
+                                 : cfg3(cs[e], us[e], is[e], p.cfg_scale, cfg_img);
             if (p.use_rescale) {
                 const float resc = __fmul_rn(mo, factor);
                 mo = __fadd_rn(__fmul_rn(p.guidance_rescale, resc), __fmul_rn(p.one_minus_gr, mo));
@@ -344,11 +357,13 @@ extern "C" int dcb_small_linear(const float* a, int lda, const float* w, const f
     return check_launch("small_linear");
 }
 
-extern "C" int dcb_ddim_update(const float* x, const float* e_cond, const float* e_uncond, const float* noise,
-                               int B, long long per_sample, const dcb_ddim_coeffs* c, float* stds_ws, float* x_prev,
-                               float* pred_x0, void* stream) {
+static int ddim_update_impl(const float* x, const float* e_cond, const float* e_uncond, const float* e_uncond_img,
+                            float cfg_img, const float* noise, int B, long long per_sample, const dcb_ddim_coeffs* c,
+                            float* stds_ws, float* x_prev, float* pred_x0, void* stream) {
     if (!x || !e_cond || !noise || !c || !x_prev || !pred_x0 || B < 1 || per_sample < 4 || (per_sample & 3))
         return set_error(DCB_ERR_INVALID, "ddim_update: bad argument (per_sample multiple of 4)");
+    if (e_uncond_img != nullptr && e_uncond == nullptr)
+        return set_error(DCB_ERR_INVALID, "ddim_update: the image-only branch needs the unconditional branch");
     const int use_cfg = (e_uncond != nullptr) ? 1 : 0;
     const int use_rescale = (use_cfg && c->guidance_rescale > 0.f) ? 1 : 0;
     if (use_rescale && stds_ws == nullptr) return set_error(DCB_ERR_INVALID, "ddim_update: stds workspace needed");
@@ -360,9 +375,25 @@ extern "C" int dcb_ddim_update(const float* x, const float* e_cond, const float*
     p.sqrt_a_t = c->sqrt_a_t; p.sqrt_1m_a_t = c->sqrt_1m_a_t;
     p.sqrt_a_prev = c->sqrt_a_prev; p.dir_coef = c->dir_coef; p.sigma_t = c->sigma_t;
     p.temperature = c->temperature; p.x0_rescale = c->x0_rescale;
-    if (use_rescale) cfg_std_kernel<<<B, 1024, 0, s>>>(e_cond, e_uncond, per_sample, c->cfg_scale, stds_ws);
+    if (use_rescale)
+        cfg_std_kernel<<<B, 1024, 0, s>>>(e_cond, e_uncond, e_uncond_img, per_sample, c->cfg_scale, cfg_img, stds_ws);
     const long long total = static_cast<long long>(B) * per_sample;
-    ddim_update_kernel<<<blocks_for(total / 4, 256), 256, 0, s>>>(x, e_cond, e_uncond, noise, stds_ws, per_sample, total,
-                                                                  p, x_prev, pred_x0);
+    ddim_update_kernel<<<blocks_for(total / 4, 256), 256, 0, s>>>(x, e_cond, e_uncond, e_uncond_img, cfg_img, noise, stds_ws,
+                                                                  per_sample, total, p, x_prev, pred_x0);
     return check_launch("ddim_update");
+}
+
+extern "C" int dcb_ddim_update(const float* x, const float* e_cond, const float* e_uncond, const float* noise,
+                               int B, long long per_sample, const dcb_ddim_coeffs* c, float* stds_ws, float* x_prev,
+                               float* pred_x0, void* stream) {
+    return ddim_update_impl(x, e_cond, e_uncond, nullptr, 0.f, noise, B, per_sample, c, stds_ws, x_prev, pred_x0, stream);
+}
+
+extern "C" int dcb_ddim_update_multicond(const float* x, const float* e_cond, const float* e_uncond,
+                                         const float* e_uncond_img, float cfg_img, const float* noise, int B,
+                                         long long per_sample, const dcb_ddim_coeffs* c, float* stds_ws, float* x_prev,
+                                         float* pred_x0, void* stream) {
+    if (e_uncond_img == nullptr) return set_error(DCB_ERR_INVALID, "ddim_update_multicond: null image-only branch");
+    return ddim_update_impl(x, e_cond, e_uncond, e_uncond_img, cfg_img, noise, B, per_sample, c, stds_ws, x_prev, pred_x0,
+                            stream);
 }

@@ -174,35 +174,42 @@ class DDIMSampler(object):
                 intermediates['pred_x0'].append(pred_x0)
         return img, intermediates
 
-    # cond / uncond as one batch ----------------------------------------------------------------
+    # cond / uncond (/ image-only uncond) as one batch -----------------------------------------------
     @staticmethod
-    def _cat_cond(c, uc):
-        if isinstance(c, torch.Tensor) and isinstance(uc, torch.Tensor) and c.shape == uc.shape:
-            return torch.cat([c, uc], 0)
-        if isinstance(c, dict) and isinstance(uc, dict) and c.keys() == uc.keys():
+    def _cat_cond(*cs):
+        """Batch-concatenate structurally identical conditionings (tensors, or dicts of tensors / tensor lists);
+        None if they do not line up (the branches are then evaluated one by one)."""
+        def same(ts):
+            return all(isinstance(t, torch.Tensor) for t in ts) and all(t.shape == ts[0].shape for t in ts)
+        if same(cs):
+            return torch.cat(cs, 0)
+        if all(isinstance(c, dict) for c in cs) and all(c.keys() == cs[0].keys() for c in cs):
             out = {}
-            for k in c:
-                a, bb = c[k], uc[k]
-                if isinstance(a, (list, tuple)) and isinstance(bb, (list, tuple)) and len(a) == len(bb) and \
-                        all(isinstance(x, torch.Tensor) and isinstance(y, torch.Tensor) and x.shape == y.shape
-                            for x, y in zip(a, bb)):
-                    out[k] = [torch.cat([x, y], 0) for x, y in zip(a, bb)]
-                elif isinstance(a, torch.Tensor) and isinstance(bb, torch.Tensor) and a.shape == bb.shape:
-                    out[k] = torch.cat([a, bb], 0)
+            for k in cs[0]:
+                vals = [c[k] for c in cs]
+                if all(isinstance(v, (list, tuple)) for v in vals) and all(len(v) == len(vals[0]) for v in vals) and \
+                        all(same([v[j] for v in vals]) for j in range(len(vals[0]))):
+                    out[k] = [torch.cat([v[j] for v in vals], 0) for j in range(len(vals[0]))]
+                elif same(vals):
+                    out[k] = torch.cat(vals, 0)
                 else:
                     return None
             return out
         return None
 
-    def _eval_pair(self, x, t, c, uc, kwargs):
-        b = x.shape[0]
-        both = self._cat_cond(c, uc) if self.batch_cfg else None
-        if both is None:
-            return self.model.apply_model(x, t, c, **kwargs), self.model.apply_model(x, t, uc, **kwargs)
-        kw2 = {k: (torch.cat([v, v], 0) if isinstance(v, torch.Tensor) and v.dim() >= 1 and v.shape[0] == b else v)
+    def _eval_branches(self, x, t, conds, kwargs):
+        """One UNet forward over all guidance branches (same x, t; different conditioning) -> list of outputs."""
+        b, n = x.shape[0], len(conds)
+        allc = self._cat_cond(*conds) if self.batch_cfg else None
+        if allc is None:
+            return [self.model.apply_model(x, t, c, **kwargs) for c in conds]
+        kwn = {k: (torch.cat([v] * n, 0) if isinstance(v, torch.Tensor) and v.dim() >= 1 and v.shape[0] == b else v)
                for k, v in kwargs.items()}
-        out = self.model.apply_model(torch.cat([x, x], 0), torch.cat([t, t], 0), both, **kw2)
-        return out[:b].contiguous(), out[b:].contiguous()
+        out = self.model.apply_model(torch.cat([x] * n, 0), torch.cat([t] * n, 0), allc, **kwn)
+        return [out[i * b:(i + 1) * b].contiguous() for i in range(n)]
+
+    def _eval_pair(self, x, t, c, uc, kwargs):
+        return tuple(self._eval_branches(x, t, [c, uc], kwargs))
 
     @torch.no_grad()
     def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,

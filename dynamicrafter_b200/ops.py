@@ -563,14 +563,20 @@ def small_linear(a, w, bias=None, *, silu_in=False, silu_out=False, out=None, ac
     return out
 
 
-def ddim_update(x, e_cond, e_uncond, noise, coeffs):
-    """coeffs: _lib.DdimCoeffs.  Returns (x_prev, pred_x0)."""
-    require_cuda(x, e_cond, e_uncond, noise)
+def ddim_update(x, e_cond, e_uncond, noise, coeffs, e_uncond_img=None, cfg_img=None):
+    """coeffs: _lib.DdimCoeffs.  e_uncond_img / cfg_img: third branch of the multi-condition sampler.
+    Returns (x_prev, pred_x0)."""
+    require_cuda(x, e_cond, e_uncond, noise, e_uncond_img)
     B = x.shape[0]
     per = x.numel() // B
     x_prev = torch.empty_like(x)
     pred = torch.empty_like(x)
     stds = torch.empty((B, 2), dtype=F32, device=x.device)
+    if e_uncond_img is not None:
+        check(_lib.lib().dcb_ddim_update_multicond(ptr(x), ptr(e_cond), ptr(e_uncond), ptr(e_uncond_img), _c_f(cfg_img),
+                                                   ptr(noise), _c_i(B), _c_ll(per), ctypes.byref(coeffs), ptr(stds),
+                                                   ptr(x_prev), ptr(pred), _stream()), "dcb_ddim_update_multicond")
+        return x_prev, pred
     check(_lib.lib().dcb_ddim_update(ptr(x), ptr(e_cond), ptr(e_uncond), ptr(noise), _c_i(B), _c_ll(per),
                                      ctypes.byref(coeffs), ptr(stds), ptr(x_prev), ptr(pred), _stream()),
           "dcb_ddim_update")

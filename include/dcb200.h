@@ -219,6 +219,11 @@ typedef struct {
 int dcb_ddim_update(const float* x, const float* e_cond, const float* e_uncond, const float* noise,
                     int B, long long per_sample, const dcb_ddim_coeffs* c, float* stds_ws, float* x_prev,
                     float* pred_x0, void* stream);
+/* Three-branch guidance of the multi-condition sampler (ddim_multiplecond.py:229-236):
+ * model_output = e_uncond + cfg_img * (e_uncond_img - e_uncond) + cfg_scale * (e_cond - e_uncond_img); the rest as above. */
+int dcb_ddim_update_multicond(const float* x, const float* e_cond, const float* e_uncond, const float* e_uncond_img,
+                              float cfg_img, const float* noise, int B, long long per_sample, const dcb_ddim_coeffs* c,
+                              float* stds_ws, float* x_prev, float* pred_x0, void* stream);
 
 #ifdef __cplusplus
 }

@@ -87,7 +87,8 @@ def rescale_noise_cfg(noise_cfg, noise_text, guidance_rescale):
 
 
 def p_sample_ddim(tables, dt, apply_model, x, cond, t, index, ucg_scale=1.0, uncond=None,
-                  guidance_rescale=0.0, temperature=1.0, noise=None, **kw):
+                  guidance_rescale=0.0, temperature=1.0, noise=None, uncond_img=None, cfg_img=None, **kw):
+    """uncond_img / cfg_img: third branch of the multi-condition sampler (ddim_multiplecond.py:220-236)."""
     b = x.shape[0]
     if uncond is None or ucg_scale == 1.0:
         out = apply_model(x, t, cond, **kw)
@@ -95,7 +96,12 @@ def p_sample_ddim(tables, dt, apply_model, x, cond, t, index, ucg_scale=1.0, unc
     else:
         e_c = apply_model(x, t, cond, **kw)
         e_u = apply_model(x, t, uncond, **kw)
-        out = e_u + ucg_scale * (e_c - e_u)
+        if uncond_img is not None:
+            e_ui = apply_model(x, t, uncond_img, **kw)
+            ci = ucg_scale if cfg_img is None else cfg_img
+            out = e_u + ci * (e_ui - e_u) + ucg_scale * (e_c - e_ui)
+        else:
+            out = e_u + ucg_scale * (e_c - e_u)
         if guidance_rescale > 0.0:
             out = rescale_noise_cfg(out, e_c, guidance_rescale)
     is_v = tables.parameterization == "v"
@@ -127,7 +133,7 @@ def p_sample_ddim(tables, dt, apply_model, x, cond, t, index, ucg_scale=1.0, unc
 @torch.no_grad()
 def sample(tables, apply_model, S, shape, cond, uncond=None, ucg_scale=1.0, eta=0.0,
            timestep_spacing="uniform", guidance_rescale=0.0, x_T=None, log_every_t=100,
-           record_steps=False, **kw):
+           record_steps=False, uncond_img=None, cfg_img=None, **kw):
     """Returns (samples, intermediates[, per-step list of (x_prev, pred_x0)])."""
     dt = ddim_tables(tables, S, timestep_spacing, eta)
     img = torch.randn(shape) if x_T is None else x_T
@@ -140,7 +146,7 @@ def sample(tables, apply_model, S, shape, cond, uncond=None, ucg_scale=1.0, eta=
         ts = torch.full((shape[0],), int(step), dtype=torch.long)
         img, pred_x0 = p_sample_ddim(tables, dt, apply_model, img, cond, ts, index,
                                      ucg_scale=ucg_scale, uncond=uncond,
-                                     guidance_rescale=guidance_rescale, **kw)
+                                     guidance_rescale=guidance_rescale, uncond_img=uncond_img, cfg_img=cfg_img, **kw)
         if record_steps:
             steps.append((img, pred_x0))
         if index % log_every_t == 0 or index == total - 1:

@@ -221,6 +221,27 @@ def golden_ddim():
                                                last_pred_x0=inter["pred_x0"][-1].clone())
             print(tag, eta, float(samples.mean()), float(samples.std()))
 
+    # (ii-b) the multi-condition sampler (ddim_multiplecond.py: cond / uncond / image-only uncond, cfg_img) with the
+    # same mock denoiser
+    from lvdm.models.samplers.ddim_multiplecond import DDIMSampler as DDIMSamplerMC
+    DDIMSamplerMC.register_buffer = lambda self, n, a: setattr(self, n, a)
+    for tag, yml, S, spacing, gr in (("mockmc_c2", "inference_512_v1.0.yaml", 50, "uniform_trailing", 0.7),
+                                     ("mockmc_c1", "inference_256_v1.0.yaml", 10, "uniform", 0.0)):
+        model, _ = build_lvd(TINY_UNET_256 if "256" in yml else TINY_UNET, TINY_VAE, yml, 21)
+        model.apply_model = lambda x, t, c, **kw: torch.tanh(0.3 * x + c)
+        for eta in (0.0, 1.0):
+            smp = DDIMSamplerMC(model)
+            torch.manual_seed(0)
+            samples, inter = smp.sample(S=S, batch_size=2, shape=(4, 16, 8, 8),
+                                        conditioning=torch.tensor([0.1]),
+                                        unconditional_conditioning=torch.tensor([-0.1]),
+                                        unconditional_guidance_scale=7.5, eta=eta, verbose=False,
+                                        timestep_spacing=spacing, guidance_rescale=gr, cfg_img=2.0,
+                                        unconditional_conditioning_img_nonetext=torch.tensor([0.05]))
+            out[f"{tag}_eta{int(eta)}"] = dict(samples=samples.clone(), n_inter=len(inter["x_inter"]),
+                                               last_pred_x0=inter["pred_x0"][-1].clone())
+            print(tag, eta, float(samples.mean()), float(samples.std()))
+
     # (iii) end-to-end: real (tiny) UNet through apply_model + decode_first_stage
     for tag, yml, S, spacing, gr, ucfg in (
             ("e2e_c2", "inference_512_v1.0.yaml", 4, "uniform_trailing", 0.7, TINY_UNET),
@@ -243,7 +264,15 @@ def golden_ddim():
                                     unconditional_conditioning_img_nonetext=None)
         with torch.no_grad():
             video = model.decode_first_stage(samples)
+        # the same run without noise (eta = 0), every step logged: teacher-forcing trajectory for the CUDA path
+        smp0 = DDIMSampler(model)
+        _, traj = smp0.sample(S=S, batch_size=B, shape=(4, T, h, w), conditioning=cond,
+                              unconditional_guidance_scale=7.5, unconditional_conditioning=uc,
+                              eta=0.0, verbose=False, x_T=x_T, fs=fs, timestep_spacing=spacing,
+                              guidance_rescale=gr, log_every_t=1, cfg_img=None,
+                              unconditional_conditioning_img_nonetext=None)
         out[tag] = dict(samples=samples.clone(), video=video.clone(), S=S, spacing=spacing, gr=gr,
+                        traj_x=torch.stack(traj["x_inter"]).clone(), traj_pred_x0=torch.stack(traj["pred_x0"]).clone(),
                         unet_shapes=shapes_of(model.model.diffusion_model),
                         vae_shapes=shapes_of(model.first_stage_model),
                         ucfg=ucfg, seed=31, yaml=yml)

@@ -164,6 +164,76 @@ def test_sampler_with_mock_denoiser_teacher_forced(tag, eta):
     assert worst < 2e-6     # tanh on GPU vs CPU differs by ~1 ulp; the update itself adds no error
 
 
+@pytest.mark.parametrize("tag", ["mockmc_c2", "mockmc_c1"])
+def test_multicond_sampler_vs_reference_golden(tag):
+    """drop-in for ddim_multiplecond.DDIMSampler (three guidance branches as one batch, fused
+    3-term combine + update) against the reference run with the mock denoiser, eta = 0, free running over all steps."""
+    from oracle import ddim_oracle
+    from dynamicrafter_b200.lvdm.models.samplers.ddim_multiplecond import DDIMSampler
+    g = load_golden("ddim.pt")[tag + "_eta0"]
+    c = SCHED["c2" if tag.endswith("c2") else "c1"]
+    gr = 0.7 if tag.endswith("c2") else 0.0
+    tab = ddim_oracle.DiffusionTables(**c["kw"])
+    dev = torch.device("cuda")
+    smp = DDIMSampler(_MockDiffusion(tab, lambda x, t, cnd, **kw: torch.tanh(0.3 * x + cnd.reshape(-1, 1, 1, 1, 1)), dev))
+    torch.manual_seed(0)
+    x_T = torch.randn((2, 4, 16, 8, 8))                       # the reference drew x_T first from the same CPU stream
+    one = lambda v: torch.full((2,), v, device=dev)           # per-sample conditioning so the branches batch
+    samples, inter = smp.sample(S=c["S"], batch_size=2, shape=(4, 16, 8, 8), conditioning=one(0.1),
+                                unconditional_conditioning=one(-0.1), unconditional_guidance_scale=7.5, eta=0.0,
+                                verbose=False, x_T=x_T.cuda(), timestep_spacing=c["spacing"], guidance_rescale=gr,
+                                cfg_img=2.0, unconditional_conditioning_img_nonetext=one(0.05))
+    err = rel_l2(samples.cpu(), g["samples"])
+    print(f"\n{tag}: {c['S']}-step multi-condition sampler vs reference golden rel-L2 {err:.3e}")
+    assert len(inter["x_inter"]) == g["n_inter"]
+    assert err < 1e-4      # tanh differs by ~1 ulp between CPU and GPU; errors compound over up to 50 steps
+
+
+@pytest.mark.parametrize("tag,mode,tol_x,tol_p", [("e2e_c2", "bf16", 0.1, 0.15), ("e2e_c1", "bf16", 0.1, 0.15),
+                                                 ("e2e_c2", "fp32", 1e-3, 1e-3), ("e2e_c1", "fp32", 1e-3, 1e-3)])
+def test_real_unet_teacher_forced_against_reference_trajectory(tag, mode, tol_x, tol_p):
+    from dynamicrafter_b200.precision import use_precision
+    with use_precision(mode):
+        _teacher_forced(tag, tol_x, tol_p)
+
+
+def _teacher_forced(tag, tol_x, tol_p):
+    """per-step parity with teacher forcing -- feed the REFERENCE's x_t of every step of its eta = 0
+    run (real tiny UNet, CFG 7.5, guidance rescale) into p_sample_ddim and compare pred_x0 / x_{t-1}."""
+    from oracle import ddim_oracle
+    from dynamicrafter_b200.lvdm.models.samplers.ddim import DDIMSampler
+    import numpy as np
+    g = load_golden("ddim.pt")[tag]
+    c = SCHED["c2" if tag.endswith("c2") else "c1"]
+    tab = ddim_oracle.DiffusionTables(**c["kw"])
+    ucfg, seed = g["ucfg"], g["seed"]
+    unet = _build_unet(ucfg, g["unet_shapes"], seed)
+    dev = torch.device("cuda")
+    B, T, h, w = 1, 16, 8, 8
+    cond = {"c_crossattn": [synth_input("cond", (B, 77 + 16 * T, 1024), seed).cuda()],
+            "c_concat": [synth_input("concat", (B, 4, T, h, w), seed).cuda()]}
+    uc = {"c_crossattn": [synth_input("uncond", (B, 77 + 16 * T, 1024), seed).cuda()], "c_concat": cond["c_concat"]}
+    fs = torch.tensor([ucfg["default_fs"]] * B, dtype=torch.long, device=dev)
+
+    def apply_model(x, t, cnd, **kw):
+        return unet(torch.cat([x] + cnd["c_concat"], dim=1), t, context=torch.cat(cnd["c_crossattn"], 1), **kw)
+
+    smp = DDIMSampler(_MockDiffusion(tab, apply_model, dev))
+    smp.make_schedule(g["S"], ddim_discretize=g["spacing"], ddim_eta=0.0, verbose=False)
+    steps = np.flip(smp.ddim_timesteps)
+    assert g["traj_x"].shape[0] == g["S"] + 1
+    worst_x, worst_p = 0.0, 0.0
+    for i, step in enumerate(steps):
+        index = g["S"] - i - 1
+        ts = torch.full((B,), int(step), device=dev, dtype=torch.long)
+        xp, p0 = smp.p_sample_ddim(g["traj_x"][i].cuda(), cond, ts, index=index, unconditional_guidance_scale=7.5,
+                                   unconditional_conditioning=uc, fs=fs, guidance_rescale=g["gr"])
+        worst_x = max(worst_x, rel_l2(xp.cpu(), g["traj_x"][i + 1]))
+        worst_p = max(worst_p, rel_l2(p0.cpu(), g["traj_pred_x0"][i + 1]))
+    print(f"\n{tag}: teacher-forced worst per-step rel-L2  x_prev {worst_x:.3e}  pred_x0 {worst_p:.3e}")
+    assert worst_x < tol_x and worst_p < tol_p   # CFG 7.5 amplifies the per-forward error (bf16 bar 2e-2) ~5x
+
+
 @pytest.mark.parametrize("tag,mode,tol", [("e2e_c2", "bf16", 0.1), ("e2e_c1", "bf16", 0.1), ("e2e_c2", "fp32", 5e-3)])
 def test_end_to_end_sample_and_decode(tag, mode, tol):
     """DDIMSampler.sample over the real (tiny) UNet + VAE decode vs the reference golden, free running; in bf16 mode

@@ -102,6 +102,23 @@ def test_sampler_with_mock_denoiser(tag, eta):
     assert torch.equal(inter["pred_x0"][-1], g["last_pred_x0"])
 
 
+@pytest.mark.parametrize("tag,eta", [("mockmc_c2", 0.0), ("mockmc_c2", 1.0), ("mockmc_c1", 0.0), ("mockmc_c1", 1.0)])
+def test_multicond_sampler_with_mock_denoiser(tag, eta):
+    """ddim_multiplecond.py (cond / uncond / image-only uncond, cfg_img = 2): oracle vs the reference run, bit-exact."""
+    g = load_golden("ddim.pt")[f"{tag}_eta{int(eta)}"]
+    c = SCHED["c2" if tag.endswith("c2") else "c1"]
+    tab = ddim_oracle.DiffusionTables(**c["kw"])
+    gr = 0.7 if tag.endswith("c2") else 0.0
+    torch.manual_seed(0)
+    samples, inter = ddim_oracle.sample(
+        tab, lambda x, t, cnd: torch.tanh(0.3 * x + cnd), c["S"], (2, 4, 16, 8, 8),
+        torch.tensor([0.1]), uncond=torch.tensor([-0.1]), ucg_scale=7.5, eta=eta,
+        timestep_spacing=c["spacing"], guidance_rescale=gr, uncond_img=torch.tensor([0.05]), cfg_img=2.0)
+    assert len(inter["x_inter"]) == g["n_inter"]
+    assert torch.equal(samples, g["samples"])
+    assert torch.equal(inter["pred_x0"][-1], g["last_pred_x0"])
+
+
 @pytest.mark.parametrize("tag", ["e2e_c2", "e2e_c1"])
 def test_end_to_end_oracle(tag):
     g = load_golden("ddim.pt")[tag]
