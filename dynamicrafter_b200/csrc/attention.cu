@@ -8,12 +8,15 @@
 //    (attention.py:387-390, K8); reads q/k/v rows with the frame stride of the channels-last layout so no
 //    '(b t) hw c <-> (b hw) t c' transposes exist anywhere.
 //
-// Round-1 status: both use warp-level mma.sync (HMMA) tiles with cp.async double buffering; the tcgen05/TMEM
-// version of the spatial kernel is the next optimisation step.
+//  * cross_attention_kernel: text + image cross-attention with all keys resident in shared memory.
+//
+// These are warp-level mma.sync (HMMA) kernels; the long-sequence spatial self-attention runs on tcgen05 / TMEM
+// (flash_tc.cu) and only falls back to flash_attention_kernel for short sequences.
 #include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "dcb_internal.h"
+#include "ptx.cuh"
 
 namespace dcb {
 
@@ -71,6 +74,8 @@ flash_attention_kernel(const FlashParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
     const int g = lane >> 2, t = lane & 3;
+    pdl_launch_dependents();
+    pdl_wait();
 
     // ---- Q tile -> smem (zero filled past nq)
     {
@@ -327,6 +332,8 @@ cross_attention_kernel(const FlashParams p, int tiles_per_warp) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int h = blockIdx.y, b = blockIdx.z;
     const int g = lane >> 2, t = lane & 3;
+    pdl_launch_dependents();
+    pdl_wait();
 
     // ---- K / V of both segments -> smem (rows past nk zero filled)
     auto load_kv = [&](int seg, __nv_bfloat16* dK, __nv_bfloat16* dV, int rows) {
@@ -429,6 +436,8 @@ temporal_attention_kernel(const TemporalParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long item = blockIdx.x * 4LL + warp;
     const long long items = static_cast<long long>(p.B) * p.HW * p.heads;
+    pdl_launch_dependents();
+    pdl_wait();
     if (item >= items) return;
     const int h = item % p.heads;
     const long long bp = item / p.heads;
@@ -598,7 +607,7 @@ extern "C" int dcb_flash_attention(const dcb_attention_args* a, void* stream) {
         int tpw = (tiles + kCrossWarps - 1) / kCrossWarps;
         tpw = tpw > 5 ? 5 : tpw;
         dim3 grid((tiles + kCrossWarps * tpw - 1) / (kCrossWarps * tpw), a->heads, a->batch);
-        cross_attention_kernel<NT0, NT1><<<grid, kCrossWarps * 32, smem, st>>>(p, tpw);
+        launch_pdl(kPdlAttention, cross_attention_kernel<NT0, NT1>, grid, dim3(kCrossWarps * 32), smem, st, p, tpw);
         return check_launch("cross_attention");
     }
     if (a->nq >= 512) {
@@ -609,11 +618,11 @@ extern "C" int dcb_flash_attention(const dcb_attention_args* a, void* stream) {
             cfg = true;
         }
         dim3 grid((a->nq + W * 16 - 1) / (W * 16), a->heads, a->batch);
-        flash_attention_kernel<W><<<grid, W * 32, smem, st>>>(p);
+        launch_pdl(kPdlAttention, flash_attention_kernel<W>, grid, dim3(W * 32), smem, st, p);
     } else {
         constexpr int W = 4, smem = (W * 16 + 4 * 64) * kD * 2;
         dim3 grid((a->nq + W * 16 - 1) / (W * 16), a->heads, a->batch);
-        flash_attention_kernel<W><<<grid, W * 32, smem, st>>>(p);
+        launch_pdl(kPdlAttention, flash_attention_kernel<W>, grid, dim3(W * 32), smem, st, p);
     }
     return check_launch("flash_attention");
 }
@@ -631,7 +640,8 @@ extern "C" int dcb_temporal_attention(const void* q, const void* k, const void* 
     p.B = B; p.L = L; p.HW = HW; p.heads = heads;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     const long long items = static_cast<long long>(B) * HW * heads;
-    temporal_attention_kernel<<<static_cast<unsigned>((items + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    launch_pdl(kPdlAttention, temporal_attention_kernel, dim3(static_cast<unsigned>((items + 3) / 4)), dim3(128), 0,
+               static_cast<cudaStream_t>(stream), p);
     return check_launch("temporal_attention");
 }
 

@@ -1,4 +1,5 @@
 // Error reporting and device checks of the C ABI.
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 
@@ -24,6 +25,14 @@ int num_sms() {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     }
     return n;
+}
+
+// DCB_PDL: bit mask of the kernel classes launched with programmatic stream serialization
+// (1 tap_gemm, 2 layer norm, 4 group norm, 8 attention); default set by measurement, see DESIGN.md.
+bool pdl_enabled(int cls) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DCB_PDL"); v = (e == nullptr) ? 1 : atoi(e); }
+    return (v & cls) != 0;
 }
 
 int check_launch(const char* what) {

@@ -8,6 +8,27 @@ namespace dcb {
 int set_error(int code, const char* fmt, ...);   // records a thread-local message, returns code
 int num_sms();                                    // SM count of the current device (cached)
 int check_launch(const char* what);               // cudaGetLastError -> status
+bool pdl_enabled(int cls);                        // programmatic dependent launch per kernel class (DCB_PDL bit mask)
+constexpr int kPdlGemm = 1, kPdlLayerNorm = 2, kPdlGroupNorm = 4, kPdlAttention = 8;
 // tcgen05 flash attention (flash_tc.cu); DCB_ERR_UNSUPPORTED if the arguments do not fit that kernel
 int flash_tc_launch(const dcb_attention_args* a, cudaStream_t stream);
+
+// Launch with programmatic stream serialization (the kernel MUST call pdl_wait() before touching global memory).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    if (pdl_enabled(cls)) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 }  // namespace dcb

@@ -92,6 +92,8 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();        // prologue done: the next kernel may start its own
+    pdl_wait();                     // our predecessor's q / k / v are complete and visible
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -326,7 +328,7 @@ int flash_tc_launch(const dcb_attention_args* a, cudaStream_t stream) {
     p.ntiles = (a->nq + kFK - 1) / kFK;
     p.scale_log2 = a->softmax_scale * 1.4426950408889634f;
     dim3 grid((a->nq + kFQ - 1) / kFQ, a->heads, a->batch);
-    flash_tc_kernel<<<grid, kFThreads, kFSmem, stream>>>(tq, tk, tv, to, p);
+    launch_pdl(kPdlAttention, flash_tc_kernel, grid, dim3(kFThreads), kFSmem, stream, tq, tk, tv, to, p);
     return check_launch("flash_tc");
 }
 

@@ -3,9 +3,11 @@
 //
 // Replaces ATen native_group_norm / layer_norm at basics.py:76-87 (eps 1e-5, fp32), attention.py:225-227,
 // 265,331 (LN eps 1e-5, GN eps 1e-6), openaimodel3d.py:256-262, ae_modules.py:15-16 (eps 1e-6).
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "dcb_internal.h"
+#include "ptx.cuh"
 
 namespace dcb {
 
@@ -307,6 +309,8 @@ gn_fused_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int 
     const int r1 = min(S, r0 + rows_per_chunk);
     constexpr int kV = 16 / sizeof(T);        // channels per 16-byte load: 4 (fp32) or 8 (bf16)
     const int Qb1 = (C1 / kV + 31) >> 5, Qb2 = (C2 / kV + 31) >> 5, Qb = Qb1 + Qb2;
+    pdl_launch_dependents();
+    pdl_wait();
 
     // ---- phase 1: per-(row split, channel) sums of this block's rows; an item = (32 lanes x 16 bytes of channels,
     // row split), 8 rows in flight per lane
@@ -472,6 +476,8 @@ layer_norm_kernel(const float* __restrict__ x, int rows, int C, const float* __r
     const int lane = threadIdx.x & 31;
     const int W = gridDim.x * (blockDim.x >> 5);
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_launch_dependents();
+    pdl_wait();
     if (row >= rows) return;
     const int Q = C >> 2;
     const float inv_c = 1.0f / C;
@@ -748,7 +754,7 @@ static int launch_gn_fused(const T* x1, const T* x2, int C1, int C2, int G, int 
     nch = (S + rpc - 1) / rpc;
     size_t smem = static_cast<size_t>(split) * C * 2 * sizeof(float);
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.gridDim = dim3(nch, G);
@@ -757,6 +763,11 @@ static int launch_gn_fused(const T* x1, const T* x2, int C1, int C2, int G, int 
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (pdl_enabled(kPdlGroupNorm)) {
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 2;
+    }
     cudaError_t e = cudaLaunchKernelEx(&cfg, gn_fused_kernel<T, TOut>, x1, x2, C1, C2, S, rpc, split,
                                        static_cast<float*>(workspace), counters, eps, gamma, beta, silu_act,
                                        static_cast<TOut*>(y), static_cast<TOut*>(raw));
@@ -812,10 +823,10 @@ extern "C" int dcb_layer_norm(const float* x, int rows, int C, const float* gamm
     if (blocks > num_sms() * per_sm) blocks = num_sms() * per_sm;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     __nv_bfloat16* y = static_cast<__nv_bfloat16*>(y_bf16);
-    if (kq == 3) layer_norm_kernel<3><<<blocks, 256, 0, s>>>(x, rows, C, gamma, beta, eps, y);
-    else if (kq == 5) layer_norm_kernel<5><<<blocks, 256, 0, s>>>(x, rows, C, gamma, beta, eps, y);
-    else if (kq == 10) layer_norm_kernel<10><<<blocks, 256, 0, s>>>(x, rows, C, gamma, beta, eps, y);
-    else layer_norm_kernel<20><<<blocks, 256, 0, s>>>(x, rows, C, gamma, beta, eps, y);
+    if (kq == 3) launch_pdl(kPdlLayerNorm, layer_norm_kernel<3, __nv_bfloat16>, dim3(blocks), dim3(256), 0, s, x, rows, C, gamma, beta, eps, y);
+    else if (kq == 5) launch_pdl(kPdlLayerNorm, layer_norm_kernel<5, __nv_bfloat16>, dim3(blocks), dim3(256), 0, s, x, rows, C, gamma, beta, eps, y);
+    else if (kq == 10) launch_pdl(kPdlLayerNorm, layer_norm_kernel<10, __nv_bfloat16>, dim3(blocks), dim3(256), 0, s, x, rows, C, gamma, beta, eps, y);
+    else launch_pdl(kPdlLayerNorm, layer_norm_kernel<20, __nv_bfloat16>, dim3(blocks), dim3(256), 0, s, x, rows, C, gamma, beta, eps, y);
     return check_launch("layer_norm");
 }
 

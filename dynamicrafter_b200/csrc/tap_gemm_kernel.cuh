@@ -224,6 +224,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if constexpr (k2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // prologue done: let the next kernel of the stream start its own prologue, then wait for our predecessor's data
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (whole warp runs the loop with
@@ -559,7 +562,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     p.stage_bytes = static_cast<uint32_t>(p.rows_per_tile * kBlockK * 2 + kBRows * kBlockK * 2);
     p.res_bytes = static_cast<uint32_t>(p.rows_per_tile * 64);
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     cfg.blockDim = dim3(Threads<k2>::value);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
@@ -576,6 +579,13 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     } else {
         const int tiles = p.num_m_tiles * p.num_n_tiles;
         cfg.gridDim = dim3(tiles < num_sms() ? tiles : num_sms());
+        cfg.attrs = attr;
+        cfg.numAttrs = 0;
+    }
+    if (pdl_enabled(kPdlGemm)) {
+        attr[cfg.numAttrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
+        ++cfg.numAttrs;
     }
     cudaError_t e = cudaLaunchKernelEx(&cfg, tap_gemm_kernel<BN, kF32, k2, kCS>, tmA, tmB, tmOut, tmRes, p);
     if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "tap_gemm launch: %s", cudaGetErrorString(e));
