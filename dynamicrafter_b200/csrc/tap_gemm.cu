@@ -96,7 +96,7 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
         const long long m_tiles = static_cast<long long>((a->D1 + a->b1 - 1) / a->b1) * ((a->D2 + a->b2 - 1) / a->b2) *
                                   ((a->D3 + a->b3 - 1) / a->b3);
         if (a->geglu) bn = (a->N % 256 == 0) ? 256 : 128;
-        else if (a->N % 256 == 0 && m_tiles * (a->N / 256) >= 2LL * num_sms()) bn = 256;
+        else if (a->N % 256 == 0 && m_tiles * (a->N / 256) >= 1LL * num_sms()) bn = 256;   // >= one round of CTA pairs
         else bn = (a->N % 160 == 0) ? 160 : 128;
     }
     if (bn != 128 && bn != 160 && bn != 256) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: block_n must be 128, 160 or 256");
