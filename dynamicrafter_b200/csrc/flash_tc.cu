@@ -1,12 +1,15 @@
 // tcgen05 / TMEM / TMA flash attention for the spatial self-attention of the UNet (attention.py:101-125, head_dim 64).
 //
-// CTA = one 128-query tile of one (batch, head); 192 threads:
+// CTA = one 128-query tile of one (batch, head); 320 threads:
 //   warp 0      TMA producer: Q tile once, then K_j / V_j tiles (128 keys x 64) into 2-deep rings (SWIZZLE_128B)
 //   warp 1      TMEM owner + tcgen05.mma issuer:  S_j = Q K_j^T (128x128, fp32 in TMEM, double buffered) and
 //               O_j = P_j V_j (128x64, written over the consumed S_j columns; V is the MN-major B operand)
-//   warps 2..5  softmax: one thread per query row (no shuffles): tcgen05.ld S_j, running max / sum in fp32,
-//               P_j = exp2(...) as bf16 into smem (A operand of the PV MMA), O += O_j with the usual rescale
-//               kept in registers, final O / l -> bf16 -> swizzled smem -> TMA store.
+//   warps 2..9  softmax: TWO threads per query row (warps w and w + 4 share a TMEM lane quarter): both find the row
+//               max of S_j (tcgen05.ld, no shuffles), each exponentiates ITS 64 keys into the bf16 P_j tile in smem
+//               (A operand of the PV MMA) and accumulates ITS 32 output columns of O += O_j in registers with the
+//               usual (lazy) rescale; partial row sums are combined once at the end; O / l -> bf16 -> swizzled smem
+//               -> TMA store.  Two threads per row double the warps the schedulers can pick from: the softmax is
+//               latency bound (exp2 + TMEM round trips), not throughput bound.
 // S_{j+1} is issued before P_j V_j, so the tensor core works on the next scores while the softmax warps are busy;
 // ~113 KB smem and 256 TMEM columns per CTA let two CTAs share an SM for further overlap.
 // The N x N score matrix never leaves the SM (the eager reference materialises 1 GB per layer at 320x512).
@@ -19,8 +22,30 @@ constexpr int kFQ = 128;              // queries per CTA
 constexpr int kFK = 128;              // keys per tile
 constexpr int kFD = 64;               // head dim
 constexpr int kTileBytes = 128 * 128; // 128 rows x 64 bf16
-constexpr int kFThreads = 192;
+constexpr int kFThreads = 320;
 constexpr int kFSmem = 7 * kTileBytes + 256;   // Q, K[2], V[2], P[2 halves] + barriers
+
+// -DDCB_TRACE: CTA (0,0,0) logs (clock, event, tile) per role: 0 producer, 1 mma, 2 softmax warp 2, 3 softmax warp 6
+#ifdef DCB_TRACE
+static __device__ unsigned long long g_flash_trace[4 * 4096];
+struct FlashTrace {
+    unsigned n = 1;
+    __device__ __forceinline__ void ev(int role, unsigned code, unsigned arg) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && n < 4096u)
+            g_flash_trace[role * 4096 + n++] = (static_cast<unsigned long long>(clock64()) << 20) | (code << 12) | (arg & 0xfffu);
+    }
+    __device__ __forceinline__ void done(int role) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_flash_trace[role * 4096] = n;
+    }
+};
+#define FTR_DECL FlashTrace ftr;
+#define FTR(role, code, arg) ftr.ev(role, code, arg)
+#define FTR_DONE(role) ftr.done(role)
+#else
+#define FTR_DECL
+#define FTR(role, code, arg)
+#define FTR_DONE(role)
+#endif
 
 struct FlashTcParams {
     int nk, ntiles;
@@ -54,6 +79,26 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f via the 1.5 * 2^23 trick, degree-3 minimax
+// polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P), exponent added
+// as an integer.  Measured on B200: the XU pipe is the busiest pipe of this kernel (54 %) but not its limiter --
+// offloading 25 % of the exponentials is neutral, 50 % costs 6 % (7 more issue slots per element), so the default
+// mask is 0; kept for head dims / clocks where the balance differs.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.f);
+    const float t = x + 12582912.f;
+    const float n = t - 12582912.f;
+    const float f = x - n;
+    float p = fmaf(0.05517196f, f, 0.24261114f);
+    p = fmaf(p, f, 0.69326091f);
+    p = fmaf(p, f, 0.99992806f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+#ifndef DCB_FLASH_POLY_MASK
+#define DCB_FLASH_POLY_MASK 0x0          // which of the four 8-key groups of a 32-key chunk use ex2_poly (bit g4)
+#endif
+
 __global__ void __launch_bounds__(kFThreads, 2)
 flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const FlashTcParams p) {
@@ -76,6 +121,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kFQ, head = blockIdx.y, batch = blockIdx.z;
     const int T = p.ntiles;
+    FTR_DECL
 
     if ((smem_u32(fsm) & 1023) != 0) __trap();           // SWIZZLE_128B tiles need 1024-byte alignment
     if (warp == 0 && lane == 0) {
@@ -83,7 +129,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1);
-            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 4);
+            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 8);
         }
         fence_barrier_init();
     }
@@ -106,6 +152,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int b = j & 1;
             mbar_wait(&kv_empty[b], ((j >> 1) & 1) ^ 1);
             if (elect_one()) {
+                FTR(0, 1, j);
                 mbar_arrive_expect_tx(&k_full[b], kTileBytes);
                 tma_load_3d(sK + b * kTileBytes, &tmK, &k_full[b], head * kFD, j * kFK, batch);
                 mbar_arrive_expect_tx(&v_full[b], kTileBytes);
@@ -121,8 +168,10 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         auto issue_S = [&](int j) {
             const int b = j & 1;
             mbar_wait(&k_full[b], (j >> 1) & 1);
+            if (lane == 0) FTR(1, 2, j);
             if (j >= 2) mbar_wait(&s_free[b], ((j - 2) >> 1) & 1);      // softmax done with O_{j-2} in this buffer
             tc_fence_after();
+            if (lane == 0) FTR(1, 3, j);
             if (elect_one()) {
                 const uint64_t ad = make_sw128_kmajor_desc(aQ);
                 const uint64_t bd = make_sw128_kmajor_desc(smem_u32(sK + b * kTileBytes));
@@ -138,8 +187,10 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int b = j & 1;
             if (j + 1 < T) issue_S(j + 1);                                // next scores while softmax_j runs
             mbar_wait(&p_full[b], (j >> 1) & 1);
+            if (lane == 0) FTR(1, 4, j);
             mbar_wait(&v_full[b], (j >> 1) & 1);
             tc_fence_after();
+            if (lane == 0) FTR(1, 5, j);
             if (elect_one()) {
                 const uint32_t aP = smem_u32(sP), aV = smem_u32(sV + b * kTileBytes);
 #pragma unroll
@@ -154,42 +205,50 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             __syncwarp();
         }
     } else {
-        // ------------------------------------------------------------------ softmax / output: thread = query row
-        const int q = warp & 3;
+        // ------------------------------------------------------------------ softmax / output: 2 threads per query row
+        const int q = warp & 3;                    // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;          // which 64 keys of a tile / which 32 output columns are mine
         const int r = q * 32 + lane;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const float sl2 = p.scale_log2;
-        float m_run = -INFINITY, l_run = 0.f;
-        float o[kFD];
+        float m_run = -INFINITY, l_run = 0.f;      // l_run: sum over MY keys only
+        float o[kFD / 2];
 #pragma unroll
-        for (int i = 0; i < kFD; ++i) o[i] = 0.f;
+        for (int i = 0; i < kFD / 2; ++i) o[i] = 0.f;
 
+        // pass 1 of a tile: wait for S_j, row max over all 128 keys (both threads of a row compute the same value)
+        auto row_max = [&](int j) -> float {
+            const int b = j & 1;
+            const uint32_t t_s = t_row + b * 128;
+            const int kmax = p.nk - j * kFK;
+            mbar_wait(&s_full[b], (j >> 1) & 1);
+            tc_fence_after();
+            if (lane == 0 && q == 2) FTR(2 + half, 6, j);
+            float mx = -INFINITY;
+            // four round trips of 32 columns: two loads in flight per trip were measured slower (register spills)
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                uint32_t v0[32];
+                tmem_ld32(t_s + c4 * 32, v0);
+                tmem_ld_wait();
+                if (kmax >= kFK) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v0[i + 1])));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c4 * 32 + i < kmax) mx = fmaxf(mx, __uint_as_float(v0[i]));
+                }
+            }
+            return mx;
+        };
+        // software pipeline: the row max of tile j + 1 is computed while the tensor core runs P_j V_j
+        float mx = row_max(0);
         for (int j = 0; j < T; ++j) {
             const int b = j & 1;
             const uint32_t t_s = t_row + b * 128;
             const int kmax = p.nk - j * kFK;                               // keys valid in this tile (>= 128 unless last)
-            mbar_wait(&s_full[b], (j >> 1) & 1);
-            tc_fence_after();
             const bool ragged = kmax < kFK;                                // warp-uniform
-            // ---- pass 1: tile row max (two 64-column batches so only two TMEM round trips are exposed)
-            float mx = -INFINITY;
-#pragma unroll
-            for (int c2 = 0; c2 < 2; ++c2) {
-                uint32_t v0[32], v1[32];
-                tmem_ld32(t_s + c2 * 64, v0);
-                tmem_ld32(t_s + c2 * 64 + 32, v1);
-                tmem_ld_wait();
-                if (!ragged) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (c2 * 64 + i < kmax) mx = fmaxf(mx, __uint_as_float(v0[i]));
-                        if (c2 * 64 + 32 + i < kmax) mx = fmaxf(mx, __uint_as_float(v1[i]));
-                    }
-                }
-            }
             // ---- lazy rescale: keep exponentiating against the stale max until it is off by more than 2^8;
             // softmax is invariant to the reference value, p <= 256 is harmless in fp32 / bf16.
             const bool upd = (mx - m_run) * sl2 > 8.0f;                    // first tile: m_run = -inf -> true
@@ -199,26 +258,30 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 m_run = m_new;
                 l_run *= alpha;
 #pragma unroll
-                for (int i = 0; i < kFD; ++i) o[i] *= alpha;
+                for (int i = 0; i < kFD / 2; ++i) o[i] *= alpha;
             }
             const float msc = m_run * sl2;
             float rs = 0.f;
-            // ---- pass 2: P = exp2(S*scale - m) -> bf16 A operand in smem (P_{j-1} was consumed: o_full[j-1] awaited)
+            // ---- pass 2: my 64 keys: P = exp2(S*scale - m) -> bf16 A operand in smem (P_{j-1} was consumed: o_full[j-1]
+            // awaited by both threads of the row before they got here)
+            uint8_t* prow = sP + half * kTileBytes + r * 128;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t v[32];
-                tmem_ld32(t_s + c * 32, v);
+                tmem_ld32(t_s + half * 64 + c * 32, v);
                 tmem_ld_wait();
-                uint8_t* prow = sP + (c >> 1) * kTileBytes + r * 128;
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
                     float e[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) e[i] = ex2(fmaf(__uint_as_float(v[g4 * 8 + i]), sl2, -msc));
+                    for (int i = 0; i < 8; ++i) {
+                        const float xx = fmaf(__uint_as_float(v[g4 * 8 + i]), sl2, -msc);
+                        e[i] = ((DCB_FLASH_POLY_MASK >> g4) & 1) ? ex2_poly(xx) : ex2(xx);
+                    }
                     if (ragged) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            if (c * 32 + g4 * 8 + i >= kmax) e[i] = 0.f;
+                            if (half * 64 + c * 32 + g4 * 8 + i >= kmax) e[i] = 0.f;
                     }
                     rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
                     uint4 pk;
@@ -226,7 +289,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     __nv_bfloat162 h2 = __floats2bfloat162_rn(e[4], e[5]), h3 = __floats2bfloat162_rn(e[6], e[7]);
                     pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
                     pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                    const int chunk = (c & 1) * 4 + g4;                    // 16-byte chunk inside the 128-byte row
+                    const int chunk = c * 4 + g4;                          // 16-byte chunk inside the 128-byte row
                     *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = pk;
                 }
             }
@@ -235,26 +298,36 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[b]);
-            // ---- O += P_j V_j
+            if (lane == 0 && q == 2) FTR(2 + half, 7, j);
+            // ---- row max of the next tile (its S is already in the other TMEM buffer) while P_j V_j runs
+            float mx_next = -INFINITY;
+            if (j + 1 < T) mx_next = row_max(j + 1);
+            // ---- my 32 columns of O += P_j V_j
+            if (lane == 0 && q == 2) FTR(2 + half, 8, j);
             mbar_wait(&o_full[b], (j >> 1) & 1);
             tc_fence_after();
+            if (lane == 0 && q == 2) FTR(2 + half, 9, j);
             {
-                uint32_t v0[32], v1[32];
-                tmem_ld32(t_s, v0);
-                tmem_ld32(t_s + 32, v1);
+                uint32_t v0[32];
+                tmem_ld32(t_s + half * 32, v0);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { o[i] += __uint_as_float(v0[i]); o[32 + i] += __uint_as_float(v1[i]); }
+                for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(v0[i]);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_free[b]);
+            mx = mx_next;
         }
-        // ---- normalise, stage as bf16 (SWIZZLE_128B rows of 64) in sP half 0, TMA store (rows >= nq are clipped)
-        const float inv = 1.f / l_run;
+        // ---- combine the two partial row sums (through the idle second P half), normalise, stage as bf16
+        // (SWIZZLE_128B rows of 64) in sP half 0, TMA store (rows >= nq are clipped)
+        float* s_l = reinterpret_cast<float*>(sP + kTileBytes);           // [2][128]; all PV MMAs have retired
+        s_l[half * 128 + r] = l_run;
+        named_bar_sync(1, 256);
+        const float inv = 1.f / (s_l[r] + s_l[128 + r]);
         uint8_t* orow = sP + r * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
             uint4 pk;
             __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * c] * inv, o[8 * c + 1] * inv);
             __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
@@ -262,16 +335,19 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
             pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
             pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(orow + ((c ^ (r & 7)) << 4)) = pk;
+            *reinterpret_cast<uint4*>(orow + (((half * 4 + c) ^ (r & 7)) << 4)) = pk;
         }
         fence_proxy_async();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         if (warp == 2 && lane == 0) {
             tma_store_3d(&tmO, sP, head * kFD, q0, batch);
             tma_store_commit();
             tma_store_wait_all<0>();
         }
     }
+    if (warp == 0 && lane == 0) FTR_DONE(0);
+    if (warp == 1 && lane == 0) FTR_DONE(1);
+    if ((warp == 2 || warp == 6) && lane == 0) FTR_DONE(2 + ((warp - 2) >> 2));
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<256>(tmem_base);
@@ -333,3 +409,12 @@ int flash_tc_launch(const dcb_attention_args* a, cudaStream_t stream) {
 }
 
 }  // namespace dcb
+
+#ifdef DCB_TRACE
+extern "C" int dcb_debug_flash_trace(unsigned long long* dst, int cap) {
+    cudaDeviceSynchronize();
+    if (cap < 4 * 4096) return -1;
+    cudaMemcpyFromSymbol(dst, dcb::g_flash_trace, 4 * 4096 * sizeof(unsigned long long));
+    return 4 * 4096;
+}
+#endif
