@@ -417,6 +417,8 @@ def main():
     # ---------------- one full video through the public API: sample(50 steps) + all-gather + VAE decode
     video = None
     if not args.no_video:
+        # the UNet has run its warm-up steps; give the decoder one too (lazy weight packing, allocator growth)
+        host.decode_first_stage(inp["x_T"][:, :, :8].contiguous(), frames_per_call=8)
         barrier()
         t0 = time.perf_counter()
         samples, _ = smp.sample(S=sm["S"], batch_size=B, shape=(4, T, h, w), conditioning=cond,

@@ -90,6 +90,26 @@ def test_vae_decode_vs_reference_golden():
     assert err < BF16_TOL and psnr > 45.0
 
 
+def test_vae_decode_full_size_vs_oracle():
+    """The real decoder (ch 128, mult 1-2-4-4, mid attention over 2560 tokens) on one 40x64 latent frame of the 512
+    config against the CPU oracle: the tiny fixture above never reaches these widths / the 2560-token AttnBlock."""
+    from oracle import vae_oracle
+    from dynamicrafter_b200.configs import model_params
+    from dynamicrafter_b200.lvdm.models.autoencoder import AutoencoderKL
+    fsc = model_params("512")["first_stage_config"]["params"]
+    ae = AutoencoderKL(ddconfig=fsc["ddconfig"], embed_dim=fsc["embed_dim"])
+    sd = synth_state_dict({k: tuple(v.shape) for k, v in ae.state_dict().items()}, 11)
+    ae.load_state_dict(sd)
+    ae = ae.cuda().eval()
+    z = synth_input("z", (1, 4, 40, 64), 11) * 4.0
+    ref = vae_oracle.decode(sd, fsc["ddconfig"], z)
+    y = ae.decode(z.cuda()).cpu()
+    mse = float(((y - ref) ** 2).mean())
+    psnr = 10 * torch.log10(torch.tensor(4.0 / mse)).item()
+    print(f"\nfull-size VAE, 320x512 frame: rel-L2 {rel_l2(y, ref):.3e}, PSNR {psnr:.1f} dB")
+    assert y.shape == (1, 3, 320, 512) and rel_l2(y, ref) < BF16_TOL and psnr > 45.0
+
+
 class _MockDiffusion:
     """Duck-typed stand-in for LatentVisualDiffusion (what DDIMSampler reads)."""
 
