@@ -271,6 +271,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="fp32 = the <=1e-3 parity mode (hi/lo-split operands, 3x GEMM work, CUDA-core attention); "
                          "the headline numbers are the bf16 mode")
+    ap.add_argument("--branch-shard", action="store_true",
+                    help="N=2: ONE video, cond branch on rank 0 and uncond on rank 1, predictions all-gathered every step "
+                         "(strong scaling of single-video latency)")
     ap.add_argument("--frame-shard", action="store_true",
                     help="N>1: ONE video, its 16 frames sharded over the ranks (all-to-all around the temporal blocks); "
                          "strong scaling of single-video latency (BASELINE.json configs[3])")
@@ -308,6 +311,7 @@ def main():
             os.close(saved)
     _lib.check(_lib.lib().dcb_check_device(), "dcb_check_device")
     peaks = load_peaks()
+    torch.manual_seed(SEED)                  # same per-step noise on every rank (sharded single-video modes)
 
     host, mp = build_host(args.config, dev, with_vae=not args.no_video)
     host.unet.use_cuda_graph = not args.no_graph
@@ -315,7 +319,8 @@ def main():
     if fshard:
         from dynamicrafter_b200.parallel import FrameShard
         host.unet.frame_shard = FrameShard()
-    units = 1 if fshard else world          # videos in flight over the whole job
+    bshard = args.branch_shard and world > 1
+    units = 1 if (fshard or bshard) else world          # videos in flight over the whole job
     sm = SAMPLER[args.config]
     B, T = 1, 16
     h, w = mp["image_size"]
@@ -325,6 +330,9 @@ def main():
     cond = {"c_crossattn": [inp["cond"]], "c_concat": [inp["concat"]]}
     uc = {"c_crossattn": [inp["uncond"]], "c_concat": [inp["concat"]]}
     smp = DDIMSampler(host)
+    if bshard:
+        from dynamicrafter_b200.parallel import BranchShard
+        smp.branch_shard = BranchShard()
     smp.make_schedule(sm["S"], ddim_discretize=sm["timestep_spacing"], ddim_eta=sm["eta"], verbose=False)
     steps_desc = list(reversed(list(smp.ddim_timesteps)))
     total = len(steps_desc)
@@ -399,7 +407,7 @@ def main():
     launches_per_step = _lib.CALLS[0] - calls0
     host.unet.use_cuda_graph = not args.no_graph
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    step_tflop = 2 * UNET_TFLOP[args.config] * B / (world if fshard else 1)      # per-GPU share of one step
+    step_tflop = 2 * UNET_TFLOP[args.config] * B / (world if (fshard or bshard) else 1)      # per-GPU share of one step
     roofline = {"bound": "tensor", "kernel": "tap_gemm_kernel (tcgen05 implicit GEMM: linear + conv3x3 + temporal conv)",
                 "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": round(achieved / peaks["tflops"], 4),
@@ -428,8 +436,9 @@ def main():
         torch.cuda.synchronize()
         t_s = time.perf_counter() - t0
         from dynamicrafter_b200.parallel import all_gather_latents
-        if fshard:                                    # every rank holds the whole video: decode own frames only
-            f0, f1 = host.unet.frame_shard.frames(T)
+        if fshard or bshard:                          # every rank holds the whole video: decode own frames only
+            from dynamicrafter_b200.parallel import shard_range
+            f0, f1 = shard_range(T, rank, world)
             t1 = time.perf_counter()
             frames = host.decode_first_stage(samples[:, :, f0:f1].contiguous(), frames_per_call=8)
         else:
@@ -464,7 +473,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 4), "unit": "steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
-                "scaling": "strong" if fshard else "weak",
+                "scaling": "strong" if (fshard or bshard) else "weak",
                 "vs_baseline": None,
                 "dtype": "bf16" if args.precision == "bf16" else "fp32 (bf16 hi/lo split x3 on tensor cores)",
                 "data": "synthetic",
@@ -473,7 +482,9 @@ def main():
                                        f"{sm['guidance_rescale']}; 1 video per GPU; random-init weights (1.44 B params)",
                            "videos_per_gpu": B, "cuda_graph": (not args.no_graph) and not fshard,
                            "parallelism": (f"frame-sharded x{world}: one video, {T // world} frames per GPU, all-to-all "
-                                           "around the temporal blocks") if fshard else f"one video per GPU x{world}",
+                                           "around the temporal blocks") if fshard else
+                                          ((f"branch-sharded x{world}: one video, one guidance branch per GPU, predictions "
+                                            "all-gathered every step") if bshard else f"one video per GPU x{world}"),
                            "l2": "not flushed: per-step working set (2.9 GB bf16 weights + activations) >> 126 MB L2"},
                 "s_per_video_unet_only": round(sm["S"] * ms_per_step * 1e-3, 3),
                 "e2e": {"value": round(e2e_value, 4), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -200,6 +200,11 @@ class DDIMSampler(object):
     def _eval_branches(self, x, t, conds, kwargs):
         """One UNet forward over all guidance branches (same x, t; different conditioning) -> list of outputs."""
         b, n = x.shape[0], len(conds)
+        shard = getattr(self, "branch_shard", None)      # parallel.BranchShard: one guidance branch per GPU
+        if shard is not None:
+            if shard.world != n:
+                raise ValueError(f"branch sharding needs {n} ranks (one per guidance branch), got {shard.world}")
+            return shard.gather(self.model.apply_model(x, t, conds[shard.rank], **kwargs))
         allc = self._cat_cond(*conds) if self.batch_cfg else None
         if allc is None:
             return [self.model.apply_model(x, t, c, **kwargs) for c in conds]

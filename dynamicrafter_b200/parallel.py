@@ -93,3 +93,24 @@ def all_reduce_sums(sums, shard):
     """In-place SUM of the GroupNorm partial (sum, sum of squares) over the ranks holding the instance."""
     dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=shard.group)
     return sums
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Guidance branches over GPUs (SURVEY.md 8(e) row 1, option (i)): the cond / uncond (/ image-only) forwards of one
+# video share nothing but x_t, so rank r evaluates branch r % n_branches and the [B, 4, T, h, w] predictions (655 KB
+# each at the 512 config) are all-gathered every step; every rank then applies the fused update redundantly.
+# ------------------------------------------------------------------------------------------------------------
+class BranchShard:
+    """One guidance branch per rank: the world size must equal the number of branches of the sampler (2, or 3 for the
+    multi-condition sampler)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def gather(self, mine):
+        """mine: this rank's branch output -> list of all branch outputs in branch order."""
+        outs = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(outs, mine.contiguous(), group=self.group)
+        return outs

@@ -354,8 +354,10 @@ def test_unet_full_512_config_vs_oracle_reduced_frames():
     assert err32 < FP32_TOL
 
 
-def test_frame_sharded_unet_matches_single_gpu():
-    """frames sharded over 2 GPUs, all-to-all around the temporal blocks (needs >= 2 GPUs)."""
+@pytest.mark.parametrize("script", ["frame_shard_check.py", "branch_shard_check.py"])
+def test_sharded_single_video_modes_match_single_gpu(script):
+    """frames sharded over 2 GPUs (all-to-all around the temporal blocks) and guidance branches sharded
+    over 2 GPUs (predictions all-gathered every step); both need >= 2 GPUs."""
     import os, socket, subprocess, sys
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
@@ -365,7 +367,7 @@ def test_frame_sharded_unet_matches_single_gpu():
     s.close()
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(here, "frame_shard_check.py")],
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(here, script)],
                        capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0
