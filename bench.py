@@ -87,6 +87,11 @@ class ClockSampler:
                 "power_w_max": max(pw), "samples": len(sm)}
 
 
+def _graph_collectives():
+    from dynamicrafter_b200.lvdm import _packing
+    return _packing.GRAPH_COLLECTIVES
+
+
 def build_host(cfg_name, device, with_vae=True):
     from dynamicrafter_b200.configs import model_params
     from dynamicrafter_b200.host import DiffusionHost
@@ -316,10 +321,24 @@ def main():
     host, mp = build_host(args.config, dev, with_vae=not args.no_video)
     host.unet.use_cuda_graph = not args.no_graph
     fshard = args.frame_shard and world > 1
+    bshard = args.branch_shard and world > 1
+    fgroup = bgroup = None
+    nf = world                                # ranks sharing the frames of one guidance branch
+    if fshard and bshard:
+        # 2 x (world / 2): rank r runs guidance branch r % 2 on frame shard r // 2
+        assert world % 2 == 0 and world >= 4, "--frame-shard --branch-shard needs 4 or 8 ranks"
+        nf = world // 2
+        for br in range(2):
+            g = dist.new_group([r for r in range(world) if r % 2 == br])
+            if rank % 2 == br:
+                fgroup = g
+        for fi in range(nf):
+            g = dist.new_group([2 * fi, 2 * fi + 1])
+            if rank // 2 == fi:
+                bgroup = g
     if fshard:
         from dynamicrafter_b200.parallel import FrameShard
-        host.unet.frame_shard = FrameShard()
-    bshard = args.branch_shard and world > 1
+        host.unet.frame_shard = FrameShard(fgroup)
     units = 1 if (fshard or bshard) else world          # videos in flight over the whole job
     sm = SAMPLER[args.config]
     B, T = 1, 16
@@ -332,7 +351,7 @@ def main():
     smp = DDIMSampler(host)
     if bshard:
         from dynamicrafter_b200.parallel import BranchShard
-        smp.branch_shard = BranchShard()
+        smp.branch_shard = BranchShard(bgroup)
     smp.make_schedule(sm["S"], ddim_discretize=sm["timestep_spacing"], ddim_eta=sm["eta"], verbose=False)
     steps_desc = list(reversed(list(smp.ddim_timesteps)))
     total = len(steps_desc)
@@ -454,7 +473,7 @@ def main():
         vid_tflop = 100 * UNET_TFLOP[args.config] + VAE_TFLOP[args.config]
         video = {"s_per_video": round(float(tv[0]), 3), "sample_s": round(float(tv[1]), 3), "decode_s": round(float(tv[2]), 3),
                  "videos_per_s_all_gpus": round(units / float(tv[0]), 4), "tflops": round(vid_tflop / float(tv[0]), 1),
-                 "frac_of_peak": round(vid_tflop / float(tv[0]) / peaks["tflops"], 4),
+                 "frac_of_peak": round(vid_tflop / float(tv[0]) / peaks["tflops"] / (world if (fshard or bshard) else 1), 4),
                  "finite": bool(torch.isfinite(frames).all())}
 
     # ---------------- CPU baseline (rank 0, N=1): the oracle on a bounded sample
@@ -480,8 +499,9 @@ def main():
                 "config": {"workload": f"DynamiCrafter {args.config} ({h * 8}x{w * 8}x16f, latent {h}x{w}), DDIM {sm['S']} "
                                        f"{sm['timestep_spacing']} eta {sm['eta']}, CFG {sm['cfg']}, guidance_rescale "
                                        f"{sm['guidance_rescale']}; 1 video per GPU; random-init weights (1.44 B params)",
-                           "videos_per_gpu": B, "cuda_graph": (not args.no_graph) and not fshard,
-                           "parallelism": (f"frame-sharded x{world}: one video, {T // world} frames per GPU, all-to-all "
+                           "videos_per_gpu": B, "cuda_graph": (not args.no_graph) and (not fshard or _graph_collectives()),
+                           "parallelism": (f"frame-sharded x{nf}" + (" x 2 guidance branches" if bshard else "") +
+                                           f": one video, {T // nf} frames per GPU, all-to-all "
                                            "around the temporal blocks") if fshard else
                                           ((f"branch-sharded x{world}: one video, one guidance branch per GPU, predictions "
                                             "all-gathered every step") if bshard else f"one video per GPU x{world}"),
@@ -493,6 +513,15 @@ def main():
                 "video": video, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
+        from dynamicrafter_b200.lvdm import _packing
+        if fshard and _packing.GRAPH_COLLECTIVES and not args.no_graph:
+            # CUDA graphs that contain NCCL kernels: process-group / graph teardown hangs with torch 2.11 + NCCL 2.28,
+            # so leave without it once every rank has finished (the JSON line is already out)
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
