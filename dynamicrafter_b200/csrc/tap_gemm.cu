@@ -202,6 +202,7 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (a->geglu && !obf) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: geglu writes bf16 only");
+    if (a->geglu && a->residual != nullptr) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: geglu takes no residual");
     if (a->colsum != nullptr) return tap_gemm_launch_cs(bn, obf, pair, tmA, tmB, tmOut, tmRes, p, s);
     return launch_all<false>(bn, obf, pair, tmA, tmB, tmOut, tmRes, p, s);
 }
