@@ -23,8 +23,10 @@ def _no_tf32():
     torch.backends.cudnn.allow_tf32 = False
 
 
+# the last three rows: short-K, large-M launches of the 40x64 level (one of them ragged in M)
 @pytest.mark.parametrize("M,K,N", [(300, 320, 320), (128, 64, 128), (1000, 1280, 512), (77, 1024, 640), (4096, 320, 960),
-                                   (40000, 128, 1280), (20480, 640, 512)])
+                                   (40000, 128, 1280), (20480, 640, 512), (20480, 320, 320), (19000, 320, 960),
+                                   (40960, 256, 640)])
 def test_linear_bias_residual(M, K, N):
     from dynamicrafter_b200 import ops
     a, w = _mk((M, K), 1), _mk((N, K), 2, K ** -0.5)
@@ -50,10 +52,10 @@ def test_linear_strided_a_and_small_n():
     _close(out, ref, 1e-4)
 
 
-@pytest.mark.parametrize("K,inner,bn", [(128, 320, 128), (64, 256, 128), (320, 1280, 128), (320, 1280, 256), (64, 256, 256)])
-def test_geglu(K, inner, bn):
+@pytest.mark.parametrize("K,inner,bn,M", [(128, 320, 128, 200), (64, 256, 128, 200), (320, 1280, 128, 200),
+                                          (320, 1280, 256, 200), (64, 256, 256, 200), (320, 1280, 256, 20480)])
+def test_geglu(K, inner, bn, M):
     from dynamicrafter_b200 import ops
-    M = 200
     a, w = _mk((M, K), 5), _mk((2 * inner, K), 6, K ** -0.5)
     bias = torch.randn(2 * inner, device="cuda") * 0.1
     h = a.float() @ w.float().t() + bias
