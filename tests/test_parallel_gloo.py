@@ -91,3 +91,79 @@ def test_frame_pixel_transposes_world2():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) == 1.0
+
+
+def _branch_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dynamicrafter_b200.parallel import BranchShard
+    from dynamicrafter_b200.lvdm.models.samplers.ddim import DDIMSampler
+
+    class _Model:                                   # apply_model marks which conditioning it was given
+        num_timesteps = 1000
+        def apply_model(self, x, t, c, **kw):
+            return x + c
+
+    smp = DDIMSampler.__new__(DDIMSampler)
+    smp.model, smp.batch_cfg = _Model(), True
+    smp.branch_shard = BranchShard()
+    x = torch.zeros(1, 4, 2, 2, 2)
+    outs = smp._eval_branches(x, torch.zeros(1, dtype=torch.long), [torch.tensor([1.0]), torch.tensor([-2.0])], {})
+    ok = len(outs) == 2 and float(outs[0].mean()) == 1.0 and float(outs[1].mean()) == -2.0
+    try:                                            # three branches on two ranks must be refused
+        smp._eval_branches(x, None, [torch.tensor([1.0])] * 3, {})
+        ok = False
+    except ValueError:
+        pass
+    t = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(float(t))
+    dist.destroy_process_group()
+
+
+def test_branch_sharded_guidance_world2():
+    """one guidance branch per rank: rank r evaluates conditioning r, every rank ends with both predictions."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_branch_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) == 1.0
+
+
+def test_cat_cond_structures():
+    """the guidance branches are batched only when their conditionings line up structurally."""
+    from dynamicrafter_b200.lvdm.models.samplers.ddim import DDIMSampler
+    a, b = torch.ones(2, 3), torch.zeros(2, 3)
+    assert DDIMSampler._cat_cond(a, b).shape == (4, 3)
+    d1 = {"c_crossattn": [a], "c_concat": [torch.ones(2, 1)]}
+    d2 = {"c_crossattn": [b], "c_concat": [torch.ones(2, 1)]}
+    got = DDIMSampler._cat_cond(d1, d2, d2)
+    assert got["c_crossattn"][0].shape == (6, 3) and got["c_concat"][0].shape == (6, 1)
+    assert DDIMSampler._cat_cond(a, torch.zeros(2, 4)) is None
+    assert DDIMSampler._cat_cond(d1, {"c_crossattn": [b]}) is None
+    assert DDIMSampler._cat_cond(a, d1) is None
+
+
+def test_precision_switch():
+    from dynamicrafter_b200 import precision
+    assert precision.get_precision() in ("bf16", "fp32")
+    before = precision.get_precision()
+    with precision.use_precision("fp32"):
+        assert precision.fp32_mode()
+        with precision.use_precision("bf16"):
+            assert not precision.fp32_mode()
+        assert precision.fp32_mode()
+    assert precision.get_precision() == before
+    import pytest
+    with pytest.raises(ValueError):
+        precision.set_precision("fp16")
