@@ -84,6 +84,27 @@ class DiffusionHost(torch.nn.Module):
         shape = (x_t.shape[0],) + (1,) * (x_t.dim() - 1)
         return self.sqrt_alphas_cumprod[t].reshape(shape) * v + self.sqrt_one_minus_alphas_cumprod[t].reshape(shape) * x_t
 
+    def get_first_stage_encoding(self, encoder_posterior, noise=None):
+        """ddpm3d.py:611-618."""
+        z = encoder_posterior if isinstance(encoder_posterior, torch.Tensor) else encoder_posterior.sample(noise=noise)
+        return self.scale_factor * z
+
+    @torch.no_grad()
+    def encode_first_stage(self, x, frames_per_call=None):
+        """ddpm3d.py:620-644: [b, 3, t, H, W] (or [n, 3, H, W]) images in [-1, 1] -> scaled latents.  GroupNorm and
+        attention are per frame, so frames are batched (frames_per_call bounds memory, like perframe_ae)."""
+        five_d = x.dim() == 5
+        if five_d:
+            b, c, t, h, w = x.shape
+            x = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+        n = x.shape[0]
+        step = frames_per_call or n
+        out = torch.cat([self.get_first_stage_encoding(self.first_stage_model.encode(x[i:i + step].contiguous()))
+                         for i in range(0, n, step)], 0)
+        if five_d:
+            out = out.reshape(b, t, out.shape[1], out.shape[2], out.shape[3]).permute(0, 2, 1, 3, 4).contiguous()
+        return out
+
     @torch.no_grad()
     def decode_first_stage(self, z, frames_per_call=None, **kwargs):
         """ddpm3d.py:646-671.  The reference decodes frame by frame when perframe_ae (a memory workaround);

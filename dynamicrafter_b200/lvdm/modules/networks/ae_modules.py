@@ -47,14 +47,26 @@ class Upsample(PackedModule):
         return h.like(ops.conv3x3(up, nf, 2 * h.H, 2 * h.W, p["w"], bias=p["b"]), 2 * h.H, 2 * h.W)
 
 
-class Downsample(nn.Module):
-    """Encoder-side parameter holder (ae_modules.py:90-109)."""
+class Downsample(PackedModule):
+    """ae_modules.py:90-109: pad (0,1,0,1) then 3x3 stride-2 conv = implicit GEMM over the four 2x2 phase planes
+    with tap k reading pixel 2i + k (TMA zero fill supplies the right / bottom padding)."""
 
     def __init__(self, in_channels, with_conv):
         super().__init__()
+        if not with_conv:
+            raise NotImplementedError("avg-pool downsampling is not used by DynamiCrafter")
         self.with_conv, self.in_channels = with_conv, in_channels
-        if with_conv:
-            self.conv = torch.nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
+        self.conv = torch.nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
+
+    def _pack(self):
+        return {"w": pack_conv3x3(self.conv.weight), "b": _f32(self.conv.bias)}
+
+    def _fwd(self, h):
+        p = self.packed()
+        nf = h.B * h.T
+        planes = ops.space_to_depth(h.x, nf, h.H, h.W)
+        o = ops.conv3x3_s2(planes, nf, h.H, h.W, p["w"], bias=p["b"], asym=True)
+        return h.like(o, H=(h.H - 2) // 2 + 1, W=(h.W - 2) // 2 + 1)
 
 
 class ResnetBlock(PackedModule):
@@ -151,13 +163,15 @@ def make_attn(in_channels, attn_type="vanilla"):
     return AttnBlock(in_channels)
 
 
-class Encoder(nn.Module):
-    """Parameter holder with the reference's keys (ae_modules.py:364-436); not executed by dcb200."""
+class Encoder(PackedModule):
+    """ae_modules.py:364-463 on the dcb200 kernels (same conv / GroupNorm / attention kernels as the Decoder)."""
 
     def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
                  resamp_with_conv=True, in_channels, resolution, z_channels, double_z=True,
                  use_linear_attn=False, attn_type="vanilla", **ignore_kwargs):
         super().__init__()
+        if use_linear_attn:
+            raise NotImplementedError("linear attention is not used by DynamiCrafter")
         self.ch, self.temb_ch = ch, 0
         self.num_resolutions, self.num_res_blocks = len(ch_mult), num_res_blocks
         self.resolution, self.in_channels = resolution, in_channels
@@ -187,10 +201,40 @@ class Encoder(nn.Module):
         self.norm_out = Normalize(block_in)
         self.conv_out = torch.nn.Conv2d(block_in, 2 * z_channels if double_z else z_channels, kernel_size=3,
                                         stride=1, padding=1)
+        self.out_channels = self.conv_out.out_channels
 
+    def _pack(self):
+        return {"w_in": pack_conv3x3(self.conv_in.weight), "b_in": _f32(self.conv_in.bias),
+                "w_out": pack_conv3x3(self.conv_out.weight), "b_out": _f32(self.conv_out.bias)}
+
+    def _own_version(self):
+        return sum(q._version for q in (self.conv_in.weight, self.conv_in.bias, self.conv_out.weight, self.conv_out.bias))
+
+    def _fwd_rows(self, x_rows, n, hh, ww):
+        """x_rows: bf16 [n*hh*ww, 64] channels-last image (zero-padded channels) -> (fp32 [n*(hh/8)*(ww/8), 2z], h, w)."""
+        p = self.packed()
+        h = Act(ops.conv3x3(x_rows, n, hh, ww, p["w_in"], bias=p["b_in"]), n, 1, hh, ww)
+        for i_level in range(self.num_resolutions):
+            for i_block in range(self.num_res_blocks):
+                h = self.down[i_level].block[i_block]._fwd(h)
+                if len(self.down[i_level].attn) > 0:
+                    h = self.down[i_level].attn[i_block]._fwd(h)
+            if i_level != self.num_resolutions - 1:
+                h = self.down[i_level].downsample._fwd(h)
+        h = self.mid.block_1._fwd(h)
+        h = self.mid.attn_1._fwd(h)
+        h = self.mid.block_2._fwd(h)
+        y = _gn(self.norm_out, h, True)
+        return ops.conv3x3(y, n, h.H, h.W, p["w_out"], bias=p["b_out"]), h.H, h.W
+
+    @torch.no_grad()
     def forward(self, x):
-        raise NotImplementedError("VAE encode runs once per video and is outside the dcb200 hot path "
-                                  "(use the reference Encoder; SURVEY.md 8(f) N2)")
+        """x: [n, in_channels, H, W] fp32 -> [n, 2*z_channels, H/8, W/8] (ae_modules.py:438)."""
+        if not x.is_cuda:
+            raise RuntimeError("dcb200 Encoder runs on CUDA tensors only (no CPU path)")
+        n, c, hh, ww = x.shape
+        o, H, W = self._fwd_rows(ops.nchw_to_rows(x, 64), n, hh, ww)
+        return ops.rows_to_nchw(o, n, self.out_channels, 1, H, W, five_d=False).to(x.dtype)
 
 
 class Decoder(PackedModule):

@@ -513,16 +513,25 @@ def space_to_depth(x, nf, H, W):
 _S2 = {0: (1, -1), 1: (0, 0), 2: (1, 0)}   # k -> (phase, offset)
 
 
-def conv3x3_s2(planes, nf, H, W, w, *, bias=None, f32=True, bf16=False):
-    """planes: output of space_to_depth ([4*nf*Hp*Wp, C]); w: bf16 [N, 9*C] (ky,kx,c). -> [nf*Ho*Wo, N]"""
+# same conv with the VAE encoder's asymmetric padding (0,1,0,1) (ae_modules.py:103-106): tap k reads pixel 2i + k
+_S2_ASYM = {0: (0, 0), 1: (1, 0), 2: (0, 1)}
+
+
+def conv3x3_s2(planes, nf, H, W, w, *, bias=None, f32=True, bf16=False, asym=False):
+    """planes: output of space_to_depth ([4*nf*Hp*Wp, C]); w: bf16 [N, 9*C] (ky,kx,c). -> [nf*Ho*Wo, N].
+    asym=False: stride 2, pad 1 (UNet Downsample); asym=True: pad right / bottom only, then stride 2 (VAE encoder)."""
     C = planes.shape[1]
     Hp, Wp = (H + 1) // 2, (W + 1) // 2
-    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if asym:
+        Ho, Wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
+    else:
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    tab = _S2_ASYM if asym else _S2
     taps = []
     for ky in range(3):
-        py, oy = _S2[ky]
+        py, oy = tab[ky]
         for kx in range(3):
-            px, ox = _S2[kx]
+            px, ox = tab[kx]
             taps.append((ox, oy, (py * 2 + px) * nf))
     N = w.shape[0]
     of, ob, ld = _outputs(nf * Ho * Wo, N, None, f32, bf16, planes.device)

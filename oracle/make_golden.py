@@ -153,8 +153,21 @@ def golden_vae():
     z = synth_input("z", (2, 4, 8, 12), 11)
     with torch.no_grad():
         y = dec(pq(z))                                           # autoencoder.py:104-107
-    torch.save(dict(dd=TINY_VAE, seed=11, zshape=(2, 4, 8, 12), y=y.clone(), shapes=shapes), os.path.join(OUT, "vae_tiny.pt"))
-    print("vae_tiny y std", float(y.std()))
+    # encode side: Encoder + quant_conv -> moments of the posterior (autoencoder.py:97-102)
+    from lvdm.modules.networks.ae_modules import Encoder
+    enc = Encoder(**TINY_VAE).eval()
+    qc = torch.nn.Conv2d(2 * TINY_VAE["z_channels"], 2 * 4, 1)  # autoencoder.py:34
+    eshapes = {"encoder." + k: v for k, v in shapes_of(enc).items()}
+    eshapes.update({"quant_conv." + k: v for k, v in shapes_of(qc).items()})
+    esd = synth_state_dict(eshapes, 11)
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in esd.items() if k.startswith("encoder.")})
+    qc.load_state_dict({k[len("quant_conv."):]: v for k, v in esd.items() if k.startswith("quant_conv.")})
+    img = synth_input("img", (2, 3, 64, 96), 11)
+    with torch.no_grad():
+        moments = qc(enc(img))
+    torch.save(dict(dd=TINY_VAE, seed=11, zshape=(2, 4, 8, 12), y=y.clone(), shapes=shapes, enc_shapes=eshapes,
+                    img_shape=(2, 3, 64, 96), moments=moments.clone()), os.path.join(OUT, "vae_tiny.pt"))
+    print("vae_tiny y std", float(y.std()), "moments std", float(moments.std()))
 
 
 def build_lvd(unet_cfg, vae_cfg, base_yaml, seed):

@@ -1,10 +1,11 @@
-"""Functional fp32 restatement of AutoencoderKL.decode (TEST INFRASTRUCTURE).
+"""Functional fp32 restatement of AutoencoderKL.decode and .encode (TEST INFRASTRUCTURE).
 
 ``sd`` is the ``first_stage_model`` state_dict restricted to ``post_quant_conv.*`` and
 ``decoder.*`` keys; ``dd`` is ``first_stage_config.params.ddconfig``.
 Follows lvdm/models/autoencoder.py:104-107 and lvdm/modules/networks/ae_modules.py
 (Decoder.forward :539-578, ResnetBlock.forward :190-210, AttnBlock.forward :53-78,
-Upsample.forward :123-127, Normalize :15-16 -> GroupNorm(32, eps=1e-6)).
+Upsample.forward :123-127, Normalize :15-16 -> GroupNorm(32, eps=1e-6)); encode: autoencoder.py:97-102,
+Encoder.forward :438-463, Downsample.forward :103-109 (pad (0,1,0,1) + stride-2 conv).
 """
 import torch
 import torch.nn.functional as F
@@ -84,3 +85,23 @@ def decode_first_stage(sd, dd, z5, scale_factor=0.18215):
     frames = [decode(sd, dd, 1.0 / scale_factor * z[i:i + 1]) for i in range(z.shape[0])]
     out = torch.cat(frames, dim=0)
     return out.reshape(b, t, out.shape[1], out.shape[2], out.shape[3]).permute(0, 2, 1, 3, 4).contiguous()
+
+
+@torch.no_grad()
+def encode(sd, dd, x):
+    """x: [n, 3, H, W] image in [-1, 1] -> moments [n, 2*embed_dim, H/8, W/8] (mean | logvar), i.e. the
+    ``parameters`` of the reference's DiagonalGaussianDistribution (autoencoder.py:97-102)."""
+    ch, mult, nrb = dd["ch"], list(dd["ch_mult"]), dd["num_res_blocks"]
+    h = _conv(sd, "encoder.conv_in", x.float(), 1)
+    for lvl in range(len(mult)):
+        for blk in range(nrb):
+            h = resnet_block(sd, f"encoder.down.{lvl}.block.{blk}", h)
+        if lvl != len(mult) - 1:
+            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0)
+            h = F.conv2d(h, sd[f"encoder.down.{lvl}.downsample.conv.weight"], sd[f"encoder.down.{lvl}.downsample.conv.bias"],
+                         stride=2, padding=0)
+    h = resnet_block(sd, "encoder.mid.block_1", h)
+    h = attn_block(sd, "encoder.mid.attn_1", h)
+    h = resnet_block(sd, "encoder.mid.block_2", h)
+    h = _conv(sd, "encoder.conv_out", _swish(_gn(sd, "encoder.norm_out", h)), 1)
+    return _conv(sd, "quant_conv", h, 0)

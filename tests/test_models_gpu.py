@@ -90,6 +90,29 @@ def test_vae_decode_vs_reference_golden():
     assert err < BF16_TOL and psnr > 45.0
 
 
+def test_vae_encode_vs_reference_golden():
+    """AutoencoderKL.encode (Encoder with the pad-(0,1,0,1) stride-2 Downsample + quant_conv) against
+    the reference's moments; the posterior object mirrors lvdm/distributions.py."""
+    from dynamicrafter_b200.lvdm.models.autoencoder import AutoencoderKL
+    g = load_golden("vae_tiny.pt")
+    ae = AutoencoderKL(ddconfig=g["dd"], embed_dim=4)
+    full = {k: tuple(v.shape) for k, v in ae.state_dict().items()}
+    sd = synth_state_dict(full, 99)                                  # decoder side: anything
+    sd.update(synth_state_dict(g["enc_shapes"], g["seed"]))          # encoder + quant_conv: the golden's weights
+    ae.load_state_dict(sd)
+    ae = ae.cuda().eval()
+    img = synth_input("img", g["img_shape"], g["seed"])
+    post = ae.encode(img.cuda())
+    m = post.parameters.cpu()
+    err = rel_l2(m, g["moments"])
+    print(f"\nvae_tiny encode: moments rel-L2 vs reference golden {err:.3e}")
+    assert m.shape == g["moments"].shape and err < BF16_TOL
+    assert torch.equal(post.mode(), post.mean) and post.sample(torch.zeros_like(post.mean).cpu()).shape == post.mean.shape
+    # Encoder called directly with the reference's signature
+    h = ae.encoder(img.cuda())
+    assert h.shape == (2, 2 * g["dd"]["z_channels"], 8, 12)
+
+
 def test_vae_decode_full_size_vs_oracle():
     """The real decoder (ch 128, mult 1-2-4-4, mid attention over 2560 tokens) on one 40x64 latent frame of the 512
     config against the CPU oracle: the tiny fixture above never reaches these widths / the 2560-token AttnBlock."""

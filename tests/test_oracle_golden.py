@@ -59,6 +59,14 @@ def test_vae_oracle_matches_reference():
     assert rel_l2(y, g["y"]) < TOL
 
 
+def test_vae_encode_oracle_matches_reference():
+    g = load_golden("vae_tiny.pt")
+    sd = synth_state_dict(g["enc_shapes"], g["seed"])
+    img = synth_input("img", g["img_shape"], g["seed"])
+    m = vae_oracle.encode(sd, g["dd"], img)
+    assert m.shape == g["moments"].shape and rel_l2(m, g["moments"]) < TOL
+
+
 SCHED = {
     "c1": dict(kw=dict(parameterization="eps"), S=10, spacing="uniform", eta=1.0),
     "c2": dict(kw=dict(parameterization="v", rescale_betas_zero_snr=True, use_dynamic_rescale=True,
