@@ -261,6 +261,23 @@ ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ e_c, c
     *reinterpret_cast<float4*>(pred_x0 + i4) = make_float4(x0[0], x0[1], x0[2], x0[3]);
 }
 
+// Output stage (scripts/evaluation/inference.py:153-159, funcs.py:212-216): clamp to [-1, 1], (v + 1) / 2 * 255 with
+// the reference's fp32 operation order, truncate to uint8, [B, C, T, H, W] -> [B, T, H, W, C].  One thread per pixel.
+__global__ void __launch_bounds__(256)
+video_to_uint8_kernel(const float* __restrict__ src, int B, int C, int T, long long HW, unsigned char* __restrict__ dst) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long total = static_cast<long long>(B) * T * HW;
+    if (idx >= total) return;
+    const long long p = idx % HW;
+    const int t = static_cast<int>((idx / HW) % T), b = static_cast<int>(idx / (HW * T));
+    for (int c = 0; c < C; ++c) {
+        float v = __ldg(src + ((static_cast<long long>(b) * C + c) * T + t) * HW + p);
+        v = fminf(fmaxf(v, -1.0f), 1.0f);
+        v = __fmul_rn(__fdiv_rn(__fadd_rn(v, 1.0f), 2.0f), 255.0f);
+        dst[idx * C + c] = static_cast<unsigned char>(static_cast<int>(v));      // trunc toward zero, like .to(torch.uint8)
+    }
+}
+
 }  // namespace dcb
 
 using namespace dcb;
@@ -396,4 +413,11 @@ extern "C" int dcb_ddim_update_multicond(const float* x, const float* e_cond, co
     if (e_uncond_img == nullptr) return set_error(DCB_ERR_INVALID, "ddim_update_multicond: null image-only branch");
     return ddim_update_impl(x, e_cond, e_uncond, e_uncond_img, cfg_img, noise, B, per_sample, c, stds_ws, x_prev, pred_x0,
                             stream);
+}
+
+extern "C" int dcb_video_to_uint8(const float* src, int B, int C, int T, long long HW, unsigned char* dst, void* stream) {
+    if (!src || !dst || B < 1 || C < 1 || T < 1 || HW < 1) return set_error(DCB_ERR_INVALID, "video_to_uint8: bad argument");
+    const long long total = static_cast<long long>(B) * T * HW;
+    video_to_uint8_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, B, C, T, HW, dst);
+    return check_launch("video_to_uint8");
 }

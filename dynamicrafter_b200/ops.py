@@ -590,3 +590,14 @@ def ddim_update(x, e_cond, e_uncond, noise, coeffs, e_uncond_img=None, cfg_img=N
                                      ctypes.byref(coeffs), ptr(stds), ptr(x_prev), ptr(pred), _stream()),
           "dcb_ddim_update")
     return x_prev, pred
+
+
+def video_to_uint8(video):
+    """Decoded frames fp32 [B, C, T, H, W] in [-1, 1] -> uint8 [B, T, H, W, C] (what torchvision.io.write_video takes)."""
+    require_cuda(video)
+    v = video.float().contiguous()
+    B, C, T, H, W = v.shape
+    out = torch.empty((B, T, H, W, C), dtype=torch.uint8, device=v.device)
+    check(_lib.lib().dcb_video_to_uint8(ptr(v), _c_i(B), _c_i(C), _c_i(T), _c_ll(H * W), ptr(out), _stream()),
+          "dcb_video_to_uint8")
+    return out

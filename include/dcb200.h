@@ -182,6 +182,10 @@ int dcb_timestep_embedding(const long long* t, int B, int dim, float* out, void*
 int dcb_small_linear(const float* a, int lda, const float* w, const float* bias, int M, int N, int K,
                      int silu_in, int silu_out, int accumulate, float* out, int ldo, void* stream);
 
+/* Output stage (scripts/evaluation/inference.py:153-159): decoded frames [B, C, T, H, W] fp32 ->
+ * uint8 [B, T, H, W, C] = trunc((clamp(v, -1, 1) + 1) / 2 * 255), byte-exact with the reference's torch ops. */
+int dcb_video_to_uint8(const float* src, int B, int C, int T, long long HW, unsigned char* dst, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * fp32 parity mode (north_star: per-step eps within rel-L2 <= 1e-3 of the fp32 reference; csrc/fp32_mode.cu).
  * Contractions stay on the tensor cores: an fp32 operand becomes three bf16 columns blocks [hi | lo | hi]

@@ -198,3 +198,18 @@ def test_group_norm_bf16_source(G, S, C):
     ref = F.silu(F.group_norm(x.float().reshape(G, S, C).permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(G * S, C)
     y = ops.group_norm(x, G, S, gamma, beta, 1e-5, silu=True)
     assert _rel(y, ref) < 4e-3
+
+
+def test_video_to_uint8_byte_exact():
+    """output stage (inference.py:153-159): byte-exact against the reference's torch ops, including out-of-range
+    values, the exact endpoints and values sitting on uint8 boundaries."""
+    from dynamicrafter_b200 import ops
+    from oracle import output_oracle
+    x = _randn((2, 3, 5, 17, 23), 31, 0.9)
+    x[0, 0, 0, 0, :8] = torch.tensor([-1.0, 1.0, -3.0, 7.0, 0.0, -0.999999, 0.999999, 0.00392157], device=x.device)
+    k = torch.arange(0, 256, device=x.device, dtype=torch.float32)
+    x[1, 1, 2].reshape(-1)[:256] = k / 255.0 * 2.0 - 1.0            # values that land on (or next to) integer levels
+    got = ops.video_to_uint8(x)
+    ref = output_oracle.video_to_uint8(x)
+    assert got.dtype == torch.uint8 and got.shape == (2, 5, 17, 23, 3)
+    assert torch.equal(got.cpu(), ref)
