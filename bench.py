@@ -269,7 +269,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="512", choices=["256", "512", "1024"])
+    ap.add_argument("--config", default="512", choices=["256", "512", "1024", "512_interp"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-video", action="store_true")
@@ -345,6 +345,9 @@ def main():
     h, w = mp["image_size"]
     inp = make_inputs(mp, B, T, dev)
     pin = make_inputs(mp, B, T, dev, pinned=True)
+    if sm.get("keyframes_only"):            # interpolation / looping: only the two key frames condition the video
+        for d in (inp, pin):
+            d["concat"][:, :, 1:-1] = 0
     fs = torch.tensor([sm["fs"]] * B, dtype=torch.long, device=dev)
     cond = {"c_crossattn": [inp["cond"]], "c_concat": [inp["concat"]]}
     uc = {"c_crossattn": [inp["uncond"]], "c_concat": [inp["concat"]]}

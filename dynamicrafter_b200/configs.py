@@ -23,17 +23,24 @@ MODEL_PARAMS = {
                  unet_config=dict(params=dict(_UNET, default_fs=10)), first_stage_config=dict(params=_VAE)),
 }
 
+# generative frame interpolation / looping video (configs[4] of BASELINE.json; scripts/run_application.sh): the 512 model
+# with two-keyframe conditioning -- c_concat holds the first and last frame latents and zeros in between
+# (inference.py:245-248) -- and fs = 5
+MODEL_PARAMS["512_interp"] = MODEL_PARAMS["512"]
+
 # sampler settings of scripts/run.sh in the reference
 SAMPLER = {
     "256": dict(S=50, eta=1.0, cfg=7.5, timestep_spacing="uniform", guidance_rescale=0.0, fs=3),
     "512": dict(S=50, eta=1.0, cfg=7.5, timestep_spacing="uniform_trailing", guidance_rescale=0.7, fs=24),
     "1024": dict(S=50, eta=1.0, cfg=7.5, timestep_spacing="uniform_trailing", guidance_rescale=0.7, fs=10),
+    "512_interp": dict(S=50, eta=1.0, cfg=7.5, timestep_spacing="uniform_trailing", guidance_rescale=0.7, fs=5,
+                       keyframes_only=True),
 }
 
 # algorithmic FLOPs (2*MAC, conv + matmul only) of ONE UNet forward (B=1, 16 frames) and of the
 # 16-frame VAE decode, in TFLOP
-UNET_TFLOP = {"256": 4.904, "512": 12.603, "1024": 52.336}
-VAE_TFLOP = {"256": 9.955, "512": 25.016, "1024": 92.069}
+UNET_TFLOP = {"256": 4.904, "512": 12.603, "1024": 52.336, "512_interp": 12.603}
+VAE_TFLOP = {"256": 9.955, "512": 25.016, "1024": 92.069, "512_interp": 25.016}
 
 
 def model_params(name):
