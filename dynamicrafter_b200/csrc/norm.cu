@@ -212,12 +212,18 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
     return p;
 }
 
-template <typename T>
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* v) { *reinterpret_cast<uint4*>(p) = pack8(v); }
+__device__ __forceinline__ void store8(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+template <typename T, typename TOut = __nv_bfloat16>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int C2, int S,
                 int rows_per_chunk, const float* __restrict__ stats, const float* __restrict__ gamma,
-                const float* __restrict__ beta, int do_silu, __nv_bfloat16* __restrict__ y,
-                __nv_bfloat16* __restrict__ raw) {
+                const float* __restrict__ beta, int do_silu, TOut* __restrict__ y,
+                TOut* __restrict__ raw) {
     extern __shared__ float s_ab[];          // A[C] | B[C]
     const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
     const int C = C1 + C2, cg = C / kGroups;
@@ -244,7 +250,7 @@ gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int 
         float v[8];
         ld8(src, v);
         const int c0 = o * 8;
-        if (raw != nullptr) *reinterpret_cast<uint4*>(raw + row * C + c0) = pack8(v);
+        if (raw != nullptr) store8(raw + row * C + c0, v);
         if (y != nullptr) {
             const float4 A0 = *reinterpret_cast<const float4*>(s_ab + c0), A1 = *reinterpret_cast<const float4*>(s_ab + c0 + 4);
             const float4 B0 = *reinterpret_cast<const float4*>(s_ab + C + c0), B1 = *reinterpret_cast<const float4*>(s_ab + C + c0 + 4);
@@ -253,9 +259,9 @@ gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int 
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const float t = fmaf(v[e], am[e], bm[e]);
-                v[e] = do_silu ? silu_fast(t) : t;
+                v[e] = do_silu ? (sizeof(TOut) == 4 ? t / (1.0f + expf(-t)) : silu_fast(t)) : t;
             }
-            *reinterpret_cast<uint4*>(y + row * C + c0) = pack8(v);
+            store8(y + row * C + c0, v);
         }
         rr += drr;
         o += dO;
@@ -286,12 +292,6 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 #ifndef DCB_GN_OCC
 #define DCB_GN_OCC 3        // resident blocks per SM the register allocation must allow
 #endif
-__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* v) { *reinterpret_cast<uint4*>(p) = pack8(v); }
-__device__ __forceinline__ void store8(float* p, const float* v) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
-
 // TOut = bf16 (tensor-core operand) or float (fp32 parity mode, fp32_mode.cu)
 template <typename T, typename TOut = __nv_bfloat16>
 __global__ void __launch_bounds__(256, DCB_GN_OCC)
@@ -704,10 +704,25 @@ extern "C" int dcb_group_norm_apply(const float* x1, const float* x2, int C1, in
     int nch = 1;
     const int rpc = apply_rows_per_chunk(G, S, C, &nch);
     const size_t smem = static_cast<size_t>(C) * 2 * sizeof(float);
-    gn_apply_kernel<float><<<dim3(nch, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+    gn_apply_kernel<float, __nv_bfloat16><<<dim3(nch, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         x1, x2, C1, C2, S, rpc, stats, gamma, beta, silu_act, static_cast<__nv_bfloat16*>(y_bf16),
         static_cast<__nv_bfloat16*>(raw_bf16));
     return check_launch("group_norm_apply");
+}
+
+// fp32 output (fp32 parity mode with sharded instances: sums -> all-reduce -> stats -> this)
+extern "C" int dcb_group_norm_apply_f32out(const float* x, int C, int G, int S, const float* stats, const float* gamma,
+                                           const float* beta, int silu_act, float* y, void* stream) {
+    if (x == nullptr || y == nullptr || stats == nullptr || gamma == nullptr || beta == nullptr)
+        return set_error(DCB_ERR_INVALID, "group_norm_apply_f32out: null argument");
+    if (C % kGroups != 0 || (C & 7) || G < 1 || S < 1 || C > kMaxC)
+        return set_error(DCB_ERR_INVALID, "group_norm_apply_f32out: C=%d G=%d S=%d", C, G, S);
+    int nch = 1;
+    const int rpc = apply_rows_per_chunk(G, S, C, &nch);
+    const size_t smem = static_cast<size_t>(C) * 2 * sizeof(float);
+    gn_apply_kernel<float, float><<<dim3(nch, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        x, nullptr, C, 0, S, rpc, stats, gamma, beta, silu_act, y, nullptr);
+    return check_launch("group_norm_apply_f32out");
 }
 
 extern "C" int dcb_group_norm_apply_bf16(const void* x, int C, int G, int S, const float* stats, const float* gamma,
@@ -719,7 +734,7 @@ extern "C" int dcb_group_norm_apply_bf16(const void* x, int C, int G, int S, con
     int nch = 1;
     const int rpc = apply_rows_per_chunk(G, S, C, &nch);
     const size_t smem = static_cast<size_t>(C) * 2 * sizeof(float);
-    gn_apply_kernel<__nv_bfloat16><<<dim3(nch, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+    gn_apply_kernel<__nv_bfloat16, __nv_bfloat16><<<dim3(nch, G), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), nullptr, C, 0, S, rpc, stats, gamma, beta, silu_act,
         static_cast<__nv_bfloat16*>(y_bf16), nullptr);
     return check_launch("group_norm_apply_bf16");

@@ -288,6 +288,12 @@ def _group_norm_sharded(x1, G, S, gamma, beta, eps, silu, shard):
     count = float(S) * shard.world * (C // 32)
     check(L.dcb_group_norm_stats_from_sums(ptr(sums), _c_i(G), ctypes.c_double(count), _c_f(eps), ptr(stats), _stream()),
           "dcb_group_norm_stats_from_sums")
+    if fp32_mode():
+        assert x1.dtype == F32
+        y = torch.empty((G * S, C), dtype=F32, device=dev)
+        check(L.dcb_group_norm_apply_f32out(ptr(x1), _c_i(C), _c_i(G), _c_i(S), ptr(stats), ptr(gamma), ptr(beta),
+                                            _c_i(1 if silu else 0), ptr(y), _stream()), "dcb_group_norm_apply_f32out")
+        return y
     y = torch.empty((G * S, C), dtype=BF16, device=dev)
     if x1.dtype == BF16:
         check(L.dcb_group_norm_apply_bf16(ptr(x1), _c_i(C), _c_i(G), _c_i(S), ptr(stats), ptr(gamma), ptr(beta),
@@ -302,8 +308,10 @@ def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False
     """x1: fp32 [G*S, C1] (+ x2 [G*S, C2] concatenated on channels) -> bf16 normalised operand
     (and/or bf16 raw copy of the concat)."""
     require_cuda(x1, x2, gamma, beta)
+    if _SHARDED_GN[0] is not None:
+        assert x2 is None and not want_raw and want_norm and colsums is None
+        return _group_norm_sharded(x1, G, S, gamma, beta, eps, silu, _SHARDED_GN[0])
     if fp32_mode():
-        assert _SHARDED_GN[0] is None, "the fp32 parity mode is single-GPU"
         assert x1.dtype == F32 and x1.is_contiguous() and x1.shape[0] == G * S and want_norm
         C1, C2, dev, L = x1.shape[1], (0 if x2 is None else x2.shape[1]), x1.device, _lib.lib()
         ws, cnt = _gn_scratch(dev, G)
@@ -313,9 +321,6 @@ def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False
                                             ptr(beta), _c_i(1 if silu else 0), ptr(y), ptr(raw), ptr(ws), ptr(cnt),
                                             _stream()), "dcb_group_norm_fused_f32out")
         return (y, raw) if want_raw else y
-    if _SHARDED_GN[0] is not None:
-        assert x2 is None and not want_raw and want_norm and colsums is None
-        return _group_norm_sharded(x1, G, S, gamma, beta, eps, silu, _SHARDED_GN[0])
     if x1.dtype == BF16:
         # block-internal activation kept in bf16 by its producer: single source, normalised output only
         assert x2 is None and not want_raw and x1.is_contiguous() and x1.shape[0] == G * S

@@ -127,6 +127,9 @@ int dcb_group_norm_sums(const float* x1, const float* x2, int C1, int C2, int G,
 int dcb_group_norm_sums_bf16(const void* x, int C, int G, int S, double* sums, void* workspace,
                              unsigned* counters, void* stream);
 int dcb_group_norm_stats_from_sums(const double* sums, int G, double count, float eps, float* stats, void* stream);
+/* fp32-output apply for the fp32 parity mode on sharded instances (single fp32 source). */
+int dcb_group_norm_apply_f32out(const float* x, int C, int G, int S, const float* stats, const float* gamma,
+                                const float* beta, int silu_act, float* y, void* stream);
 /* Statistics + apply in one cooperative launch (every block resident; blocks of an instance meet at a counter):
  * same results as stats + apply, one HBM pass less for tensors that stay in L2.  counters: 2 * G unsigned, zero
  * before the first launch (self-cleaning); workspace as for dcb_group_norm_stats.  C1, C2 multiples of 8. */
