@@ -160,7 +160,7 @@ class OpTimer:
             e0.record()
             out = fn(*a, **kw)
             e1.record()
-            flops, key = 0, name
+            flops, key, nbytes = 0, name, 0
             if name == "tap_gemm":
                 dims, taps, w, N = a[1], a[4], a[5], a[6]
                 kdim = w.shape[1] // (3 if a[0].dtype == torch.float32 else 1)     # fp32 mode: algorithmic K, not 3K
@@ -170,11 +170,17 @@ class OpTimer:
                        f"res={kw.get('residual') is not None} geglu={bool(kw.get('geglu'))}")
             elif name == "group_norm":
                 key = f"group_norm G={a[1]} S={a[2]} C={a[0].shape[1] + (kw['x2'].shape[1] if kw.get('x2') is not None else 0)}"
+                # algorithmic bytes: every source element read once, every output element written once
+                outs = out if isinstance(out, tuple) else (out,)
+                nbytes = a[0].numel() * a[0].element_size() + sum(o.numel() * o.element_size() for o in outs)
+                if kw.get("x2") is not None:
+                    nbytes += kw["x2"].numel() * kw["x2"].element_size()
             elif name == "flash_attention":
                 key = f"flash_attention B={a[2]} H={a[3]} nq={a[4]} nk={[s[2] for s in a[1]]}"
             elif name == "layer_norm":
                 key = f"layer_norm rows={a[0].shape[0]} C={a[0].shape[1]}"
-            self.records.append((self.CLASSES.get(name, "layout_misc"), e0, e1, flops, key))
+                nbytes = a[0].numel() * a[0].element_size() + out.numel() * out.element_size()
+            self.records.append((self.CLASSES.get(name, "layout_misc"), e0, e1, flops, key, nbytes))
             return out
         return inner
 
@@ -185,9 +191,13 @@ class OpTimer:
     def summary(self):
         torch.cuda.synchronize()
         by, gemm_ms, gemm_flops, n_gemm, shapes = {}, 0.0, 0.0, 0, {}
-        for cls, e0, e1, fl, key in self.records:
+        self.hbm = {}                              # class -> [algorithmic bytes, ms] of the bandwidth-bound kernels
+        for cls, e0, e1, fl, key, nb in self.records:
             ms = e0.elapsed_time(e1)
             by[cls] = by.get(cls, 0.0) + ms
+            if nb:
+                h = self.hbm.setdefault(cls, [0, 0.0])
+                h[0] += nb; h[1] += ms
             ent = shapes.setdefault(key, [0, 0.0, 0.0])
             ent[0] += 1; ent[1] += ms; ent[2] += fl
             if cls == "tcgen05_gemm_conv":
@@ -442,7 +452,12 @@ def main():
                 "kernel_share_of_step": round(gemm_ms / max(sum(by.values()), 1e-9), 4),
                 "whole_step_tflops": round(step_tflop / (ms_per_step * 1e-3), 1),
                 "whole_step_frac_of_peak": round(step_tflop / (ms_per_step * 1e-3) / peaks["tflops"], 4),
-                "whole_step_frac_of_spec_2250": round(step_tflop / (ms_per_step * 1e-3) / 2250.0, 4)}
+                "whole_step_frac_of_spec_2250": round(step_tflop / (ms_per_step * 1e-3) / 2250.0, 4),
+                # the bandwidth-bound kernel classes of the same step: algorithmic bytes (each source element read
+                # once, each output written once) / CUDA-event time, against the measured copy bandwidth
+                "hbm_bound": {k: {"achieved_gbs": round(v[0] / (v[1] * 1e-3) / 1e9, 1), "peak_gbs": peaks["hbm"],
+                                  "frac": round(v[0] / (v[1] * 1e-3) / 1e9 / peaks["hbm"], 4)}
+                              for k, v in sorted(ot.hbm.items())}}
 
     # ---------------- one full video through the public API: sample(50 steps) + all-gather + VAE decode
     video = None
