@@ -296,7 +296,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 template <typename T, typename TOut = __nv_bfloat16>
 __global__ void __launch_bounds__(256, DCB_GN_OCC)
 gn_fused_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int C2, int S, int rows_per_chunk,
-                int row_split, float* __restrict__ partial, unsigned* __restrict__ counters, float eps,
+                int row_split, int col_mode, float* __restrict__ partial, unsigned* __restrict__ counters, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
                 TOut* __restrict__ y, TOut* __restrict__ raw) {
     extern __shared__ float s_mem[];        // phase 1: [row_split][C][2] partial slots; phase 2: A[C] | B[C]
@@ -312,8 +312,45 @@ gn_fused_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int C1, int 
     pdl_launch_dependents();
     pdl_wait();
 
-    // ---- phase 1: per-(row split, channel) sums of this block's rows; an item = (32 lanes x 16 bytes of channels,
-    // row split), 8 rows in flight per lane
+    // ---- phase 1, column mode (C <= 2048: one pass of 8-channel columns covers C): the same thread -> column mapping
+    // as phase 2 (a thread owns an 8-channel column and walks down the rows, 16 / 32-byte loads, 4 rows in flight);
+    // row_split = rows the block covers per step = 256 / (C / 8), one smem slot per (row lane, channel)
+    if (col_mode) {
+        const int O = C >> 3, O1 = C1 >> 3, nrows = r1 - r0;
+        const int rpp = row_split;
+        const int my_r = tid / O, my_o = tid - my_r * O;
+        if (my_r < rpp) {
+            const int c0 = my_o * 8;
+            const size_t row0 = static_cast<size_t>(n) * S + r0 + my_r;
+            const bool first = my_o < O1;
+            const T* src = first ? (x1 + row0 * C1 + c0) : (x2 + row0 * C2 + (c0 - C1));
+            const size_t sstep = static_cast<size_t>(rpp) * (first ? C1 : C2);
+            float s[8], ss[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s[e] = 0.f; ss[e] = 0.f; }
+            for (int r = my_r; r < nrows; r += rpp * 4) {
+                float v[4][8];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (r + u * rpp < nrows) ld8(src + u * sstep, v[u]);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { s[e] += v[u][e]; ss[e] = fmaf(v[u][e], v[u][e], ss[e]); }
+                src += 4 * sstep;
+            }
+            float* dst = s_mem + (static_cast<size_t>(my_r) * C + c0) * 2;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { dst[2 * e] = s[e]; dst[2 * e + 1] = ss[e]; }
+        }
+    } else
+    // ---- phase 1, item mode: per-(row split, channel) sums of this block's rows; an item = (32 lanes x 16 bytes of
+    // channels, row split), 8 rows in flight per lane
     for (int item = warp; item < Qb * row_split; item += 8) {
         const int cb = item / row_split, split = item - cb * row_split;
         const bool second = cb >= Qb1;
@@ -762,7 +799,12 @@ static int launch_gn_fused(const T* x1, const T* x2, int C1, int C2, int G, int 
     if (nch > kMaxChunks) nch = kMaxChunks;
     int rpc = (S + nch - 1) / nch;
     int split = 1;
-    if (rpc > 8) {
+    static int col_env = -1;                        // DCB_GN_COLS=0: item-mode phase 1 everywhere (A/B testing)
+    if (col_env < 0) { const char* e = getenv("DCB_GN_COLS"); col_env = (e == nullptr) ? 1 : atoi(e); }
+    const int col_mode = (col_env && C <= 2048 && rpc > 8) ? 1 : 0;
+    if (col_mode) {
+        split = 256 / (C >> 3);                     // rows per step of the column mapping
+    } else if (rpc > 8) {
         split = pl.row_split;
         rpc = (rpc + split - 1) / split * split;
     }
@@ -783,7 +825,7 @@ static int launch_gn_fused(const T* x1, const T* x2, int C1, int C2, int G, int 
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.numAttrs = 2;
     }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gn_fused_kernel<T, TOut>, x1, x2, C1, C2, S, rpc, split,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gn_fused_kernel<T, TOut>, x1, x2, C1, C2, S, rpc, split, col_mode,
                                        static_cast<float*>(workspace), counters, eps, gamma, beta, silu_act,
                                        static_cast<TOut*>(y), static_cast<TOut*>(raw));
     if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "group_norm_fused launch: %s", cudaGetErrorString(e));
