@@ -79,7 +79,7 @@ EXPORTS = [
     "dcb_group_norm_fused", "dcb_group_norm_fused_bf16",
     "dcb_group_norm_sums", "dcb_group_norm_sums_bf16", "dcb_group_norm_stats_from_sums", "dcb_group_norm_apply_f32out",
     "dcb_flash_attention", "dcb_temporal_attention", "dcb_softmax_rows",
-    "dcb_nchw_to_rows", "dcb_rows_to_nchw", "dcb_upsample2x", "dcb_space_to_depth", "dcb_cast_bf16",
+    "dcb_nchw_to_rows", "dcb_rows_to_nchw", "dcb_upsample2x", "dcb_space_to_depth", "dcb_cast_bf16", "dcb_gelu_bf16",
     "dcb_timestep_embedding", "dcb_small_linear", "dcb_ddim_update", "dcb_ddim_update_multicond", "dcb_video_to_uint8",
     "dcb_split_bf16x3", "dcb_geglu_f32", "dcb_attention_f32", "dcb_group_norm_fused_f32out", "dcb_layer_norm_f32out",
     "dcb_nchw_to_rows_f32out", "dcb_upsample2x_f32out", "dcb_space_to_depth_f32out",

@@ -261,6 +261,18 @@ ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ e_c, c
     *reinterpret_cast<float4*>(pred_x0 + i4) = make_float4(x0[0], x0[1], x0[2], x0[3]);
 }
 
+// y = gelu(x) (exact erf, nn.GELU default; resampler.py:32), fp32 in -> bf16 operand of the next GEMM.
+__global__ void __launch_bounds__(256)
+gelu_bf16_kernel(const float* __restrict__ src, long long n8, __nv_bfloat16* __restrict__ dst) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= n8) return;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.5f * v[e] * (1.0f + erff(v[e] * 0.70710678118654752440f));
+    reinterpret_cast<uint4*>(dst)[i] = pack8_bf16(v);
+}
+
 // Output stage (scripts/evaluation/inference.py:153-159, funcs.py:212-216): clamp to [-1, 1], (v + 1) / 2 * 255 with
 // the reference's fp32 operation order, truncate to uint8, [B, C, T, H, W] -> [B, T, H, W, C].  One thread per pixel.
 __global__ void __launch_bounds__(256)
@@ -420,4 +432,11 @@ extern "C" int dcb_video_to_uint8(const float* src, int B, int C, int T, long lo
     const long long total = static_cast<long long>(B) * T * HW;
     video_to_uint8_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, B, C, T, HW, dst);
     return check_launch("video_to_uint8");
+}
+
+extern "C" int dcb_gelu_bf16(const float* src, long long n, void* dst_bf16, void* stream) {
+    if (!src || !dst_bf16 || n < 8 || (n & 7)) return set_error(DCB_ERR_INVALID, "gelu_bf16: n must be a positive multiple of 8");
+    gelu_bf16_kernel<<<blocks_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, n / 8, static_cast<__nv_bfloat16*>(dst_bf16));
+    return check_launch("gelu_bf16");
 }

@@ -380,11 +380,12 @@ def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False
     return y if want_norm else raw
 
 
-def layer_norm(x, gamma, beta, eps=1e-5):
+def layer_norm(x, gamma, beta, eps=1e-5, out_f32=False):
+    """fp32 [rows, C] -> bf16 operand (or fp32 when the result leaves the engine, out_f32=True)."""
     require_cuda(x, gamma, beta)
     assert x.dtype == F32 and x.is_contiguous()
     rows, C = x.shape
-    if fp32_mode():
+    if fp32_mode() or out_f32:
         y = torch.empty((rows, C), dtype=F32, device=x.device)
         check(_lib.lib().dcb_layer_norm_f32out(ptr(x), _c_i(rows), _c_i(C), ptr(gamma), ptr(beta), _c_f(eps), ptr(y),
                                                _stream()), "dcb_layer_norm_f32out")
@@ -605,4 +606,13 @@ def video_to_uint8(video):
     out = torch.empty((B, T, H, W, C), dtype=torch.uint8, device=v.device)
     check(_lib.lib().dcb_video_to_uint8(ptr(v), _c_i(B), _c_i(C), _c_i(T), _c_ll(H * W), ptr(out), _stream()),
           "dcb_video_to_uint8")
+    return out
+
+
+def gelu_bf16(x):
+    """fp32 contiguous -> bf16 gelu(x) (exact erf)."""
+    require_cuda(x)
+    assert x.dtype == F32 and x.is_contiguous() and x.numel() % 8 == 0
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(_lib.lib().dcb_gelu_bf16(ptr(x), _c_ll(x.numel()), ptr(out), _stream()), "dcb_gelu_bf16")
     return out

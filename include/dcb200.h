@@ -180,6 +180,8 @@ int dcb_rows_to_nchw(const float* src, int ld, int B, int C, int T, int HW, floa
 int dcb_upsample2x(const float* src, int nf, int H, int W, int C, void* dst_bf16, void* stream);
 int dcb_space_to_depth(const float* src, int nf, int H, int W, int C, void* dst_bf16, void* stream);
 int dcb_cast_bf16(const float* src, long long n, void* dst_bf16, void* stream);
+/* y = gelu(x), exact erf (nn.GELU of the Resampler feed-forward, resampler.py:27-34); contiguous, n % 8 == 0. */
+int dcb_gelu_bf16(const float* src, long long n, void* dst_bf16, void* stream);
 int dcb_timestep_embedding(const long long* t, int B, int dim, float* out, void* stream);
 /* out[m,n] (+)= silu_out?( sum_k silu_in?(a[m,k]) * w[n,k] + bias[n] ); fp32, tiny M. */
 int dcb_small_linear(const float* a, int lda, const float* w, const float* bias, int M, int N, int K,

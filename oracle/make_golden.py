@@ -293,6 +293,24 @@ def golden_ddim():
     torch.save(out, os.path.join(OUT, "ddim.pt"))
 
 
+TINY_RESAMPLER = dict(dim=256, depth=2, dim_head=64, heads=4, num_queries=4, embedding_dim=192, output_dim=256,
+                      ff_mult=4, video_length=4)
+
+
+def golden_resampler():
+    """image_proj_model: the reference Resampler on synthetic CLIP tokens."""
+    from lvdm.modules.encoders.resampler import Resampler
+    m = Resampler(**TINY_RESAMPLER).eval()
+    shapes = shapes_of(m)
+    m.load_state_dict(synth_state_dict(shapes, 51), strict=True)
+    x = synth_input("clip_tokens", (2, 37, TINY_RESAMPLER["embedding_dim"]), 51)
+    with torch.no_grad():
+        y = m(x)
+    torch.save(dict(cfg=TINY_RESAMPLER, seed=51, xshape=tuple(x.shape), shapes=shapes, y=y.clone()),
+               os.path.join(OUT, "resampler_tiny.pt"))
+    print("resampler_tiny y std", float(y.std()), tuple(y.shape))
+
+
 def golden_keys():
     """state_dict key -> shape of the full-size 512 / 256 models (drop-in contract)."""
     from lvdm.modules.networks.openaimodel3d import UNetModel

@@ -113,6 +113,22 @@ def test_vae_encode_vs_reference_golden():
     assert h.shape == (2, 2 * g["dd"]["z_channels"], 8, 12)
 
 
+def test_resampler_vs_reference_golden():
+    """drop-in Resampler (image_proj_model) -- same state_dict keys as the reference, output within the
+    bf16 bar of the reference golden."""
+    from dynamicrafter_b200.lvdm.modules.encoders.resampler import Resampler
+    g = load_golden("resampler_tiny.pt")
+    m = Resampler(**g["cfg"])
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v) for k, v in g["shapes"].items()}
+    m.load_state_dict(synth_state_dict(g["shapes"], g["seed"]), strict=True)
+    m = m.cuda().eval()
+    x = synth_input("clip_tokens", g["xshape"], g["seed"])
+    y = m(x.cuda()).cpu()
+    err = rel_l2(y, g["y"])
+    print(f"\nresampler_tiny: rel-L2 vs reference golden {err:.3e}")
+    assert y.shape == g["y"].shape and err < BF16_TOL
+
+
 def test_vae_decode_full_size_vs_oracle():
     """The real decoder (ch 128, mult 1-2-4-4, mid attention over 2560 tokens) on one 40x64 latent frame of the 512
     config against the CPU oracle: the tiny fixture above never reaches these widths / the 2560-token AttnBlock."""

@@ -59,6 +59,15 @@ def test_vae_oracle_matches_reference():
     assert rel_l2(y, g["y"]) < TOL
 
 
+def test_resampler_oracle_matches_reference():
+    from oracle import resampler_oracle
+    g = load_golden("resampler_tiny.pt")
+    sd = synth_state_dict(g["shapes"], g["seed"])
+    x = synth_input("clip_tokens", g["xshape"], g["seed"])
+    y = resampler_oracle.resampler_forward(sd, g["cfg"], x)
+    assert y.shape == g["y"].shape and rel_l2(y, g["y"]) < TOL
+
+
 def test_vae_encode_oracle_matches_reference():
     g = load_golden("vae_tiny.pt")
     sd = synth_state_dict(g["enc_shapes"], g["seed"])
