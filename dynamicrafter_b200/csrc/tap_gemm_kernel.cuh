@@ -408,10 +408,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             for (int j = 0; j < 16; ++j)
                                 o[j] = (res_row != nullptr && cb + j < p.N_out) ? __ldg(res_row + cb + j) : 0.f;
                         }
-                    } else if (!(!kF32 && p.geglu)) {          // (the GEGLU branch assigns o[] itself)
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = 0.f;
-                    }
+                    }                                          // (otherwise o[] is assigned from the accumulator below)
+                    const bool o_has_res = !kF32 && p.has_residual;
                     uint32_t v[16];
                     tmem_ld16(t_row + ci * CW + hf * 16, v);
                     if (!kF32 && p.geglu) {
@@ -434,12 +432,15 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     } else {
                         tmem_ld_wait();
-                        if (p.out_scale != 1.0f) {
+                        if (o_has_res) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) o[j] = fmaf(__uint_as_float(v[j]), p.out_scale, o[j]);
+                        } else if (p.out_scale != 1.0f) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) * p.out_scale;
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) o[j] += __uint_as_float(v[j]);
+                            for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]);
                         }
                         if (p.bias != nullptr) {
                             if (cb + 16 <= p.N_out) {
