@@ -242,32 +242,81 @@ def cpu_sample_seconds(cfg_name, frames, threads):
     return sd, (lambda: unet_oracle.unet_forward(sd, ucfg, x, ts, ctx, fs))
 
 
+def _reference_available():
+    from oracle import ref_host
+    return ref_host.ref_root() is not None
+
+
+def time_reference_steps(config, steps, warmup, budget_s):
+    """Times the UNMODIFIED reference (oracle/_ref, staged by oracle/build_ref.py) on the host cores through its own
+    public API: one step = DDIMSampler.p_sample_ddim at the full workload shape (cond forward + uncond forward +
+    update; no frame or branch extrapolation).  K is honoured up to a wall-clock budget; returns the per-step times
+    actually measured."""
+    from oracle import ref_host
+    yaml_name = {"256": "inference_256_v1.0.yaml", "512": "inference_512_v1.0.yaml", "1024": "inference_1024_v1.0.yaml",
+                 "512_interp": "inference_512_v1.0.yaml"}[config]
+    t_build = time.perf_counter()
+    step, info = ref_host.reference_step_runner(yaml_name, threads=os.cpu_count(), seed=SEED)
+    info["build_s"] = time.perf_counter() - t_build
+    t_start = time.perf_counter()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        elapsed = time.perf_counter() - t_start
+        # stop early once another step would overrun the budget (always keep >= 1 timed step)
+        if i + 1 >= warmup + 1 and elapsed + dt > budget_s and i + 1 < warmup + steps:
+            if i < warmup:                       # budget exhausted inside the warm-up: time exactly one more step
+                t0 = time.perf_counter()
+                step()
+                times.append(time.perf_counter() - t0)
+            break
+    return times, info
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation (oracle port: the reference is pure Python and its host
-    needs pytorch_lightning/open_clip which are absent, so the functional torch restatement pinned to it is timed)."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores.  oracle/_ref
+    (the unmodified reference, pure Python, staged by oracle/build_ref.py) when present -> kind "reference"; else the
+    oracle port on a bounded sample -> kind "port"."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count()
-    frames = 2
-    sd, fwd = cpu_sample_seconds(args.config, frames, threads)
-    for _ in range(min(args.warmup, 1)):
-        fwd()
-    times = []
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        fwd()
-        times.append(time.perf_counter() - t0)
-    sec = sum(times) / len(times)
-    step_s = sec * (16 / frames) * 2                  # 16 frames, cond + uncond
+    budget = float(os.environ.get("DCB_REF_BUDGET_S", "150"))
+    if _reference_available():
+        warm = min(args.warmup, 1)
+        times, info = time_reference_steps(args.config, args.steps, warm, budget)
+        step_s = sum(times) / len(times)
+        n_steps = len(times)
+        kind = "reference"
+        h, w = info["latent"]
+        sample = (f"{n_steps} full DDIM step(s) of the unmodified reference ({info['api']}), latent {h}x{w}x{info['frames']}f, "
+                  f"2 UNet forwards per step, {threads} threads, {warm} warm-up step(s); no extrapolation; "
+                  f"--steps {args.steps} requested, bounded by a {budget:.0f} s budget")
+    else:
+        frames = 2
+        sd, fwd = cpu_sample_seconds(args.config, frames, threads)
+        for _ in range(min(args.warmup, 1)):
+            fwd()
+        times = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            fwd()
+            times.append(time.perf_counter() - t0)
+        step_s = sum(times) / len(times) * (16 / frames) * 2                  # 16 frames, cond + uncond
+        n_steps, warm, kind = args.steps, min(args.warmup, 1), "port"
+        sample = (f"oracle UNet forward (fp32 eager torch, {threads} threads), 1 CFG branch, {frames} of 16 frames at latent "
+                  f"40x64; step time extrapolated x{16 // frames} frames x2 branches (oracle/_ref not staged)")
     val = 1.0 / step_s
-    sample = (f"oracle UNet forward (fp32 eager torch, {threads} threads), 1 CFG branch, {frames} of 16 frames at latent 40x64; "
-              f"step time extrapolated x{16 // frames} frames x2 branches")
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "DynamiCrafter 512 (320x512x16f latent 40x64), DDIM 50 CFG 7.5, UNet step; CPU"},
-            "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": n_steps,
+            "warmup": warm, "steps_requested": args.steps, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "DynamiCrafter 512 (320x512x16f, latent 40x64), DDIM 50 uniform_trailing eta 1.0, CFG 7.5, "
+                                   "guidance_rescale 0.7; 1 video; reference default-init weights (1.44 B params); CPU"},
+            "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -494,18 +543,25 @@ def main():
                  "frac_of_peak": round(vid_tflop / float(tv[0]) / peaks["tflops"] / (world if (fshard or bshard) else 1), 4),
                  "finite": bool(torch.isfinite(frames).all())}
 
-    # ---------------- CPU baseline (rank 0, N=1): the oracle on a bounded sample
+    # ---------------- CPU baseline (rank 0, N=1): the unmodified reference (oracle/_ref) on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count()
-        frames_s = 2
-        _, fwd = cpu_sample_seconds(args.config, frames_s, threads)
-        t0 = time.perf_counter()
-        fwd()
-        sec = time.perf_counter() - t0
-        cpu = {"value": 1.0 / (sec * (16 / frames_s) * 2), "unit": "steps/s", "cores": threads, "kind": "port",
-               "sample": f"1 oracle UNet forward (1 CFG branch, {frames_s} of 16 frames, latent {h}x{w}) = {sec:.1f} s; "
-                         f"x{16 // frames_s} frames x2 branches extrapolated"}
+        if _reference_available():
+            times, info = time_reference_steps(args.config, 1, 0, 1e9)
+            cpu = {"value": 1.0 / times[0], "unit": "steps/s", "cores": threads, "kind": "reference",
+                   "sample": f"1 full DDIM step of the unmodified reference ({info['api']}) at the workload shape "
+                             f"(latent {h}x{w}x16f, cond + uncond forward + update) = {times[0]:.1f} s, un-warmed; "
+                             "no extrapolation"}
+        else:
+            frames_s = 2
+            _, fwd = cpu_sample_seconds(args.config, frames_s, threads)
+            t0 = time.perf_counter()
+            fwd()
+            sec = time.perf_counter() - t0
+            cpu = {"value": 1.0 / (sec * (16 / frames_s) * 2), "unit": "steps/s", "cores": threads, "kind": "port",
+                   "sample": f"1 oracle UNet forward (1 CFG branch, {frames_s} of 16 frames, latent {h}x{w}) = {sec:.1f} s; "
+                             f"x{16 // frames_s} frames x2 branches extrapolated"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 4), "unit": "steps/s", "n_gpus": world, "steps": args.steps,

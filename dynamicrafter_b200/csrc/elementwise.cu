@@ -427,6 +427,27 @@ extern "C" int dcb_ddim_update_multicond(const float* x, const float* e_cond, co
                             stream);
 }
 
+// out[b, i] = a[b] * x0[b, i] + c[b] * noise[b, i] with two explicitly rounded products and one rounded sum (the order
+// torch's eager `a * x0 + c * noise` evaluates, ddpm3d.py:305-308 q_sample / ddim.py:304-319 stochastic_encode).
+namespace dcb {
+__global__ void __launch_bounds__(256)
+q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const float* __restrict__ a,
+                const float* __restrict__ c, long long per, long long total, float* __restrict__ out) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= total) return;
+    const long long b = i / per;
+    out[i] = __fadd_rn(__fmul_rn(__ldg(a + b), x0[i]), __fmul_rn(__ldg(c + b), noise[i]));
+}
+}  // namespace dcb
+
+extern "C" int dcb_q_sample(const float* x0, const float* noise, const float* a, const float* c, int B, long long per_sample,
+                            float* out, void* stream) {
+    if (!x0 || !noise || !a || !c || !out || B < 1 || per_sample < 1) return set_error(DCB_ERR_INVALID, "q_sample: bad argument");
+    const long long total = static_cast<long long>(B) * per_sample;
+    q_sample_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x0, noise, a, c, per_sample, total, out);
+    return check_launch("q_sample");
+}
+
 extern "C" int dcb_video_to_uint8(const float* src, int B, int C, int T, long long HW, unsigned char* dst, void* stream) {
     if (!src || !dst || B < 1 || C < 1 || T < 1 || HW < 1) return set_error(DCB_ERR_INVALID, "video_to_uint8: bad argument");
     const long long total = static_cast<long long>(B) * T * HW;

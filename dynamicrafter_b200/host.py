@@ -84,6 +84,13 @@ class DiffusionHost(torch.nn.Module):
         shape = (x_t.shape[0],) + (1,) * (x_t.dim() - 1)
         return self.sqrt_alphas_cumprod[t].reshape(shape) * v + self.sqrt_one_minus_alphas_cumprod[t].reshape(shape) * x_t
 
+    def q_sample(self, x_start, t, noise=None):
+        """ddpm3d.py:305-308 (used by the sampler's mask / x0 blend path, ddim.py:179)."""
+        from dynamicrafter_b200 import ops
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        return ops.q_sample(x_start, noise, self.sqrt_alphas_cumprod[t], self.sqrt_one_minus_alphas_cumprod[t])
+
     def get_first_stage_encoding(self, encoder_posterior, noise=None):
         """ddpm3d.py:611-618."""
         z = encoder_posterior if isinstance(encoder_posterior, torch.Tensor) else encoder_posterior.sample(noise=noise)

@@ -174,6 +174,42 @@ class DDIMSampler(object):
                 intermediates['pred_x0'].append(pred_x0)
         return img, intermediates
 
+    @torch.no_grad()
+    def decode(self, x_latent, cond, t_start, unconditional_guidance_scale=1.0, unconditional_conditioning=None,
+               use_original_steps=False, callback=None, **kwargs):
+        """ddim.py:282-301: denoise `x_latent` from DDIM index t_start - 1 down to 0 (img2img-style partial runs).
+        Extra kwargs (fs, guidance_rescale, ...) are forwarded to p_sample_ddim."""
+        if use_original_steps:
+            raise NotImplementedError("use_original_steps is not used on the DynamiCrafter inference path")
+        timesteps = self.ddim_timesteps[:t_start]
+        time_range = np.flip(timesteps)
+        total_steps = timesteps.shape[0]
+        x_dec = x_latent
+        for i, step in enumerate(time_range):
+            index = total_steps - i - 1
+            ts = torch.full((x_latent.shape[0],), int(step), device=x_latent.device, dtype=torch.long)
+            self._step_hint = int(step)
+            x_dec, _ = self.p_sample_ddim(x_dec, cond, ts, index=index,
+                                          unconditional_guidance_scale=unconditional_guidance_scale,
+                                          unconditional_conditioning=unconditional_conditioning, **kwargs)
+            self._step_hint = None
+            if callback:
+                callback(i)
+        return x_dec
+
+    @torch.no_grad()
+    def stochastic_encode(self, x0, t, use_original_steps=False, noise=None):
+        """ddim.py:304-319: x_t = sqrt(a_t) x0 + sqrt(1 - a_t) noise with the DDIM tables gathered at index t."""
+        if use_original_steps:
+            sa, s1m = self._sqrt_acp, self._sqrt_1m_acp
+        else:
+            sa = torch.sqrt(torch.as_tensor(self.ddim_alphas, dtype=torch.float32))
+            s1m = torch.as_tensor(self.ddim_sqrt_one_minus_alphas, dtype=torch.float32)
+        if noise is None:
+            noise = torch.randn_like(x0)
+        ti = t.detach().to("cpu", torch.long).reshape(-1)
+        return ops.q_sample(x0, noise, sa[ti], s1m[ti])
+
     # cond / uncond (/ image-only uncond) as one batch -----------------------------------------------
     @staticmethod
     def _cat_cond(*cs):

@@ -216,12 +216,19 @@ _GN_SCRATCH = {}
 _GN_FUSED_MAX_BYTES = int(float(os.environ.get("DCB_GN_FUSED_MB", "4096")) * (1 << 20))
 
 
+_GN_RETIRED = []         # outgrown scratch buffers: kept alive because captured CUDA graphs bake in their addresses
+
+
 def _gn_scratch(dev, G):
-    """(workspace, counters) reused by every GroupNorm launch on this device (stream ordered)."""
+    """(workspace, counters) reused by every GroupNorm launch on this device.  The engine is single-stream (launches
+    and graph replays are stream ordered), so one pair per device is enough.  A buffer that is outgrown is retired,
+    not freed -- a CUDA graph captured earlier keeps replaying against the old addresses."""
     key = (dev.index, )
     ent = _GN_SCRATCH.get(key)
     if ent is None or ent[2] < G:
-        cap = max(G, 64)
+        if ent is not None:
+            _GN_RETIRED.append(ent)
+        cap = max(2 * G, 256)
         nbytes = _lib.lib().dcb_group_norm_workspace_bytes(cap)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         cnt = torch.zeros(2 * cap, dtype=torch.int32, device=dev)     # fused kernel: arrive + leave counters
@@ -596,6 +603,20 @@ def ddim_update(x, e_cond, e_uncond, noise, coeffs, e_uncond_img=None, cfg_img=N
                                      ctypes.byref(coeffs), ptr(stds), ptr(x_prev), ptr(pred), _stream()),
           "dcb_ddim_update")
     return x_prev, pred
+
+
+def q_sample(x0, noise, a, c):
+    """out[b] = a[b] * x0[b] + c[b] * noise[b]; a, c: fp32 [B] (forward diffusion of clean latents)."""
+    require_cuda(x0, noise, a, c)
+    x0 = x0.float().contiguous()
+    noise = noise.float().contiguous()
+    B = x0.shape[0]
+    a = a.to(device=x0.device, dtype=F32).reshape(B).contiguous()
+    c = c.to(device=x0.device, dtype=F32).reshape(B).contiguous()
+    out = torch.empty_like(x0)
+    check(_lib.lib().dcb_q_sample(ptr(x0), ptr(noise), ptr(a), ptr(c), _c_i(B), _c_ll(x0.numel() // B), ptr(out),
+                                  _stream()), "dcb_q_sample")
+    return out
 
 
 def video_to_uint8(video):

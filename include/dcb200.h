@@ -234,6 +234,12 @@ int dcb_ddim_update_multicond(const float* x, const float* e_cond, const float* 
                               float cfg_img, const float* noise, int B, long long per_sample, const dcb_ddim_coeffs* c,
                               float* stds_ws, float* x_prev, float* pred_x0, void* stream);
 
+/* Forward diffusion of clean latents: out[b] = a[b] * x0[b] + c[b] * noise[b] (two rounded products, one rounded sum:
+ * bit-exact with torch's eager expression).  Replaces LatentDiffusion.q_sample (ddpm3d.py:305-308; the sampler's
+ * mask / x0 blend path, ddim.py:174-180) and DDIMSampler.stochastic_encode (ddim.py:304-319).  a, c: [B] device floats. */
+int dcb_q_sample(const float* x0, const float* noise, const float* a, const float* c, int B, long long per_sample,
+                 float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

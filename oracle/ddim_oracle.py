@@ -133,8 +133,9 @@ def p_sample_ddim(tables, dt, apply_model, x, cond, t, index, ucg_scale=1.0, unc
 @torch.no_grad()
 def sample(tables, apply_model, S, shape, cond, uncond=None, ucg_scale=1.0, eta=0.0,
            timestep_spacing="uniform", guidance_rescale=0.0, x_T=None, log_every_t=100,
-           record_steps=False, uncond_img=None, cfg_img=None, **kw):
-    """Returns (samples, intermediates[, per-step list of (x_prev, pred_x0)])."""
+           record_steps=False, uncond_img=None, cfg_img=None, mask=None, x0=None, clean_cond=False, **kw):
+    """Returns (samples, intermediates[, per-step list of (x_prev, pred_x0)]).
+    mask / x0 / clean_cond: the inpainting-style blend of ddim.py:174-180 (q_sample: ddpm3d.py:305-308)."""
     dt = ddim_tables(tables, S, timestep_spacing, eta)
     img = torch.randn(shape) if x_T is None else x_T
     inter = {"x_inter": [img], "pred_x0": [img]}
@@ -144,6 +145,15 @@ def sample(tables, apply_model, S, shape, cond, uncond=None, ucg_scale=1.0, eta=
     for i, step in enumerate(time_range):
         index = total - i - 1
         ts = torch.full((shape[0],), int(step), dtype=torch.long)
+        if mask is not None:
+            assert x0 is not None
+            if clean_cond:
+                img_orig = x0
+            else:
+                nz = torch.randn_like(x0)
+                img_orig = (_gather(tables.sqrt_alphas_cumprod, ts, x0.ndim) * x0 +
+                            _gather(tables.sqrt_one_minus_alphas_cumprod, ts, x0.ndim) * nz)
+            img = img_orig * mask + (1. - mask) * img
         img, pred_x0 = p_sample_ddim(tables, dt, apply_model, img, cond, ts, index,
                                      ucg_scale=ucg_scale, uncond=uncond,
                                      guidance_rescale=guidance_rescale, uncond_img=uncond_img, cfg_img=cfg_img, **kw)

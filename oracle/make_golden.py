@@ -293,6 +293,43 @@ def golden_ddim():
     torch.save(out, os.path.join(OUT, "ddim.pt"))
 
 
+def golden_mask():
+    """Sampler mask / x0 blend path (ddim.py:174-180) with the mock denoiser: clean_cond=True (deterministic) and
+    clean_cond=False (q_sample noise from the CPU generator), eta = 0; plus one stochastic_encode / decode round."""
+    from lvdm.models.samplers.ddim import DDIMSampler
+    DDIMSampler.register_buffer = lambda self, n, a: setattr(self, n, a)
+    out = {}
+    shape = (2, 4, 16, 8, 8)
+    mask = (synth_input("mask", (2, 1, 16, 8, 8), 61) > 0).float()
+    x0 = synth_input("x0", shape, 61)
+    x_T = synth_input("x_T", shape, 61)
+    for tag, yml, S, spacing, gr in (("c2", "inference_512_v1.0.yaml", 50, "uniform_trailing", 0.7),
+                                     ("c1", "inference_256_v1.0.yaml", 10, "uniform", 0.0)):
+        model, _ = build_lvd(TINY_UNET_256 if "256" in yml else TINY_UNET, TINY_VAE, yml, 21)
+        model.apply_model = lambda x, t, c, **kw: torch.tanh(0.3 * x + c)
+        for clean in (True, False):
+            smp = DDIMSampler(model)
+            torch.manual_seed(0)
+            samples, _ = smp.sample(S=S, batch_size=2, shape=shape[1:], conditioning=torch.tensor([0.1]),
+                                    unconditional_conditioning=torch.tensor([-0.1]), unconditional_guidance_scale=7.5,
+                                    eta=0.0, verbose=False, timestep_spacing=spacing, guidance_rescale=gr, x_T=x_T,
+                                    mask=mask, x0=x0, clean_cond=clean)
+            out[f"{tag}_clean{int(clean)}"] = samples.clone()
+            print("mask", tag, clean, float(samples.mean()), float(samples.std()))
+        # stochastic_encode to DDIM index 30 (C1: 6) with given noise, then decode back (ddim.py:282-319)
+        smp = DDIMSampler(model)
+        smp.make_schedule(S, ddim_discretize=spacing, ddim_eta=0.0, verbose=False)
+        t_enc = 30 if S == 50 else 6
+        noise = synth_input("enc_noise", shape, 61)
+        z = smp.stochastic_encode(x0, torch.tensor([t_enc] * 2), noise=noise)
+        dec = smp.decode(z, torch.tensor([0.1]), t_enc, unconditional_guidance_scale=7.5,
+                         unconditional_conditioning=torch.tensor([-0.1]))
+        out[f"{tag}_enc"] = z.clone()
+        out[f"{tag}_dec"] = dec.clone()
+        out[f"{tag}_t_enc"] = t_enc
+    torch.save(out, os.path.join(OUT, "ddim_mask.pt"))
+
+
 TINY_RESAMPLER = dict(dim=256, depth=2, dim_head=64, heads=4, num_queries=4, embedding_dim=192, output_dim=256,
                       ff_mult=4, video_length=4)
 

@@ -162,3 +162,24 @@ def test_end_to_end_oracle(tag):
     from oracle.make_golden import TINY_VAE
     video = vae_oracle.decode_first_stage(vsd, TINY_VAE, g["samples"])
     assert rel_l2(video, g["video"]) < TOL
+
+
+@pytest.mark.parametrize("tag", ["c2", "c1"])
+def test_sampler_mask_x0_path_oracle(tag):
+    """ddim.py:174-180 (mask / x0 blend; clean_cond and q_sample variants) against the reference run with the mock
+    denoiser: the clean_cond run is deterministic, the q_sample run consumes the same CPU generator stream."""
+    g = load_golden("ddim_mask.pt")
+    kw = dict(parameterization="v", rescale_betas_zero_snr=True, use_dynamic_rescale=True, base_scale=0.7) \
+        if tag == "c2" else dict(parameterization="eps")
+    S, spacing, gr = (50, "uniform_trailing", 0.7) if tag == "c2" else (10, "uniform", 0.0)
+    tab = ddim_oracle.DiffusionTables(**kw)
+    shape = (2, 4, 16, 8, 8)
+    mask = (synth_input("mask", (2, 1, 16, 8, 8), 61) > 0).float()
+    x0, x_T = synth_input("x0", shape, 61), synth_input("x_T", shape, 61)
+    fn = lambda x, t, c: torch.tanh(0.3 * x + c)
+    for clean in (True, False):
+        torch.manual_seed(0)
+        y, _ = ddim_oracle.sample(tab, fn, S, shape, torch.tensor([0.1]), uncond=torch.tensor([-0.1]), ucg_scale=7.5,
+                                  eta=0.0, timestep_spacing=spacing, guidance_rescale=gr, x_T=x_T, mask=mask, x0=x0,
+                                  clean_cond=clean)
+        assert torch.equal(y, g[f"{tag}_clean{int(clean)}"]), (tag, clean)
