@@ -595,7 +595,14 @@ extern "C" int dcb_flash_attention(const dcb_attention_args* a, void* stream) {
     static int use_cross = -1;                  // DCB_CROSS_ATTN=0 forces the tiled kernel (A/B testing)
     if (use_cross < 0) { const char* e = getenv("DCB_CROSS_ATTN"); use_cross = (e == nullptr) ? 1 : atoi(e); }
     if (use_cross && a->nseg == 2 && a->nk[0] <= 80 && a->nk[1] <= 16) {
-        // text + image cross-attention: all keys resident in shared memory, warps stream over the queries
+        // text + image cross-attention: tcgen05 kernel with the 96 key slots resident in shared memory (attn_tc.cu)
+        static int use_ctc = -1;                // DCB_CROSS_TC=0 forces the mma.sync resident-key kernel (A/B testing)
+        if (use_ctc < 0) { const char* e = getenv("DCB_CROSS_TC"); use_ctc = (e == nullptr) ? 1 : atoi(e); }
+        if (use_ctc) {
+            const int rc = cross_tc_launch(a, st);
+            if (rc != DCB_ERR_UNSUPPORTED) return rc;
+        }
+        // mma.sync variant: all keys resident in shared memory, warps stream over the queries
         constexpr int NT0 = 10, NT1 = 2;
         constexpr int smem = (2 * (NT0 + NT1) * 8 + kCrossWarps * kCrossStages * 16) * kD * 2;
         static bool cfg = false;
@@ -633,6 +640,15 @@ extern "C" int dcb_temporal_attention(const void* q, const void* k, const void* 
     if (!q || !k || !v || !o || B < 1 || HW < 1 || heads < 1) return set_error(DCB_ERR_INVALID, "temporal_attention: bad argument");
     if (head_dim != kD || L < 1 || L > 16) return set_error(DCB_ERR_UNSUPPORTED, "temporal_attention: head_dim 64 and <= 16 frames only");
     if ((ldq & 7) || (ldk & 7) || (ldv & 7) || (ldo & 7)) return set_error(DCB_ERR_INVALID, "temporal_attention: alignment");
+    {
+        static int use_ttc = -1;                // DCB_TEMPORAL_TC=0 forces the mma.sync kernel (A/B testing)
+        if (use_ttc < 0) { const char* e = getenv("DCB_TEMPORAL_TC"); use_ttc = (e == nullptr) ? 1 : atoi(e); }
+        if (use_ttc) {
+            const int rc = temporal_tc_launch(q, k, v, o, ldq, ldk, ldv, ldo, B, L, HW, heads, softmax_scale,
+                                              static_cast<cudaStream_t>(stream));
+            if (rc != DCB_ERR_UNSUPPORTED) return rc;
+        }
+    }
     TemporalParams p;
     p.q = static_cast<const __nv_bfloat16*>(q); p.k = static_cast<const __nv_bfloat16*>(k);
     p.v = static_cast<const __nv_bfloat16*>(v); p.o = static_cast<__nv_bfloat16*>(o);

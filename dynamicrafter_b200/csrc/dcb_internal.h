@@ -12,6 +12,10 @@ bool pdl_enabled(int cls);                        // programmatic dependent laun
 constexpr int kPdlGemm = 1, kPdlLayerNorm = 2, kPdlGroupNorm = 4, kPdlAttention = 8;
 // tcgen05 flash attention (flash_tc.cu); DCB_ERR_UNSUPPORTED if the arguments do not fit that kernel
 int flash_tc_launch(const dcb_attention_args* a, cudaStream_t stream);
+// tcgen05 text + image cross-attention and temporal attention (attn_tc.cu); DCB_ERR_UNSUPPORTED if the arguments do not fit
+int cross_tc_launch(const dcb_attention_args* a, cudaStream_t stream);
+int temporal_tc_launch(const void* q, const void* k, const void* v, void* o, long long ldq, long long ldk, long long ldv,
+                       long long ldo, int B, int L, int HW, int heads, float softmax_scale, cudaStream_t stream);
 
 // Launch with programmatic stream serialization (the kernel MUST call pdl_wait() before touching global memory).
 template <typename... KArgs, typename... Args>

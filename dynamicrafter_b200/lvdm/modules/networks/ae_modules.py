@@ -2,8 +2,8 @@
 
 Decoder (ae_modules.py:466-578), ResnetBlock (:151-210), AttnBlock (:26-78), Upsample (:111-127) keep the
 reference constructor arguments and ``state_dict`` keys.  The convolutions are the same tcgen05 implicit-GEMM
-kernel as the UNet; the single-head d=C mid-block attention is expressed as GEMMs (scores = q k^T, V^T =
-W_v y^T, out = P V) around a row-softmax kernel -- its N x N scores (N = latent h*w) fit in L2.
+kernel as the UNet; the single-head d=C mid-block attention is a flash-style tcgen05 kernel (dcb_vae_attention: one
+launch for all frames, the N x N scores never reach HBM).
 
 ``Encoder`` is a parameter holder only (checkpoint compatibility); encoding runs once per video and is outside
 the hot path.
@@ -129,25 +129,20 @@ class AttnBlock(PackedModule):
         self.proj_out = torch.nn.Conv2d(in_channels, in_channels, kernel_size=1, stride=1, padding=0)
 
     def _pack(self):
-        return {"wqk": torch.cat([pack_linear(self.q.weight), pack_linear(self.k.weight)], 0).contiguous(),
-                "bqk": torch.cat([_f32(self.q.bias), _f32(self.k.bias)], 0).contiguous(),
-                "wv": pack_linear(self.v.weight), "bv": _f32(self.v.bias),
+        return {"wqkv": torch.cat([pack_linear(self.q.weight), pack_linear(self.k.weight), pack_linear(self.v.weight)],
+                                  0).contiguous(),
+                "bqkv": torch.cat([_f32(self.q.bias), _f32(self.k.bias), _f32(self.v.bias)], 0).contiguous(),
                 "wo": pack_linear(self.proj_out.weight), "bo": _f32(self.proj_out.bias)}
 
     def _fwd(self, h):
+        """GroupNorm -> fused q/k/v 1x1 convs (one GEMM) -> flash attention with d = C over the h*w tokens of every frame
+        (one launch for all frames, scores stay on the SM) -> proj_out + residual (ae_modules.py:53-78)."""
         p = self.packed()
         nf, S, C = h.B * h.T, h.H * h.W, h.C
         y = _gn(self.norm, h, False)                              # bf16 [nf*S, C]
-        qk = ops.linear(y, p["wqk"], bias=p["bqk"])               # bf16 [nf*S, 2C]
-        o = torch.empty((nf * S, C), dtype=torch.bfloat16, device=y.device)
+        qkv = ops.linear(y, p["wqkv"], bias=p["bqkv"])            # bf16 [nf*S, 3C]
         scale = float(int(C) ** (-0.5))                           # ae_modules.py:67
-        for f in range(nf):
-            rows = slice(f * S, (f + 1) * S)
-            scores = ops.linear(qk[rows, :C], qk[rows, C:], f32=True, bf16=False)     # [S, S] = q k^T
-            prob = ops.softmax_rows(scores, scale)                                    # bf16, softmax over keys
-            vt = ops.linear(p["wv"], y[rows])                                         # [C, S] = W_v y^T  (V^T)
-            # rows of P sum to 1, so the value bias is added after P V
-            ops.linear(prob, vt, bias=p["bv"], out=o[rows])
+        o = ops.vae_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], nf, S, C, scale)
         return h.like(ops.linear(o, p["wo"], bias=p["bo"], residual=h.x, f32=True, bf16=False))
 
     def forward(self, x):

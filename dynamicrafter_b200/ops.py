@@ -455,6 +455,18 @@ def temporal_attention(q, k, v, B, L, HW, heads, scale, out=None):
     return out
 
 
+def vae_attention(q, k, v, frames, tokens, C, scale, out=None):
+    """q/k/v: bf16 2-D views [frames*tokens, >= C]; single head of width C (<= 512) per frame -> bf16 [frames*tokens, C]."""
+    require_cuda(q, k, v)
+    assert q.dtype == BF16 and k.dtype == BF16 and v.dtype == BF16
+    if out is None:
+        out = torch.empty((frames * tokens, C), dtype=BF16, device=q.device)
+    check(_lib.lib().dcb_vae_attention(ptr(q), ptr(k), ptr(v), ptr(out), _c_ll(q.stride(0)), _c_ll(k.stride(0)),
+                                       _c_ll(v.stride(0)), _c_ll(out.stride(0)), _c_i(frames), _c_i(tokens), _c_i(C),
+                                       _c_f(scale), _stream()), "dcb_vae_attention")
+    return out
+
+
 def softmax_rows(x, scale):
     require_cuda(x)
     rows, n = x.shape

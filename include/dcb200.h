@@ -167,7 +167,12 @@ int dcb_flash_attention(const dcb_attention_args* args, void* stream);
 int dcb_temporal_attention(const void* q, const void* k, const void* v, void* o, long long ldq,
                            long long ldk, long long ldv, long long ldo, int B, int L, int HW, int heads,
                            int head_dim, float softmax_scale, void* stream);
-/* y = softmax(scale * x) row-wise, fp32 in, bf16 out (VAE AttnBlock, ae_modules.py:66-68). */
+/* Single-head attention with a wide head (d = C <= 512, C % 64 == 0) for every frame in one launch: o = softmax(q k^T *
+ * scale) v over the `tokens` rows of each frame; q/k/v/o are bf16 [frames*tokens, >= C] with row pitches ld*.  Flash
+ * style on tcgen05 / TMEM (no N x N scores in HBM).  Replaces AttnBlock.forward's two bmm + softmax (ae_modules.py:61-74). */
+int dcb_vae_attention(const void* q, const void* k, const void* v, void* o, long long ldq, long long ldk, long long ldv,
+                      long long ldo, int frames, int tokens, int C, float softmax_scale, void* stream);
+/* y = softmax(scale * x) row-wise, fp32 in, bf16 out (materialised-score variant of ae_modules.py:66-68; kept for tests). */
 int dcb_softmax_rows(const float* x, long long rows, int n, long long ldx, float scale, void* y_bf16,
                      long long ldy, void* stream);
 

@@ -213,3 +213,44 @@ def test_video_to_uint8_byte_exact():
     ref = output_oracle.video_to_uint8(x)
     assert got.dtype == torch.uint8 and got.shape == (2, 5, 17, 23, 3)
     assert torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("F_,N,C", [(2, 96, 256), (1, 2560, 512), (3, 300, 512), (2, 129, 128), (1, 640, 384), (2, 40, 64)])
+def test_vae_wide_head_attention(F_, N, C):
+    """dcb_vae_attention: single head of width C per frame (ae_modules.py:61-74), ragged token counts, 1-2 output slices."""
+    from dynamicrafter_b200 import ops
+    qkv = _randn((F_ * N, 3 * C), 44, 0.7).to(torch.bfloat16)
+    scale = C ** -0.5
+    out = ops.vae_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], F_, N, C, scale)
+    f = qkv.float().reshape(F_, N, 3, C).permute(2, 0, 1, 3)
+    ref = _sdpa(f[0], f[1], f[2], scale).reshape(F_ * N, C)
+    assert _rel(out, ref) < 1e-2
+
+
+def test_temporal_attention_large_and_ragged():
+    """tcgen05 temporal kernel: location counts that are not multiples of the 8-location tile, several CTAs' worth."""
+    from dynamicrafter_b200 import ops
+    for B, L, HW, H in [(2, 16, 2560, 5), (1, 16, 643, 2), (2, 9, 50, 3)]:
+        inner = H * 64
+        qkv = _randn((B * L * HW, 3 * inner), 12).to(torch.bfloat16)
+        out = ops.temporal_attention(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], B, L, HW, H, 0.125)
+        f = qkv.float().reshape(B, L, HW, 3, H, 64).permute(3, 0, 2, 4, 1, 5)
+        ref = _sdpa(f[0], f[1], f[2], 0.125).permute(0, 3, 1, 2, 4).reshape(B * L * HW, inner)
+        assert _rel(out, ref) < 1e-2, (B, L, HW, H)
+
+
+def test_cross_attention_bench_shape():
+    """tcgen05 cross kernel at the 512 config's finest level: 32 frames x 5 heads x 2560 queries, 77 + 16 keys."""
+    from dynamicrafter_b200 import ops
+    B, T, H, N, NT, NI = 2, 16, 5, 2560, 77, 16
+    inner, nb = H * 64, B * T
+    q = _randn((nb * N, inner), 9).to(torch.bfloat16)
+    kv_t = _randn((B * NT, 2 * inner), 10).to(torch.bfloat16)
+    kv_i = _randn((nb * NI, 2 * inner), 11).to(torch.bfloat16)
+    out = ops.flash_attention(q, [(kv_t[:, :inner], kv_t[:, inner:], NT, T, 1.0),
+                                  (kv_i[:, :inner], kv_i[:, inner:], NI, 1, 0.8)], nb, H, N, 0.125)
+    qf = q.float().reshape(nb, N, H, 64).permute(0, 2, 1, 3)
+    kt = kv_t.float().reshape(B, NT, 2, H, 64).permute(2, 0, 3, 1, 4).repeat_interleave(T, dim=1)
+    ki = kv_i.float().reshape(nb, NI, 2, H, 64).permute(2, 0, 3, 1, 4)
+    ref = _sdpa(qf, kt[0], kt[1], 0.125) + 0.8 * _sdpa(qf, ki[0], ki[1], 0.125)
+    assert _rel(out, ref.permute(0, 2, 1, 3).reshape(nb * N, inner)) < 1e-2
