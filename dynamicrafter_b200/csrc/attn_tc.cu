@@ -26,8 +26,11 @@ constexpr int kTThreads = 320;
 constexpr int kCrossKeys = 96;               // 80 text slots (77 used) + 16 image slots
 constexpr int kCrossText = 80;
 constexpr int kCrossKVBytes = kCrossKeys * 128;
-constexpr int kCrossSmem = 2 * kCrossKVBytes + 2 * (kTTile + 2 * kTTile) + 256;       // K, V, 2 x (Q, P[2])
-constexpr int kTempSmem = 2 * (3 * kTTile + 2 * kTTile) + 256;                        // 2 x (Q, K, V, P[2])
+// load ring (decoupled from the two compute sets so that several tiles' worth of HBM requests are always in flight)
+constexpr int kCrossStages = 5;              // Q tiles
+constexpr int kTempStages = 4;               // {Q, K, V} tiles
+constexpr int kCrossSmem = 4 * kCrossKVBytes + kCrossStages * kTTile + 2 * 2 * kTTile + 256;   // K/V x2, Q ring, P x2
+constexpr int kTempSmem = kTempStages * 3 * kTTile + 2 * kTTile + 256;                         // {Q,K,V} ring, P x1
 
 struct AttnTcParams {
     int mode_tiles;          // tiles per (batch, head): cross: ceil(nq / 128); temporal: ceil(HW / 8)
@@ -74,25 +77,25 @@ __global__ void __launch_bounds__(kTThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                const __grid_constant__ CUtensorMap tmV1, const __grid_constant__ CUtensorMap tmO, const AttnTcParams p) {
+    constexpr int NS = kTemporal ? kTempStages : kCrossStages;
+    constexpr int kStageBytes = kTemporal ? 3 * kTTile : kTTile;
+    constexpr int NP = kTemporal ? 1 : 2;                    // P buffers (temporal: one, shared by both groups)
     extern __shared__ __align__(1024) uint8_t asm_[];
     // ---- shared memory carve-up
-    uint8_t* sKres = asm_;                                   // cross: resident K (96 x 128 B)
-    uint8_t* sVres = asm_ + kCrossKVBytes;                   // cross: resident V
-    uint8_t* set_base = kTemporal ? asm_ : asm_ + 2 * kCrossKVBytes;
-    constexpr int kSetBytes = kTemporal ? 5 * kTTile : 3 * kTTile;
-    auto sQ = [&](int s) { return set_base + s * kSetBytes; };
-    auto sK = [&](int s) { return kTemporal ? set_base + s * kSetBytes + kTTile : sKres; };
-    auto sV = [&](int s) { return kTemporal ? set_base + s * kSetBytes + 2 * kTTile : sVres; };
-    auto sP = [&](int s) { return set_base + s * kSetBytes + (kTemporal ? 3 : 1) * kTTile; };
-    uint64_t* bars = reinterpret_cast<uint64_t*>(set_base + 2 * kSetBytes);
-    uint64_t* q_full = bars;            // [2]
-    uint64_t* set_free = bars + 2;      // [2]
-    uint64_t* s_full = bars + 4;        // [2]
-    uint64_t* p_full = bars + 6;        // [2]
-    uint64_t* o_full = bars + 8;        // [2]
-    uint64_t* s_free = bars + 10;       // [2]
-    uint64_t* kv_full = bars + 12;      // cross
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint8_t* kv_base = asm_;                                 // cross: 2 x {K, V} of 96 x 128 B (double buffered over pairs)
+    uint8_t* ring = kTemporal ? asm_ : asm_ + 4 * kCrossKVBytes;
+    uint8_t* p_base = ring + NS * kStageBytes;
+    auto sQ = [&](int st) { return ring + st * kStageBytes; };
+    auto sP = [&](int s) { return p_base + (NP == 2 ? s : 0) * 2 * kTTile; };
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_base + NP * 2 * kTTile);
+    uint64_t* q_full = bars;                  // [NS]
+    uint64_t* stage_free = bars + NS;         // [NS]
+    uint64_t* s_full = bars + 2 * NS;         // [2]
+    uint64_t* p_full = bars + 2 * NS + 2;     // [2]
+    uint64_t* o_full = bars + 2 * NS + 4;     // [2]
+    uint64_t* s_free = bars + 2 * NS + 6;     // [2]
+    uint64_t* kv_full = bars + 2 * NS + 8;    // [2] cross
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // contiguous tile range of this CTA
@@ -100,16 +103,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int t_begin = static_cast<int>(T * blockIdx.x / gridDim.x);
     const int t_end = static_cast<int>(T * (blockIdx.x + 1) / gridDim.x);
     const int ntiles = t_end - t_begin;
+    // cross: sequence number (within this CTA) of the (batch, head) pair a tile belongs to
+    const int pair0 = t_begin / p.mode_tiles;
+    auto pair_seq = [&](int i) { return (t_begin + i) / p.mode_tiles - pair0; };
 
     if ((smem_u32(asm_) & 1023) != 0) __trap();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK0); tma_prefetch_desc(&tmV0); tma_prefetch_desc(&tmO);
         if (!kTemporal) { tma_prefetch_desc(&tmK1); tma_prefetch_desc(&tmV1); }
+        for (int i = 0; i < NS; ++i) { mbar_init(&q_full[i], 1); mbar_init(&stage_free[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&q_full[i], 1); mbar_init(&set_free[i], 1); mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 4);
+            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 4);
+            mbar_init(&kv_full[i], 1);
         }
-        mbar_init(kv_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<256>(tmem_slot);
@@ -130,39 +136,46 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        int cur_pair = -1;
+        int cur_seq = -1;
+        int first_of_prev = 0;                     // first tile (CTA-local index) of the previous pair
         for (int i = 0; i < ntiles; ++i) {
-            const int s = i & 1;
+            const int st = i % NS, u = i / NS;
             int b, h, j;
             decode(t_begin + i, b, h, j);
-            mbar_wait(&set_free[s], ((i >> 1) & 1) ^ 1);
+            mbar_wait(&stage_free[st], (u & 1) ^ 1);
             if (!kTemporal) {
-                const int pair = (t_begin + i) / p.mode_tiles;
-                if (pair != cur_pair) {
-                    // every MMA that reads the old K / V has retired once both sets were handed back
-                    if (i >= 1) mbar_wait(&set_free[s ^ 1], (((i - 1) >> 1) & 1));
-                    cur_pair = pair;
+                const int m = pair_seq(i);
+                if (m != cur_seq) {
+                    // K / V buffer m & 1 was last read by the tiles of pair m - 2, the last of which is tile
+                    // first_of_prev - 1: it and its predecessor (the other softmax group) must have finished
+                    if (m >= 2) {
+                        for (int e = first_of_prev - 1; e >= first_of_prev - 2 && e >= 0; --e)
+                            if (e + NS > i) mbar_wait(&stage_free[e % NS], (e / NS) & 1);   // (older: seen when its stage was reloaded)
+                    }
+                    first_of_prev = i;
+                    cur_seq = m;
+                    uint8_t* kb = kv_base + (m & 1) * 2 * kCrossKVBytes;
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(kv_full, 2 * kCrossKVBytes);
-                        tma_ld3(sKres, &tmK0, kv_full, h * 64, 0, b / p.kv_div0);
-                        tma_ld3(sVres, &tmV0, kv_full, h * 64, 0, b / p.kv_div0);
-                        tma_ld3(sKres + kCrossText * 128, &tmK1, kv_full, h * 64, 0, b / p.kv_div1);
-                        tma_ld3(sVres + kCrossText * 128, &tmV1, kv_full, h * 64, 0, b / p.kv_div1);
+                        mbar_arrive_expect_tx(&kv_full[m & 1], 2 * kCrossKVBytes);
+                        tma_ld3(kb, &tmK0, &kv_full[m & 1], h * 64, 0, b / p.kv_div0);
+                        tma_ld3(kb + kCrossKVBytes, &tmV0, &kv_full[m & 1], h * 64, 0, b / p.kv_div0);
+                        tma_ld3(kb + kCrossText * 128, &tmK1, &kv_full[m & 1], h * 64, 0, b / p.kv_div1);
+                        tma_ld3(kb + kCrossKVBytes + kCrossText * 128, &tmV1, &kv_full[m & 1], h * 64, 0, b / p.kv_div1);
                     }
                     __syncwarp();
                 }
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&q_full[s], kTTile);
-                    tma_ld3(sQ(s), &tmQ, &q_full[s], h * 64, j * 128, b);
+                    mbar_arrive_expect_tx(&q_full[st], kTTile);
+                    tma_ld3(sQ(st), &tmQ, &q_full[st], h * 64, j * 128, b);
                 }
             } else {
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&q_full[s], 3 * kTTile);
+                    mbar_arrive_expect_tx(&q_full[st], 3 * kTTile);
 #pragma unroll
                     for (int loc = 0; loc < 8; ++loc) {
-                        tma_load_4d(sQ(s) + loc * 2048, &tmQ, &q_full[s], h * 64, j * 8 + loc, 0, b);
-                        tma_load_4d(sK(s) + loc * 2048, &tmK0, &q_full[s], h * 64, j * 8 + loc, 0, b);
-                        tma_load_4d(sV(s) + loc * 2048, &tmV0, &q_full[s], h * 64, j * 8 + loc, 0, b);
+                        tma_load_4d(sQ(st) + loc * 2048, &tmQ, &q_full[st], h * 64, j * 8 + loc, 0, b);
+                        tma_load_4d(sQ(st) + kTTile + loc * 2048, &tmK0, &q_full[st], h * 64, j * 8 + loc, 0, b);
+                        tma_load_4d(sQ(st) + 2 * kTTile + loc * 2048, &tmV0, &q_full[st], h * 64, j * 8 + loc, 0, b);
                     }
                 }
             }
@@ -173,14 +186,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         constexpr int kSN = kTemporal ? 128 : kCrossKeys;
         constexpr uint32_t kIdescS = make_idesc_bf16(128, kSN);
         constexpr uint32_t kIdescPV = make_idesc_bf16(128, 64) | (1u << 16);       // B (= V) is MN-major
-        int cur_pair = -1;
-        uint32_t kv_phase = 0;
+        int cur_seq = -1;
+        auto k_of = [&](int i) -> uint32_t {        // smem address of the K tile of CTA-local tile i (V follows)
+            if (kTemporal) return smem_u32(sQ(i % NS) + kTTile);
+            return smem_u32(kv_base + (pair_seq(i) & 1) * 2 * kCrossKVBytes);
+        };
         auto issue_PV = [&](int j) {
             const int s = j & 1;
             mbar_wait(&p_full[s], (j >> 1) & 1);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t aP = smem_u32(sP(s)), aV = smem_u32(sV(s));
+                const uint32_t aP = smem_u32(sP(s)), aV = k_of(j) + (kTemporal ? kTTile : kCrossKVBytes);
 #pragma unroll
                 for (int kk = 0; kk < kSN / 16; ++kk) {
                     const uint64_t ad = make_sw128_kmajor_desc(aP + (kk >> 2) * kTTile) + 2 * (kk & 3);
@@ -192,53 +208,51 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             __syncwarp();
         };
         for (int i = 0; i < ntiles; ++i) {
-            const int s = i & 1;
-            bool new_pair = false;
+            const int s = i & 1, st = i % NS;
             if (!kTemporal) {
-                const int pair = (t_begin + i) / p.mode_tiles;
-                new_pair = pair != cur_pair;
-                cur_pair = pair;
+                const int m = pair_seq(i);
+                if (m != cur_seq) {
+                    cur_seq = m;
+                    mbar_wait(&kv_full[m & 1], (m >> 1) & 1);
+                }
             }
-            if (new_pair) {
-                // P_{i-1} V still reads the OLD V: issue it before waiting for the new K / V (the producer reloads them
-                // only after both sets were handed back, i.e. after that product has retired)
-                if (i >= 1) issue_PV(i - 1);
-                mbar_wait(kv_full, kv_phase);
-                kv_phase ^= 1;
-            }
-            mbar_wait(&q_full[s], (i >> 1) & 1);
+            mbar_wait(&q_full[st], (i / NS) & 1);
             mbar_wait(&s_free[s], ((i >> 1) & 1) ^ 1);            // softmax group done with O_{i-2} in this TMEM set
             tc_fence_after();
             if (elect_one()) {
-                const uint64_t ad = make_sw128_kmajor_desc(smem_u32(sQ(s)));
-                const uint64_t bd = make_sw128_kmajor_desc(smem_u32(sK(s)));
+                const uint64_t ad = make_sw128_kmajor_desc(smem_u32(sQ(st)));
+                const uint64_t bd = make_sw128_kmajor_desc(k_of(i));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + s * 128, ad + 2 * k, bd + 2 * k, kIdescS, k != 0);
                 umma_commit(&s_full[s]);
             }
             __syncwarp();
-            if (!new_pair && i >= 1) issue_PV(i - 1);             // S_i is in flight while the softmax of tile i-1 finishes
+            if (i >= 1) issue_PV(i - 1);                          // S_i is in flight while the softmax of tile i-1 finishes
         }
         if (ntiles >= 1) issue_PV(ntiles - 1);
     } else {
         // ------------------------------------------------------------------ softmax groups
         const int q = warp & 3;                         // TMEM lane quarter
-        const int g = (warp - 2) >> 2;                  // group = set
+        const int g = (warp - 2) >> 2;                  // group = TMEM set = tile parity
         const int r = q * 32 + lane;                    // tile row of this thread
         const bool leader = (warp - 2) == g * 4 && lane == 0;
         const uint32_t t_row = tmem_base + g * 128 + (static_cast<uint32_t>(q * 32) << 16);
         const float sl2 = p.scale_log2;
         uint8_t* const prow0 = sP(g) + r * 128;          // row r of P tile 0 (keys 0..63); tile 1 at + kTTile
         if (kTemporal) {
-            // zero my P row once: only the diagonal block is rewritten per tile
+            // zero the (shared) P tile once: only the diagonal blocks are rewritten per tile
+            if (g == 0) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                *reinterpret_cast<uint4*>(prow0 + (c << 4)) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(prow0 + kTTile + (c << 4)) = make_uint4(0, 0, 0, 0);
+                for (int c = 0; c < 8; ++c) {
+                    *reinterpret_cast<uint4*>(prow0 + (c << 4)) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(prow0 + kTTile + (c << 4)) = make_uint4(0, 0, 0, 0);
+                }
             }
+            named_bar_sync(3, 256);
         }
         for (int i = g, it = 0; i < ntiles; i += 2, ++it) {
             const uint32_t ph = it & 1;
+            const int st = i % NS;
             int b, h, j;
             decode(t_begin + i, b, h, j);
             mbar_wait(&s_full[g], ph);
@@ -307,6 +321,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     l += sv[k];
                 }
                 const float inv = 1.f / l;
+                // the single P tile is shared by both groups: P_{i-1} V_{i-1} (the other group's tile) must have retired
+                if (i >= 1) mbar_wait(&o_full[g ^ 1], ((i - 1) >> 1) & 1);
                 const int c0 = 2 * (r >> 4);                 // first 16-byte chunk of my diagonal block (keys 16 * (r / 16) ..)
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
@@ -323,7 +339,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[g]);
-            // ---- O = P V -> bf16 -> staging (the Q tile of this set: S has consumed it) -> TMA store
+            // ---- O = P V -> bf16 -> staging (the Q tile of this stage: S has consumed it) -> TMA store
             mbar_wait(&o_full[g], ph);
             tc_fence_after();
             uint32_t o0[32], o1[32];
@@ -333,7 +349,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_free[g]);
-            uint8_t* orow = sQ(g) + r * 128;
+            uint8_t* orow = sQ(st) + r * 128;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const uint32_t* src = (c < 4) ? (o0 + 8 * c) : (o1 + 8 * (c - 4));
@@ -348,14 +364,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             named_bar_sync(1 + g, 128);
             if (leader) {
                 if (!kTemporal) {
-                    tma_st3(&tmO, sQ(g), h * 64, j * 128, b);
+                    tma_st3(&tmO, sQ(st), h * 64, j * 128, b);
                 } else {
 #pragma unroll
-                    for (int loc = 0; loc < 8; ++loc) tma_store_4d(&tmO, sQ(g) + loc * 2048, h * 64, j * 8 + loc, 0, b);
+                    for (int loc = 0; loc < 8; ++loc) tma_store_4d(&tmO, sQ(st) + loc * 2048, h * 64, j * 8 + loc, 0, b);
                 }
                 tma_store_commit();
                 tma_store_wait_read<0>();
-                mbar_arrive(&set_free[g]);                 // Q (+K, V) tiles and the staging are free again
+                mbar_arrive(&stage_free[st]);              // the stage (Q, K, V tiles + staging) is free again
             }
         }
         if (leader) tma_store_wait_all<0>();

@@ -619,7 +619,7 @@ def ddim_update(x, e_cond, e_uncond, noise, coeffs, e_uncond_img=None, cfg_img=N
 
 def q_sample(x0, noise, a, c):
     """out[b] = a[b] * x0[b] + c[b] * noise[b]; a, c: fp32 [B] (forward diffusion of clean latents)."""
-    require_cuda(x0, noise, a, c)
+    require_cuda(x0, noise)                 # a, c: tiny per-sample coefficient vectors, host or device
     x0 = x0.float().contiguous()
     noise = noise.float().contiguous()
     B = x0.shape[0]

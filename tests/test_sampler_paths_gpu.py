@@ -19,7 +19,9 @@ def _setup(tag):
     tab = ddim_oracle.DiffusionTables(**c["kw"])
     dev = torch.device("cuda")
     model = _MockDiffusion(tab, lambda x, t, cnd, **kw: torch.tanh(0.3 * x + cnd), dev)
-    return DDIMSampler(model), model, tab, c, gr, dev
+    smp = DDIMSampler(model)
+    smp.batch_cfg = False          # the mock conditioning is a broadcast scalar, not a per-sample tensor
+    return smp, model, tab, c, gr, dev
 
 
 @pytest.mark.parametrize("tag", ["c2", "c1"])
