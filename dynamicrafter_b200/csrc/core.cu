@@ -28,10 +28,11 @@ int num_sms() {
 }
 
 // DCB_PDL: bit mask of the kernel classes launched with programmatic stream serialization
-// (1 tap_gemm, 2 layer norm, 4 group norm, 8 attention); default set by measurement, see DESIGN.md.
+// (1 tap_gemm, 2 layer norm, 4 cooperative group norm, 8 attention, 16 group-norm finalize + streaming apply); default
+// set by measurement, see DESIGN.md.
 bool pdl_enabled(int cls) {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("DCB_PDL"); v = (e == nullptr) ? 1 : atoi(e); }
+    if (v < 0) { const char* e = getenv("DCB_PDL"); v = (e == nullptr) ? 17 : atoi(e); }
     return (v & cls) != 0;
 }
 

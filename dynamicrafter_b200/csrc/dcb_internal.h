@@ -9,7 +9,7 @@ int set_error(int code, const char* fmt, ...);   // records a thread-local messa
 int num_sms();                                    // SM count of the current device (cached)
 int check_launch(const char* what);               // cudaGetLastError -> status
 bool pdl_enabled(int cls);                        // programmatic dependent launch per kernel class (DCB_PDL bit mask)
-constexpr int kPdlGemm = 1, kPdlLayerNorm = 2, kPdlGroupNorm = 4, kPdlAttention = 8;
+constexpr int kPdlGemm = 1, kPdlLayerNorm = 2, kPdlGroupNorm = 4, kPdlAttention = 8, kPdlGnStream = 16;
 // tcgen05 flash attention (flash_tc.cu); DCB_ERR_UNSUPPORTED if the arguments do not fit that kernel
 int flash_tc_launch(const dcb_attention_args* a, cudaStream_t stream);
 // tcgen05 text + image cross-attention and temporal attention (attn_tc.cu); DCB_ERR_UNSUPPORTED if the arguments do not fit

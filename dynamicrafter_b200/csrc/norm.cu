@@ -668,6 +668,8 @@ gn_finalize_kernel(const float* __restrict__ colsum, int ld, int rows_per_instan
     __shared__ double red[2][256];
     const int g = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
     const int cg = C / kGroups;
+    pdl_launch_dependents();
+    pdl_wait();                                          // the producer GEMM's partial sums are complete and visible
     const float2* base = reinterpret_cast<const float2*>(colsum) + static_cast<size_t>(n) * rows_per_instance * ld + g * cg;
     // thread (rsub, c): fixed column c of the group, rows rsub, rsub + R, ... with 8 independent loads in flight
     const int tpr = cg <= 256 ? cg : 256;                 // threads along the columns of the group
@@ -708,8 +710,8 @@ extern "C" int dcb_group_norm_finalize(const float* colsum, int colsum_ld, int r
                                        float eps, float* stats, void* stream) {
     if (colsum == nullptr || stats == nullptr || rows_per_instance < 1 || C % kGroups != 0 || G < 1 || colsum_ld < C || count <= 0)
         return set_error(DCB_ERR_INVALID, "group_norm_finalize: bad argument");
-    gn_finalize_kernel<<<dim3(kGroups, G), 256, 0, static_cast<cudaStream_t>(stream)>>>(colsum, colsum_ld, rows_per_instance, C,
-                                                                                      count, eps, stats);
+    launch_pdl(kPdlGnStream, gn_finalize_kernel, dim3(kGroups, G), dim3(256), 0, static_cast<cudaStream_t>(stream), colsum,
+               colsum_ld, rows_per_instance, C, count, eps, stats);
     return check_launch("group_norm_finalize");
 }
 
@@ -775,6 +777,85 @@ extern "C" int dcb_group_norm_apply_bf16(const void* x, int C, int G, int S, con
         static_cast<const __nv_bfloat16*>(x), nullptr, C, 0, S, rpc, stats, gamma, beta, silu_act,
         static_cast<__nv_bfloat16*>(y_bf16), nullptr);
     return check_launch("group_norm_apply_bf16");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streaming apply for statistics that already exist (emitted by the producer GEMM's epilogue and finalised by
+// gn_finalize_kernel): y = silu?(x * A[c] + B[c]), ONE pass over x (4 or 2 bytes in, 2 bytes out per element), no grid
+// barrier, no cooperative launch; launched with programmatic stream serialization so that its prologue overlaps the
+// finalize kernel.  grid = (chunks, G); a thread owns an 8-channel column and walks down the rows of its chunk.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_stream_apply_kernel(const T* __restrict__ x, int C, int S, int rows_per_chunk, const float* __restrict__ stats,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
+                       __nv_bfloat16* __restrict__ y) {
+    extern __shared__ float s_ab[];          // A[C] | B[C]
+    const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    const int cg = C / kGroups;
+    pdl_launch_dependents();
+    pdl_wait();
+    for (int c = tid; c < C; c += 256) {
+        const int g = c / cg;
+        const float mean = __ldcg(stats + (static_cast<size_t>(n) * kGroups + g) * 2);
+        const float rstd = __ldcg(stats + (static_cast<size_t>(n) * kGroups + g) * 2 + 1);
+        const float a = rstd * gamma[c];
+        s_ab[c] = a;
+        s_ab[C + c] = beta[c] - mean * a;
+    }
+    __syncthreads();
+    const int r0 = chunk * rows_per_chunk;
+    const int nrows = min(S, r0 + rows_per_chunk) - r0;
+    const int O = C >> 3;
+    constexpr int U = 4;
+    for (int o0 = 0; o0 < O; o0 += 256) {
+        const int ow = min(256, O - o0);
+        const int rpp = 256 / ow;
+        const int my_r = tid / ow, my_o = o0 + tid - my_r * ow;
+        if (my_r >= rpp) continue;
+        const int c0 = my_o * 8;
+        float am[8], bm[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { am[e] = s_ab[c0 + e]; bm[e] = s_ab[C + c0 + e]; }
+        const size_t row0 = static_cast<size_t>(n) * S + r0 + my_r;
+        const T* src = x + row0 * C + c0;
+        const size_t step = static_cast<size_t>(rpp) * C;
+        __nv_bfloat16* dst = y + row0 * C + c0;
+        for (int r = my_r; r < nrows; r += rpp * U) {
+            float v[U][8];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (r + u * rpp < nrows) ld8(src + u * step, v[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (r + u * rpp < nrows) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float t = fmaf(v[u][e], am[e], bm[e]);
+                        v[u][e] = do_silu ? silu_fast(t) : t;
+                    }
+                    store8(dst + u * step, v[u]);
+                }
+            }
+            src += U * step;
+            dst += U * step;
+        }
+    }
+}
+
+template <typename T>
+static int launch_gn_stream_apply(const T* x, int C, int G, int S, const float* stats, const float* gamma, const float* beta,
+                                  int silu_act, void* y, cudaStream_t stream) {
+    // ~4 resident blocks' worth of chunks per SM, at least 4 rows each
+    int nch = (4 * num_sms() + G - 1) / G;
+    int rpc = (S + nch - 1) / nch;
+    const int min_rows = (8192 + C - 1) / C > 4 ? (8192 + C - 1) / C : 4;      // >= ~32 KB of fp32 input per block
+    if (rpc < min_rows) rpc = min_rows;
+    nch = (S + rpc - 1) / rpc;
+    const size_t smem = static_cast<size_t>(C) * 2 * sizeof(float);
+    launch_pdl(kPdlGnStream, gn_stream_apply_kernel<T>, dim3(nch, G), dim3(256), smem, stream, x, C, S, rpc, stats, gamma, beta,
+               silu_act, static_cast<__nv_bfloat16*>(y));
+    return check_launch("group_norm_stream_apply");
 }
 
 template <typename T, typename TOut = __nv_bfloat16>
@@ -865,6 +946,19 @@ extern "C" int dcb_group_norm_fused_bf16(const void* x, int C, int G, int S, flo
         return set_error(DCB_ERR_INVALID, "group_norm_fused_bf16: C=%d G=%d S=%d", C, G, S);
     return launch_gn_fused<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), nullptr, C, 0, G, S, eps, gamma, beta,
                                           silu_act, y_bf16, nullptr, workspace, counters, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dcb_group_norm_stream_apply(const void* x, int x_is_bf16, int C, int G, int S, const float* stats,
+                                           const float* gamma, const float* beta, int silu_act, void* y_bf16, void* stream) {
+    if (x == nullptr || y_bf16 == nullptr || stats == nullptr || gamma == nullptr || beta == nullptr)
+        return set_error(DCB_ERR_INVALID, "group_norm_stream_apply: null argument");
+    if (C % kGroups != 0 || (C & 7) || G < 1 || S < 1 || C > kMaxC || G > 65535)
+        return set_error(DCB_ERR_INVALID, "group_norm_stream_apply: C=%d G=%d S=%d", C, G, S);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (x_is_bf16)
+        return launch_gn_stream_apply<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), C, G, S, stats, gamma, beta, silu_act,
+                                                     y_bf16, s);
+    return launch_gn_stream_apply<float>(static_cast<const float*>(x), C, G, S, stats, gamma, beta, silu_act, y_bf16, s);
 }
 
 extern "C" int dcb_layer_norm(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,

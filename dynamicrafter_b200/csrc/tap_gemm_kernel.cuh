@@ -109,55 +109,55 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaxf(x, 0.f) - a * (e * poly);
 }
 
-// One transposing-butterfly step over lanes (l, l ^ m): every lane keeps one half of its N columns and receives the
-// partner's partial sums for that half, so after log2(span) steps each column total sits in exactly one lane (pair).
-template <int N>
-__device__ __forceinline__ void colsum_step(float (&sx)[16], float (&sq)[16], int m, int lane) {
-    const bool up = (lane & m) != 0;
+// Fused GroupNorm statistics: column sums / sums of squares of one staged epilogue chunk (128 rows x 64 bytes in the
+// SWIZZLE_64B slot, fp32 x16 or bf16 x32 columns) over the 32 rows of the calling warp, read back from shared memory
+// AFTER the group barrier (no shuffles on the accumulator path: 16 conflict-free 4-byte loads per lane).  Half-warp
+// h takes rows 2i + h, lane w the 4-byte word w of the row; the halves are folded with one shuffle per value.
+// Rows that share a GroupNorm slice: lw = 32 (whole warp), 16 or 8 consecutive rows -> 1, 2 or 4 partial rows, written
+// as (sum, sumsq) float2 per column at dst + seg * seg_stride.  Deterministic: fixed order, one writer per partial.
+template <bool kF32, int kSeg>
+__device__ __forceinline__ void colsum_from_slot(const uint8_t* slot, int q, int lane, float* __restrict__ dst_seg0,
+                                                 long long seg_stride, int col0, int n_out, const bool* seg_ok) {
+    constexpr int NSEG = 32 / kSeg;                   // partial rows produced by this warp
+    constexpr int IPS = 16 / NSEG;                    // loop iterations (row pairs) per segment
+    const int h = lane >> 4, w = lane & 15;
+    const uint8_t* base = slot + (q * 32 + h) * 64 + ((w & 3) << 2);
+    float sx[NSEG][2], sq[NSEG][2];
 #pragma unroll
-    for (int i = 0; i < N / 2; ++i) {
-        const float send_x = up ? sx[i] : sx[i + N / 2], keep_x = up ? sx[i + N / 2] : sx[i];
-        const float send_q = up ? sq[i] : sq[i + N / 2], keep_q = up ? sq[i + N / 2] : sq[i];
-        sx[i] = keep_x + __shfl_xor_sync(0xffffffffu, send_x, m);
-        sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, m);
+    for (int sg = 0; sg < NSEG; ++sg) { sx[sg][0] = sx[sg][1] = sq[sg][0] = sq[sg][1] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        // row q*32 + 2i + h: SWIZZLE_64B chunk index ^= (row / 2) % 4 = i % 4
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(base + i * 128 + ((((w >> 2) ^ (i & 3))) << 4));
+        constexpr int dummy = 0; (void)dummy;
+        const int sg = i / IPS;
+        if constexpr (kF32) {
+            const float v = __uint_as_float(u);
+            sx[sg][0] += v;
+            sq[sg][0] = fmaf(v, v, sq[sg][0]);
+        } else {
+            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+            sx[sg][0] += v.x; sx[sg][1] += v.y;
+            sq[sg][0] = fmaf(v.x, v.x, sq[sg][0]); sq[sg][1] = fmaf(v.y, v.y, sq[sg][1]);
+        }
     }
-}
-
-// Column sums / sums of squares of 16 output columns over the lw (8, 16 or 32) consecutive tile rows that share a
-// GroupNorm slice, reduced in registers (32 + 32 shuffles at most) and written as float2 partials:
-//   dst[(row_index) * ld + col] where the caller supplies the partial row of this warp's first segment.
-// Deterministic: fixed reduction tree, one writer per partial.
-__device__ __forceinline__ void colsum_reduce_store(float (&sx)[16], float (&sq)[16], int lw, int lane,
-                                                    float* __restrict__ dst_seg0, long long seg_stride, int col0,
-                                                    int n_out, bool seg_ok_all, const bool* seg_ok) {
-    (void)seg_ok_all;
-    int m = lw >> 1;
-    colsum_step<16>(sx, sq, m, lane); m >>= 1;
-    if (m) { colsum_step<8>(sx, sq, m, lane); m >>= 1; }
-    int ncol = (lw == 8) ? 2 : 1;                    // columns left per lane after the halving steps
-    if (lw >= 16) {
-        colsum_step<4>(sx, sq, m, lane); m >>= 1;
-        if (lw == 32) { colsum_step<2>(sx, sq, m, lane); m >>= 1; }
-    } else {
-        colsum_step<4>(sx, sq, m, lane);              // lw == 8: masks 4, 2, 1 -> 2 columns per lane
+    constexpr int NV = kF32 ? 1 : 2;
+#pragma unroll
+    for (int sg = 0; sg < NSEG; ++sg)
+#pragma unroll
+        for (int e = 0; e < NV; ++e) {
+            sx[sg][e] += __shfl_xor_sync(0xffffffffu, sx[sg][e], 16);
+            sq[sg][e] += __shfl_xor_sync(0xffffffffu, sq[sg][e], 16);
+        }
+    if (h != 0) return;
+    const int col = col0 + w * NV;
+#pragma unroll
+    for (int sg = 0; sg < NSEG; ++sg) {
+        if (!seg_ok[sg]) continue;
+        float* d = dst_seg0 + sg * seg_stride + 2 * col;
+        if (col < n_out) *reinterpret_cast<float2*>(d) = make_float2(sx[sg][0], sq[sg][0]);
+        if (NV == 2 && col + 1 < n_out) *reinterpret_cast<float2*>(d + 2) = make_float2(sx[sg][1], sq[sg][1]);
     }
-    if (lw == 32) {                                   // last pair of lanes: plain sum, even lane writes
-        sx[0] += __shfl_xor_sync(0xffffffffu, sx[0], 1);
-        sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
-    } else if (lw == 16) {
-        colsum_step<2>(sx, sq, 1, lane);
-    }
-    // which columns / segment this lane ended up with
-    int col, seg;
-    bool writer = true;
-    if (lw == 32) { col = lane >> 1; seg = 0; writer = (lane & 1) == 0; }
-    else if (lw == 16) { col = ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1); seg = lane >> 4; }
-    else { col = ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2; seg = lane >> 3; }
-    if (!writer || !seg_ok[seg]) return;
-    float* d = dst_seg0 + seg * seg_stride;
-    for (int c = 0; c < ncol; ++c)
-        if (col0 + col + c < n_out)
-            *reinterpret_cast<float2*>(d + 2 * (col0 + col + c)) = make_float2(sx[c], sq[c]);
 }
 
 template <int BN, bool kF32, bool k2, bool kCS>
@@ -479,15 +479,12 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     }
                     if constexpr (kCS) {
-                        // o[] is final: fold it into the per-slice column sums the consumer GroupNorm will finalise
-                        float sx[16], sq[16];
+                        // rows outside the tensor are clipped by the TMA store; zero them so that the column sums read
+                        // back from the slot only see real rows
+                        if (!row_ok) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float t = row_ok ? o[j] : 0.f;
-                            sx[j] = t;
-                            sq[j] = t * t;
+                            for (int j = 0; j < 16; ++j) o[j] = 0.f;
                         }
-                        colsum_reduce_store(sx, sq, p.seg_lw, lane, cs_dst, cs_stride, cb, p.N_out, true, cs_seg_ok);
                     }
                     if constexpr (kF32) {
 #pragma unroll
@@ -517,6 +514,14 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tma_store_4d(&tmOut, slot, col0, o1, o2, o3);
                     tma_store_commit();
                     DCB_TR(2 + grp, 12 + grp, cnt);
+                }
+                if constexpr (kCS) {
+                    // the slot now holds the final values of all 128 rows: fold this warp's 32 rows per column
+                    if (p.seg_lw == 32) colsum_from_slot<kF32, 32>(slot, q, lane, cs_dst, cs_stride, col0, p.N_out, cs_seg_ok);
+                    else if (p.seg_lw == 16) colsum_from_slot<kF32, 16>(slot, q, lane, cs_dst, cs_stride, col0, p.N_out, cs_seg_ok);
+                    else colsum_from_slot<kF32, 8>(slot, q, lane, cs_dst, cs_stride, col0, p.N_out, cs_seg_ok);
+                    // the leader's next residual prefetch (TMA write into a slot) must not overtake these reads
+                    if (tma_res) named_bar_sync(bar_id, 128);
                 }
             }
             if (!acc_ready) {                                            // group without chunks still tracks the ring

@@ -19,10 +19,12 @@ _LOWP = set(_os.environ.get("DCB_BF16_INTERNAL", "tconv,res").split(","))
 BF16_TCONV = "tconv" in _LOWP or "all" in _LOWP
 BF16_RES = "res" in _LOWP or "all" in _LOWP
 BF16_VAE = "vae" in _LOWP or "all" in _LOWP
-# Fused GroupNorm statistics (conv / temporal-conv epilogues emit per-column sums, a tiny finalize kernel replaces the
-# statistics pass).  Measured on B200 at the 512 config: GroupNorm -0.9 ms but GEMM epilogues +1.3 ms per step, so it
-# is OFF by default (DCB_FUSED_GN_STATS=1 enables it); see DESIGN.md.
-FUSED_GN_STATS = _os.environ.get("DCB_FUSED_GN_STATS", "0") == "1"
+# Producer-fused GroupNorm statistics: every GEMM / conv whose output feeds a GroupNorm folds per-column (sum, sumsq)
+# partials in its epilogue (read back from the staged output tile in shared memory); the consumer is a tiny finalize
+# kernel + ONE streaming apply pass (no statistics pass over the tensor, no cooperative launch / grid barrier).
+# DCB_FUSED_GN_STATS=0 restores the self-contained cooperative GroupNorm everywhere (A/B testing); it is still used
+# for skip-concat inputs (two sources), the 1x1-skip ResBlocks (raw copy wanted) and tiles the epilogue cannot segment.
+FUSED_GN_STATS = _os.environ.get("DCB_FUSED_GN_STATS", "1") == "1"
 # frame-sharded mode: also capture the NCCL calls of a forward in the CUDA graph.  Works (94.4 vs 97.7 ms/step at the
 # 1024 config on 2 GPUs) but process-group teardown then hangs with torch 2.11 / NCCL 2.28 -> off by default.
 GRAPH_COLLECTIVES = _os.environ.get("DCB_GRAPH_COLLECTIVES", "0") == "1"
@@ -124,15 +126,16 @@ class PackedModule(nn.Module):
 
 
 class Act:
-    """Channels-last activation: x is fp32 [B*T*H*W, C], rows ordered (b, t, y, x)."""
-    __slots__ = ("x", "B", "T", "H", "W")
+    """Channels-last activation: x is fp32 [B*T*H*W, C], rows ordered (b, t, y, x).  cs: the per-column statistics
+    partials its producer GEMM emitted (ops.ColSums) or None -- lets the consumer GroupNorm skip its statistics pass."""
+    __slots__ = ("x", "B", "T", "H", "W", "cs")
 
-    def __init__(self, x, B, T, H, W):
-        self.x, self.B, self.T, self.H, self.W = x, B, T, H, W
+    def __init__(self, x, B, T, H, W, cs=None):
+        self.x, self.B, self.T, self.H, self.W, self.cs = x, B, T, H, W, cs
 
     @property
     def C(self):
         return self.x.shape[1]
 
-    def like(self, x, H=None, W=None):
-        return Act(x, self.B, self.T, self.H if H is None else H, self.W if W is None else W)
+    def like(self, x, H=None, W=None, cs=None):
+        return Act(x, self.B, self.T, self.H if H is None else H, self.W if W is None else W, cs)

@@ -268,11 +268,11 @@ class SpatialTransformer(PackedModule):
         """h: Act (fp32 rows).  ctx: CrossAttentionContext.  Returns Act."""
         p = self.packed()
         nf, S = h.B * h.T, h.H * h.W
-        y = ops.group_norm(h.x, nf, S, self.norm.weight, self.norm.bias, self.norm.eps, silu=False)
+        y = ops.group_norm(h.x, nf, S, self.norm.weight, self.norm.bias, self.norm.eps, silu=False, colsums=h.cs)
         x = ops.linear(y, p["w_in"], bias=p["b_in"], f32=True, bf16=False)
         xb = self.transformer_blocks[0]._fwd_spatial(x, nf, S, ctx)
-        out = ops.linear(xb, p["w_out"], bias=p["b_out"], residual=h.x, f32=True, bf16=False)
-        return h.like(out)
+        out, cs = ops.linear(xb, p["w_out"], bias=p["b_out"], residual=h.x, f32=True, bf16=False, stats_rows=S)
+        return h.like(out, cs=cs)
 
     def forward(self, x, context=None, **kwargs):
         """x: [(b t), c, h, w] fp32; context: [(b t), 77+16, context_dim] (attention.py:294)."""
@@ -325,11 +325,11 @@ class TemporalTransformer(PackedModule):
         B, T, S = h.B, h.T, h.H * h.W
         if T > 16:
             raise NotImplementedError("temporal attention kernel handles at most 16 frames")
-        y = ops.group_norm(h.x, B, T * S, self.norm.weight, self.norm.bias, self.norm.eps, silu=False)
+        y = ops.group_norm(h.x, B, T * S, self.norm.weight, self.norm.bias, self.norm.eps, silu=False, colsums=h.cs)
         x = ops.linear(y, p["w_in"], bias=p["b_in"], f32=True, bf16=False)
         xb = self.transformer_blocks[0]._fwd_temporal(x, B, T, S)
-        out = ops.linear(xb, p["w_out"], bias=p["b_out"], residual=h.x, f32=True, bf16=False)
-        return h.like(out)
+        out, cs = ops.linear(xb, p["w_out"], bias=p["b_out"], residual=h.x, f32=True, bf16=False, stats_rows=S)
+        return h.like(out, cs=cs)
 
     def forward(self, x, context=None):
         """x: [b, c, t, h, w] fp32 (attention.py:365)."""

@@ -26,7 +26,7 @@ def Normalize(in_channels, num_groups=32):
 
 
 def _gn(norm, h, silu):
-    return ops.group_norm(h.x, h.B * h.T, h.H * h.W, norm.weight, norm.bias, norm.eps, silu=silu)
+    return ops.group_norm(h.x, h.B * h.T, h.H * h.W, norm.weight, norm.bias, norm.eps, silu=silu, colsums=h.cs)
 
 
 class Upsample(PackedModule):
@@ -44,7 +44,8 @@ class Upsample(PackedModule):
         p = self.packed()
         nf = h.B * h.T
         up = ops.upsample2x(h.x, nf, h.H, h.W)
-        return h.like(ops.conv3x3(up, nf, 2 * h.H, 2 * h.W, p["w"], bias=p["b"]), 2 * h.H, 2 * h.W)
+        out, cs = ops.conv3x3(up, nf, 2 * h.H, 2 * h.W, p["w"], bias=p["b"], stats=True)
+        return h.like(out, 2 * h.H, 2 * h.W, cs=cs)
 
 
 class Downsample(PackedModule):
@@ -65,8 +66,8 @@ class Downsample(PackedModule):
         p = self.packed()
         nf = h.B * h.T
         planes = ops.space_to_depth(h.x, nf, h.H, h.W)
-        o = ops.conv3x3_s2(planes, nf, h.H, h.W, p["w"], bias=p["b"], asym=True)
-        return h.like(o, H=(h.H - 2) // 2 + 1, W=(h.W - 2) // 2 + 1)
+        o, cs = ops.conv3x3_s2(planes, nf, h.H, h.W, p["w"], bias=p["b"], asym=True, stats=True)
+        return h.like(o, H=(h.H - 2) // 2 + 1, W=(h.W - 2) // 2 + 1, cs=cs)
 
 
 class ResnetBlock(PackedModule):
@@ -100,14 +101,15 @@ class ResnetBlock(PackedModule):
         p = self.packed()
         nf, S = h.B * h.T, h.H * h.W
         sc = "ws" in p
-        res = ops.group_norm(h.x, nf, S, self.norm1.weight, self.norm1.bias, self.norm1.eps, silu=True, want_raw=sc)
+        res = ops.group_norm(h.x, nf, S, self.norm1.weight, self.norm1.bias, self.norm1.eps, silu=True, want_raw=sc,
+                             colsums=h.cs)
         y, raw = res if sc else (res, None)
-        res1 = ops.conv3x3(y, nf, h.H, h.W, p["w1"], bias=p["b1"], f32=not _packing.BF16_VAE,
-                           bf16=_packing.BF16_VAE, stats=_packing.FUSED_GN_STATS)
-        h1, cs1 = res1 if _packing.FUSED_GN_STATS else (res1, None)
+        h1, cs1 = ops.conv3x3(y, nf, h.H, h.W, p["w1"], bias=p["b1"], f32=not _packing.BF16_VAE,
+                              bf16=_packing.BF16_VAE, stats=True)
         y2 = ops.group_norm(h1, nf, S, self.norm2.weight, self.norm2.bias, self.norm2.eps, silu=True, colsums=cs1)
         xs = ops.linear(raw, p["ws"], bias=p["bs"], f32=True, bf16=False) if sc else h.x
-        return h.like(ops.conv3x3(y2, nf, h.H, h.W, p["w2"], bias=p["b2"], residual=xs))
+        out, cs2 = ops.conv3x3(y2, nf, h.H, h.W, p["w2"], bias=p["b2"], residual=xs, stats=True)
+        return h.like(out, cs=cs2)
 
     def forward(self, x, temb=None):
         if temb is not None:
@@ -143,7 +145,8 @@ class AttnBlock(PackedModule):
         qkv = ops.linear(y, p["wqkv"], bias=p["bqkv"])            # bf16 [nf*S, 3C]
         scale = float(int(C) ** (-0.5))                           # ae_modules.py:67
         o = ops.vae_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], nf, S, C, scale)
-        return h.like(ops.linear(o, p["wo"], bias=p["bo"], residual=h.x, f32=True, bf16=False))
+        out, cs = ops.linear(o, p["wo"], bias=p["bo"], residual=h.x, f32=True, bf16=False, stats_rows=S)
+        return h.like(out, cs=cs)
 
     def forward(self, x):
         n, c, hh, ww = x.shape
@@ -208,7 +211,8 @@ class Encoder(PackedModule):
     def _fwd_rows(self, x_rows, n, hh, ww):
         """x_rows: bf16 [n*hh*ww, 64] channels-last image (zero-padded channels) -> (fp32 [n*(hh/8)*(ww/8), 2z], h, w)."""
         p = self.packed()
-        h = Act(ops.conv3x3(x_rows, n, hh, ww, p["w_in"], bias=p["b_in"]), n, 1, hh, ww)
+        h0, cs0 = ops.conv3x3(x_rows, n, hh, ww, p["w_in"], bias=p["b_in"], stats=True)
+        h = Act(h0, n, 1, hh, ww, cs0)
         for i_level in range(self.num_resolutions):
             for i_block in range(self.num_res_blocks):
                 h = self.down[i_level].block[i_block]._fwd(h)
@@ -281,7 +285,8 @@ class Decoder(PackedModule):
         """z_rows: bf16 [n*hh*ww, 64] channels-last latent (zero-padded channels) -> fp32 [n*8hh*8ww, out_ch]."""
         p = self.packed()
         self.last_z_shape = (n, self.conv_in.in_channels, hh, ww)
-        h = Act(ops.conv3x3(z_rows, n, hh, ww, p["w_in"], bias=p["b_in"]), n, 1, hh, ww)
+        h0, cs0 = ops.conv3x3(z_rows, n, hh, ww, p["w_in"], bias=p["b_in"], stats=True)
+        h = Act(h0, n, 1, hh, ww, cs0)
         h = self.mid.block_1._fwd(h)
         h = self.mid.attn_1._fwd(h)
         h = self.mid.block_2._fwd(h)

@@ -76,8 +76,8 @@ class Downsample(PackedModule):
         p = self.packed()
         nf = h.B * h.T
         planes = ops.space_to_depth(h.x, nf, h.H, h.W)
-        out = ops.conv3x3_s2(planes, nf, h.H, h.W, p["w"], bias=p["b"])
-        return h.like(out, (h.H - 1) // 2 + 1, (h.W - 1) // 2 + 1)
+        out, cs = ops.conv3x3_s2(planes, nf, h.H, h.W, p["w"], bias=p["b"], stats=True)
+        return h.like(out, (h.H - 1) // 2 + 1, (h.W - 1) // 2 + 1, cs=cs)
 
     def forward(self, x):
         assert x.shape[1] == self.channels
@@ -103,8 +103,8 @@ class Upsample(PackedModule):
         p = self.packed()
         nf = h.B * h.T
         up = ops.upsample2x(h.x, nf, h.H, h.W)
-        out = ops.conv3x3(up, nf, 2 * h.H, 2 * h.W, p["w"], bias=p["b"])
-        return h.like(out, 2 * h.H, 2 * h.W)
+        out, cs = ops.conv3x3(up, nf, 2 * h.H, 2 * h.W, p["w"], bias=p["b"], stats=True)
+        return h.like(out, 2 * h.H, 2 * h.W, cs=cs)
 
     def forward(self, x):
         assert x.shape[1] == self.channels
@@ -140,7 +140,8 @@ class TemporalConvBlock(PackedModule):
                 "b": [_f32(s[-1].bias) for s in self._stages()]}
 
     def _fwd(self, h, colsums=None):
-        """colsums: fused statistics of h.x from the GEMM that produced it (per-frame slices), or None."""
+        """colsums: fused statistics of h.x from the GEMM that produced it, or None.  Every stage's temporal conv emits
+        the column sums of its own output for the next GroupNorm (the last one for whoever consumes the block output)."""
         p = self.packed()
         B, T, S = h.B, h.T, h.H * h.W
         z = h.x
@@ -149,11 +150,9 @@ class TemporalConvBlock(PackedModule):
             y = ops.group_norm(z, B, T * S, gn.weight, gn.bias, gn.eps, silu=True, colsums=colsums)
             last = i == 3
             lowp = _packing.BF16_TCONV and not last
-            want = _packing.FUSED_GN_STATS and not last          # also emit the next GroupNorm's column sums
-            res = ops.tconv3(y, B, T, S, p["w"][i], bias=p["b"][i], residual=h.x if last else None,
-                             f32=not lowp, bf16=lowp, stats=want)
-            z, colsums = res if want else (res, None)
-        return h.like(z)
+            z, colsums = ops.tconv3(y, B, T, S, p["w"][i], bias=p["b"][i], residual=h.x if last else None,
+                                    f32=not lowp, bf16=lowp, stats=True)
+        return h.like(z, cs=colsums)
 
     def forward(self, x):
         """x: [b, c, t, h, w] (openaimodel3d.py:272)."""
@@ -208,21 +207,18 @@ class ResBlock(PackedModule, TimestepBlock):
         nf, S = h.B * h.T, h.H * h.W
         g1 = self.in_layers[0]
         has_skip_conv = "ws" in p
-        res = ops.group_norm(h.x, nf, S, g1.weight, g1.bias, g1.eps, x2=skip, silu=True, want_raw=has_skip_conv)
+        res = ops.group_norm(h.x, nf, S, g1.weight, g1.bias, g1.eps, x2=skip, silu=True, want_raw=has_skip_conv,
+                             colsums=h.cs if skip is None else None)
         y, raw = res if has_skip_conv else (res, None)
         # each conv also emits the column sums its consumer GroupNorm needs (fused statistics, no extra pass)
-        fuse = _packing.FUSED_GN_STATS
-        res1 = ops.conv3x3(y, nf, h.H, h.W, p["w1"], bias=p["b1"], group_bias=emb_out, rows_per_group=rows_per_emb,
-                           f32=not _packing.BF16_RES, bf16=_packing.BF16_RES, stats=fuse)
-        h1, cs1 = res1 if fuse else (res1, None)
+        h1, cs1 = ops.conv3x3(y, nf, h.H, h.W, p["w1"], bias=p["b1"], group_bias=emb_out, rows_per_group=rows_per_emb,
+                              f32=not _packing.BF16_RES, bf16=_packing.BF16_RES, stats=True)
         g2 = self.out_layers[0]
         y2 = ops.group_norm(h1, nf, S, g2.weight, g2.bias, g2.eps, silu=True, colsums=cs1)
         xs = ops.linear(raw, p["ws"], bias=p["bs"], f32=True, bf16=False) if has_skip_conv else h.x
-        tconv = self.use_temporal_conv and temporal
-        res2 = ops.conv3x3(y2, nf, h.H, h.W, p["w2"], bias=p["b2"], residual=xs, stats=tconv and fuse)
-        h2, cs2 = res2 if (tconv and fuse) else (res2, None)
-        out = h.like(h2)
-        if tconv:
+        h2, cs2 = ops.conv3x3(y2, nf, h.H, h.W, p["w2"], bias=p["b2"], residual=xs, stats=True)
+        out = h.like(h2, cs=cs2)
+        if self.use_temporal_conv and temporal:
             out = self.temopral_conv._fwd(out, colsums=cs2)
         return out
 
@@ -485,7 +481,8 @@ class UNetModel(PackedModule):
         ctx = self._context(context.to(dev), b, t)
         # ---- input conv
         xr = ops.nchw_to_rows(x, 64 if cin <= 64 else (cin + 63) // 64 * 64)
-        h = Act(ops.conv3x3(xr, b * t, hh, ww, pk["w_in"], bias=pk["b_in"]), b, t, hh, ww)
+        h0, cs0 = ops.conv3x3(xr, b * t, hh, ww, pk["w_in"], bias=pk["b_in"], stats=True)
+        h = Act(h0, b, t, hh, ww, cs0)
         hs = []
         for i, module in enumerate(self.input_blocks):
             if i > 0:
@@ -497,7 +494,7 @@ class UNetModel(PackedModule):
         for module in self.output_blocks:
             h = self._run(module, h, emb_all, pk, ctx, skip=hs.pop().x, shard=shard)
         g = self.out[0]
-        y = ops.group_norm(h.x, b * t, hh * ww, g.weight, g.bias, g.eps, silu=True)
+        y = ops.group_norm(h.x, b * t, hh * ww, g.weight, g.bias, g.eps, silu=True, colsums=h.cs)
         o = ops.conv3x3(y, b * t, hh, ww, pk["w_out"], bias=pk["b_out"])
         out = ops.rows_to_nchw(o, b, self.out_channels, t, hh, ww)
         if shard is not None:

@@ -52,11 +52,16 @@ def choose_box(D1, D2, D3):
 
 class ColSums:
     """Per-column (sum, sumsq) partials of a GEMM output, written by the GEMM epilogue (fused GroupNorm statistics).
-    partial: fp32 [D3 * rows_per_slice, C, 2]; slice_rows = activation rows per D3 slice."""
-    __slots__ = ("partial", "rows_per_slice", "slice_rows", "C")
+    partial: fp32 [units * rows_per_unit, C, 2]; a unit = `unit_rows` consecutive activation rows (one frame when the
+    producer's tiles never span frames, else one D3 slice) owning `rows_per_unit` consecutive partial rows."""
+    __slots__ = ("partial", "rows_per_unit", "unit_rows", "C")
 
-    def __init__(self, partial, rows_per_slice, slice_rows, C):
-        self.partial, self.rows_per_slice, self.slice_rows, self.C = partial, rows_per_slice, slice_rows, C
+    def __init__(self, partial, rows_per_unit, unit_rows, C):
+        self.partial, self.rows_per_unit, self.unit_rows, self.C = partial, rows_per_unit, unit_rows, C
+
+    def fits(self, S, C):
+        """Can a GroupNorm over instances of S rows x C channels be finalised from these partials?"""
+        return C == self.C and S % self.unit_rows == 0
 
 
 def colsum_supported(dims):
@@ -65,13 +70,21 @@ def colsum_supported(dims):
     return seg in (8, 16) or seg % 32 == 0
 
 
+def stats_enabled():
+    """Producer-fused GroupNorm statistics are used in the bf16 mode, outside frame-sharded temporal blocks."""
+    from .lvdm import _packing
+    return _packing.FUSED_GN_STATS and not fp32_mode() and _SHARDED_GN[0] is None
+
+
 def _make_colsums(dims, N, dev):
     b = choose_box(*dims)
     seg = b[0] * b[1]
-    t12 = -(-dims[0] // b[0]) * -(-dims[1] // b[1])
-    rps = t12 * max(1, seg // 32)
-    part = torch.empty((dims[2] * rps, N, 2), dtype=F32, device=dev)
-    return ColSums(part, rps, dims[0] * dims[1], N)
+    t1, t2 = -(-dims[0] // b[0]), -(-dims[1] // b[1])
+    sub = max(1, seg // 32)
+    part = torch.empty((dims[2] * t1 * t2 * sub, N, 2), dtype=F32, device=dev)
+    if b[1] == 1 and b[2] == 1:            # a tile never spans D2: partial rows are frame-major, unit = D1 rows
+        return ColSums(part, t1 * sub, dims[0], N)
+    return ColSums(part, t1 * t2 * sub, dims[0] * dims[1], N)
 
 
 def tap_gemm(a, dims, strides, adims, taps, w, N, *, bias=None, group_bias=None, rows_per_group=0,
@@ -147,8 +160,9 @@ def _outputs(rows, n_out, out, want_f32, want_bf16, dev):
 
 
 def linear(a, w, *, bias=None, residual=None, geglu=False, f32=False, bf16=True, out=None, N=None,
-           group_bias=None, rows_per_group=0, out_scale=1.0, block_n=0):
-    """a: bf16 [M, K] (row stride may exceed K); w: bf16 [N, K] -> [M, N] (or N/2 for geglu)."""
+           group_bias=None, rows_per_group=0, out_scale=1.0, block_n=0, stats_rows=0):
+    """a: bf16 [M, K] (row stride may exceed K); w: bf16 [N, K] -> [M, N] (or N/2 for geglu).
+    stats_rows = rows per frame: also emit the per-frame column sums a consumer GroupNorm needs -> (out, ColSums)."""
     M, K = a.shape
     if a.dtype == F32:                      # fp32 parity mode
         assert a.stride(1) == 1 and w.shape[1] == 3 * K
@@ -164,16 +178,26 @@ def linear(a, w, *, bias=None, residual=None, geglu=False, f32=False, bf16=True,
         s1 = a.stride(0)
         tap_gemm(a, (M, 1, 1), (s1, s1 * M, s1 * M), (M, 1, 1), [(0, 0, 0)], w, N, bias=bias, residual=residual,
                  out_f32=of, ld_out=ld, group_bias=group_bias, rows_per_group=rows_per_group, out_scale=out_scale)
-        return of
+        return (of, None) if stats_rows else of
     assert a.stride(1) == 1 and w.shape[1] == K
     N = N or w.shape[0]
     n_out = N // 2 if geglu else N
     of, ob, ld = _outputs(M, n_out, out, f32, bf16, a.device)
     s1 = a.stride(0)
+    res = of if (of is not None and ob is None) else (ob if of is None else (of, ob))
+    if stats_rows:
+        # same GEMM over a (rows per frame, 1, frames) domain so that the statistics partials are frame aligned
+        assert M % stats_rows == 0 and not geglu
+        dims = (stats_rows, 1, M // stats_rows)
+        cs = _make_colsums(dims, n_out, a.device) if (stats_enabled() and colsum_supported(dims)) else None
+        tap_gemm(a, dims, (s1, s1 * stats_rows, s1 * stats_rows), dims, [(0, 0, 0)], w, N, bias=bias, residual=residual,
+                 out_f32=of, out_bf16=ob, ld_out=ld, group_bias=group_bias, rows_per_group=rows_per_group,
+                 out_scale=out_scale, block_n=block_n, colsum=cs)
+        return res, cs
     tap_gemm(a, (M, 1, 1), (s1, s1 * M, s1 * M), (M, 1, 1), [(0, 0, 0)], w, N, bias=bias, residual=residual,
              geglu=geglu, out_f32=of, out_bf16=ob, ld_out=ld, group_bias=group_bias,
              rows_per_group=rows_per_group, out_scale=out_scale, block_n=block_n)
-    return of if (of is not None and ob is None) else (ob if of is None else (of, ob))
+    return res
 
 
 TAPS_3X3 = [(dx, dy, 0) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
@@ -187,7 +211,7 @@ def conv3x3(a, nf, H, W, w, *, bias=None, residual=None, group_bias=None, rows_p
     assert a.stride(1) == 1 and a.stride(0) == C and w.shape[1] == (27 if a.dtype == F32 else 9) * C
     N = N or w.shape[0]
     of, ob, ld = _outputs(nf * H * W, N, out, f32, bf16, a.device)
-    cs = _make_colsums((W, H, nf), N, a.device) if (stats and colsum_supported((W, H, nf))) else None
+    cs = _make_colsums((W, H, nf), N, a.device) if (stats and stats_enabled() and colsum_supported((W, H, nf))) else None
     tap_gemm(a, (W, H, nf), (C, C * W, C * W * H), (W, H, nf), TAPS_3X3, w, N, bias=bias, residual=residual,
              group_bias=group_bias, rows_per_group=rows_per_group, out_f32=of, out_bf16=ob, ld_out=ld, colsum=cs)
     res = of if of is not None else ob
@@ -200,7 +224,7 @@ def tconv3(a, B, T, HW, w, *, bias=None, residual=None, f32=True, bf16=False, ou
     assert a.stride(1) == 1 and a.stride(0) == C and w.shape[1] == (9 if a.dtype == F32 else 3) * C
     N = w.shape[0]
     of, ob, ld = _outputs(B * T * HW, N, out, f32, bf16, a.device)
-    cs = _make_colsums((HW, T, B), N, a.device) if (stats and colsum_supported((HW, T, B))) else None
+    cs = _make_colsums((HW, T, B), N, a.device) if (stats and stats_enabled() and colsum_supported((HW, T, B))) else None
     tap_gemm(a, (HW, T, B), (C, C * HW, C * HW * T), (HW, T, B), TAPS_T3, w, N, bias=bias, residual=residual,
              out_f32=of, out_bf16=ob, ld_out=ld, colsum=cs)
     res = of if of is not None else ob
@@ -250,15 +274,26 @@ def _c_f(v):
 
 
 def _stats_from_colsums(cs, G, S, C, eps, dev):
-    """Finalise fused statistics: instance g owns S / slice_rows consecutive D3 slices of the partial buffer."""
-    assert S % cs.slice_rows == 0 and cs.C == C
-    rpi = (S // cs.slice_rows) * cs.rows_per_slice
+    """Finalise fused statistics: instance g owns S / unit_rows consecutive units of the partial buffer."""
+    assert cs.fits(S, C)
+    rpi = (S // cs.unit_rows) * cs.rows_per_unit
     assert cs.partial.shape[0] == G * rpi, (cs.partial.shape, G, rpi)
     stats = torch.empty((G, 32, 2), dtype=F32, device=dev)
     check(_lib.lib().dcb_group_norm_finalize(ptr(cs.partial), _c_i(C), _c_i(rpi), _c_i(C), _c_i(G),
                                              ctypes.c_double(float(S) * (C // 32)), _c_f(eps), ptr(stats), _stream()),
           "dcb_group_norm_finalize")
     return stats
+
+
+def _group_norm_from_colsums(x, G, S, gamma, beta, eps, silu, cs):
+    """Producer-fused path: finalize (tiny) + one streaming apply pass; no statistics pass over x, no grid barrier."""
+    C, dev = x.shape[1], x.device
+    stats = _stats_from_colsums(cs, G, S, C, eps, dev)
+    y = torch.empty((G * S, C), dtype=BF16, device=dev)
+    check(_lib.lib().dcb_group_norm_stream_apply(ptr(x), _c_i(1 if x.dtype == BF16 else 0), _c_i(C), _c_i(G), _c_i(S),
+                                                 ptr(stats), ptr(gamma), ptr(beta), _c_i(1 if silu else 0), ptr(y),
+                                                 _stream()), "dcb_group_norm_stream_apply")
+    return y
 
 
 _SHARDED_GN = [None]      # FrameShard while the instances of group_norm calls are spread over ranks
@@ -316,8 +351,14 @@ def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False
     (and/or bf16 raw copy of the concat)."""
     require_cuda(x1, x2, gamma, beta)
     if _SHARDED_GN[0] is not None:
-        assert x2 is None and not want_raw and want_norm and colsums is None
+        assert x2 is None and not want_raw and want_norm
         return _group_norm_sharded(x1, G, S, gamma, beta, eps, silu, _SHARDED_GN[0])
+    if colsums is not None and (fp32_mode() or x2 is not None or want_raw or not want_norm or x1.shape[1] % 8
+                                or not x1.is_contiguous() or not colsums.fits(S, x1.shape[1])):
+        colsums = None                      # not usable here: take the self-contained path
+    if colsums is not None:
+        assert x1.shape[0] == G * S
+        return _group_norm_from_colsums(x1, G, S, gamma, beta, eps, silu, colsums)
     if fp32_mode():
         assert x1.dtype == F32 and x1.is_contiguous() and x1.shape[0] == G * S and want_norm
         C1, C2, dev, L = x1.shape[1], (0 if x2 is None else x2.shape[1]), x1.device, _lib.lib()
@@ -542,7 +583,7 @@ _S2 = {0: (1, -1), 1: (0, 0), 2: (1, 0)}   # k -> (phase, offset)
 _S2_ASYM = {0: (0, 0), 1: (1, 0), 2: (0, 1)}
 
 
-def conv3x3_s2(planes, nf, H, W, w, *, bias=None, f32=True, bf16=False, asym=False):
+def conv3x3_s2(planes, nf, H, W, w, *, bias=None, f32=True, bf16=False, asym=False, stats=False):
     """planes: output of space_to_depth ([4*nf*Hp*Wp, C]); w: bf16 [N, 9*C] (ky,kx,c). -> [nf*Ho*Wo, N].
     asym=False: stride 2, pad 1 (UNet Downsample); asym=True: pad right / bottom only, then stride 2 (VAE encoder)."""
     C = planes.shape[1]
@@ -560,9 +601,11 @@ def conv3x3_s2(planes, nf, H, W, w, *, bias=None, f32=True, bf16=False, asym=Fal
             taps.append((ox, oy, (py * 2 + px) * nf))
     N = w.shape[0]
     of, ob, ld = _outputs(nf * Ho * Wo, N, None, f32, bf16, planes.device)
+    cs = _make_colsums((Wo, Ho, nf), N, planes.device) if (stats and stats_enabled() and colsum_supported((Wo, Ho, nf))) else None
     tap_gemm(planes, (Wo, Ho, nf), (C, C * Wp, C * Wp * Hp), (Wp, Hp, 4 * nf), taps, w, N, bias=bias,
-             out_f32=of, out_bf16=ob, ld_out=ld)
-    return of if (of is not None and ob is None) else (ob if of is None else (of, ob))
+             out_f32=of, out_bf16=ob, ld_out=ld, colsum=cs)
+    res = of if (of is not None and ob is None) else (ob if of is None else (of, ob))
+    return (res, cs) if stats else res
 
 
 def cast_bf16(x):

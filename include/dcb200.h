@@ -113,6 +113,11 @@ int dcb_group_norm_apply(const float* x1, const float* x2, int C1, int C2, int G
  * `rows_per_instance` consecutive partial rows; count = elements per (instance, group). */
 int dcb_group_norm_finalize(const float* colsum, int colsum_ld, int rows_per_instance, int C, int G, double count,
                             float eps, float* stats, void* stream);
+/* y = silu?(x * rstd * gamma + beta - mean * rstd * gamma) with given statistics [G, 32, 2]: one streaming pass, x fp32 or
+ * bf16 [G*S, C], y bf16; the consumer half of the producer-fused GroupNorm (statistics from dcb_tap_gemm's colsum epilogue
+ * + dcb_group_norm_finalize).  Replaces the apply half of basics.py:76-87 / openaimodel3d.py:210-236,255-266. */
+int dcb_group_norm_stream_apply(const void* x, int x_is_bf16, int C, int G, int S, const float* stats, const float* gamma,
+                                const float* beta, int silu_act, void* y_bf16, void* stream);
 /* Same statistics / apply for a bf16 source (block-internal activations the producer GEMM wrote as bf16):
  * single source, C % 8 == 0. */
 int dcb_group_norm_stats_bf16(const void* x, int C, int G, int S, float eps, float* stats, void* workspace,

@@ -134,6 +134,15 @@ def test_fused_groupnorm_statistics_conv(nf, H, W, C, N, G):
         tol = 2e-3 if bf16 else 2e-5          # bf16 output is rounded after the statistics were taken
         assert (stats[:, :, 0] - mean).abs().max().item() < tol * (1 + mean.abs().max().item())
         assert ((stats[:, :, 1] - (var + 1e-5).rsqrt()).abs() / (var + 1e-5).rsqrt()).max().item() < (5e-3 if bf16 else 1e-4)
+    # fp32 output with the TMA-prefetched residual (the slot is refilled by TMA: extra group barrier after the read-back)
+    res = torch.randn(nf * H * W, N, device="cuda")
+    out, cs = ops.conv3x3(x.reshape(-1, C), nf, H, W, wp, bias=bias, residual=res, stats=True)
+    S = nf * H * W // G
+    stats = ops._stats_from_colsums(cs, G, S, N, 1e-5, out.device)
+    o = out.float().reshape(G, S, 32, N // 32).permute(0, 2, 1, 3).reshape(G, 32, -1)
+    mean, var = o.mean(-1), o.var(-1, unbiased=False)
+    assert (stats[:, :, 0] - mean).abs().max().item() < 2e-5 * (1 + mean.abs().max().item())
+    assert ((stats[:, :, 1] - (var + 1e-5).rsqrt()).abs() / (var + 1e-5).rsqrt()).max().item() < 1e-4
 
 
 @pytest.mark.parametrize("B,T,HW,C,N", [(2, 16, 40, 64, 128), (1, 16, 2560, 64, 64), (2, 16, 160, 64, 320)])
