@@ -27,7 +27,7 @@ class TapGemmArgs(ctypes.Structure):
         ("bias", c_vp), ("group_bias", c_vp), ("rows_per_group", c_int), ("ld_group_bias", c_int),
         ("residual", c_vp), ("ld_residual", c_int), ("geglu", c_int),
         ("out_f32", c_vp), ("out_bf16", c_vp), ("ld_out", c_int), ("out_scale", c_f),
-        ("colsum", c_vp), ("colsum_ld", c_int),
+        ("gn_acc", c_vp), ("gn_cg", c_int), ("gn_unit_mode", c_int),
     ]
 
 
@@ -75,7 +75,7 @@ def lib():
 EXPORTS = [
     "dcb_last_error", "dcb_abi_version", "dcb_check_device", "dcb_tap_gemm",
     "dcb_group_norm_workspace_bytes", "dcb_group_norm_stats", "dcb_group_norm_apply", "dcb_layer_norm",
-    "dcb_group_norm_stats_bf16", "dcb_group_norm_apply_bf16", "dcb_group_norm_finalize",
+    "dcb_group_norm_stats_bf16", "dcb_group_norm_apply_bf16", "dcb_group_norm_stats_from_acc",
     "dcb_group_norm_fused", "dcb_group_norm_fused_bf16",
     "dcb_group_norm_sums", "dcb_group_norm_sums_bf16", "dcb_group_norm_stats_from_sums", "dcb_group_norm_apply_f32out",
     "dcb_flash_attention", "dcb_temporal_attention", "dcb_softmax_rows",

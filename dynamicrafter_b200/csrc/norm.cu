@@ -661,58 +661,42 @@ extern "C" int dcb_group_norm_stats_from_sums(const double* sums, int G, double 
     return check_launch("group_norm_stats_from_sums");
 }
 
-// (mean, rstd) of instance n / group g from the per-column (sum, sumsq) partial rows a tap_gemm epilogue wrote.
-__global__ void __launch_bounds__(256)
-gn_finalize_kernel(const float* __restrict__ colsum, int ld, int rows_per_instance, int C, double count, float eps,
-                   float* __restrict__ stats) {
-    __shared__ double red[2][256];
-    const int g = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
-    const int cg = C / kGroups;
-    pdl_launch_dependents();
-    pdl_wait();                                          // the producer GEMM's partial sums are complete and visible
-    const float2* base = reinterpret_cast<const float2*>(colsum) + static_cast<size_t>(n) * rows_per_instance * ld + g * cg;
-    // thread (rsub, c): fixed column c of the group, rows rsub, rsub + R, ... with 8 independent loads in flight
-    const int tpr = cg <= 256 ? cg : 256;                 // threads along the columns of the group
-    const int R = 256 / tpr;                              // row lanes
-    const int c = tid % tpr, rsub = tid / tpr;
-    double s = 0.0, q = 0.0;
-    if (rsub < R) {
-        for (int cc = c; cc < cg; cc += tpr) {
-            for (int row = rsub; row < rows_per_instance; row += 8 * R) {
-                float2 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int rr = row + u * R;
-                    v[u] = rr < rows_per_instance ? __ldcg(base + static_cast<size_t>(rr) * ld + cc) : make_float2(0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { s += static_cast<double>(v[u].x); q += static_cast<double>(v[u].y); }
-            }
-        }
+// (mean, rstd) of one (instance, group) from the int64 fixed-point accumulator a tap_gemm epilogue filled
+// (gn_acc[unit][group][2] = round(sum * 2^20), round(sumsq * 2^20)); an instance = `upi` consecutive units.
+constexpr double kGnFixInv = 1.0 / 1048576.0;
+__device__ __forceinline__ void gn_stats_from_acc(const unsigned long long* __restrict__ acc, int n, int g, int upi,
+                                                  double count, float eps, float& mean_out, float& rstd_out) {
+    long long s = 0, q = 0;
+    const unsigned long long* a = acc + (static_cast<size_t>(n) * upi * kGroups + g) * 2;
+    for (int u = 0; u < upi; ++u) {
+        s += static_cast<long long>(__ldcg(a + static_cast<size_t>(u) * kGroups * 2));
+        q += static_cast<long long>(__ldcg(a + static_cast<size_t>(u) * kGroups * 2 + 1));
     }
-    red[0][tid] = s;
-    red[1][tid] = q;
-    __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {                 // fixed tree -> deterministic
-        if (tid < w) { red[0][tid] += red[0][tid + w]; red[1][tid] += red[1][tid + w]; }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        const double mean = red[0][0] / count;
-        double var = red[1][0] / count - mean * mean;
-        if (var < 0.0) var = 0.0;
-        stats[(static_cast<size_t>(n) * kGroups + g) * 2] = static_cast<float>(mean);
-        stats[(static_cast<size_t>(n) * kGroups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    }
+    const double mean = static_cast<double>(s) * kGnFixInv / count;
+    double var = static_cast<double>(q) * kGnFixInv / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_out = static_cast<float>(mean);
+    rstd_out = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
 }
 
-extern "C" int dcb_group_norm_finalize(const float* colsum, int colsum_ld, int rows_per_instance, int C, int G, double count,
-                                       float eps, float* stats, void* stream) {
-    if (colsum == nullptr || stats == nullptr || rows_per_instance < 1 || C % kGroups != 0 || G < 1 || colsum_ld < C || count <= 0)
-        return set_error(DCB_ERR_INVALID, "group_norm_finalize: bad argument");
-    launch_pdl(kPdlGnStream, gn_finalize_kernel, dim3(kGroups, G), dim3(256), 0, static_cast<cudaStream_t>(stream), colsum,
-               colsum_ld, rows_per_instance, C, count, eps, stats);
-    return check_launch("group_norm_finalize");
+__global__ void gn_acc_to_stats_kernel(const unsigned long long* __restrict__ acc, int upi, int n_total, double count,
+                                       float eps, float* __restrict__ stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    float m, r;
+    gn_stats_from_acc(acc, i / kGroups, i % kGroups, upi, count, eps, m, r);
+    stats[2 * i] = m;
+    stats[2 * i + 1] = r;
+}
+
+extern "C" int dcb_group_norm_stats_from_acc(const unsigned long long* gn_acc, int units_per_instance, int G, double count,
+                                             float eps, float* stats, void* stream) {
+    if (gn_acc == nullptr || stats == nullptr || units_per_instance < 1 || G < 1 || count <= 0)
+        return set_error(DCB_ERR_INVALID, "group_norm_stats_from_acc: bad argument");
+    const int n = G * kGroups;
+    gn_acc_to_stats_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(gn_acc, units_per_instance, n, count,
+                                                                                        eps, stats);
+    return check_launch("group_norm_stats_from_acc");
 }
 
 extern "C" int dcb_group_norm_stats_bf16(const void* x, int C, int G, int S, float eps, float* stats, void* workspace,
@@ -780,81 +764,93 @@ extern "C" int dcb_group_norm_apply_bf16(const void* x, int C, int G, int S, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// Streaming apply for statistics that already exist (emitted by the producer GEMM's epilogue and finalised by
-// gn_finalize_kernel): y = silu?(x * A[c] + B[c]), ONE pass over x (4 or 2 bytes in, 2 bytes out per element), no grid
-// barrier, no cooperative launch; launched with programmatic stream serialization so that its prologue overlaps the
-// finalize kernel.  grid = (chunks, G); a thread owns an 8-channel column and walks down the rows of its chunk.
+// Streaming apply for statistics the producer GEMM's epilogue accumulated (gn_acc, see tap_gemm): y = silu?(x * A[c] +
+// B[c]), ONE pass over x (4 or 2 bytes in, 2 bytes out per element): no statistics pass, no finalize launch, no grid
+// barrier, no cooperative launch.  Every block derives (mean, rstd) of its instance from the 32 x 2 x units int64 sums
+// (a few hundred bytes from L2).  grid = (chunks, G); blockDim = (C / 8) * rpp threads: a thread owns an 8-channel column
+// and walks down the rows of its chunk with U rows in flight (U = 4 fp32 / 8 bf16: >= 128 bytes per thread).
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256)
-gn_stream_apply_kernel(const T* __restrict__ x, int C, int S, int rows_per_chunk, const float* __restrict__ stats,
-                       const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
+__global__ void __launch_bounds__(512)
+gn_stream_apply_kernel(const T* __restrict__ x, int C, int S, int rows_per_chunk, const unsigned long long* __restrict__ acc,
+                       int upi, float eps, const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
                        __nv_bfloat16* __restrict__ y) {
-    extern __shared__ float s_ab[];          // A[C] | B[C]
+    __shared__ float s_mr[kGroups * 2];
     const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
     const int cg = C / kGroups;
+    const int O = C >> 3;                        // 8-channel columns per row
+    const int rpp = blockDim.x / O;              // rows covered by the block per step
+    const int my_r = tid / O, my_o = tid - my_r * O;
+    const int c0 = my_o * 8;
+    // affine coefficients that do not depend on the statistics
+    float gm[8], bt[8];
+    {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
+        gm[0] = g0.x; gm[1] = g0.y; gm[2] = g0.z; gm[3] = g0.w; gm[4] = g1.x; gm[5] = g1.y; gm[6] = g1.z; gm[7] = g1.w;
+        bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w; bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
+    }
     pdl_launch_dependents();
     pdl_wait();
-    for (int c = tid; c < C; c += 256) {
-        const int g = c / cg;
-        const float mean = __ldcg(stats + (static_cast<size_t>(n) * kGroups + g) * 2);
-        const float rstd = __ldcg(stats + (static_cast<size_t>(n) * kGroups + g) * 2 + 1);
-        const float a = rstd * gamma[c];
-        s_ab[c] = a;
-        s_ab[C + c] = beta[c] - mean * a;
+    if (tid < kGroups) {
+        float m, r;
+        gn_stats_from_acc(acc, n, tid, upi, static_cast<double>(S) * cg, eps, m, r);
+        s_mr[2 * tid] = m;
+        s_mr[2 * tid + 1] = r;
     }
     __syncthreads();
+    float am[8], bm[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int g = (c0 + e) / cg;
+        am[e] = s_mr[2 * g + 1] * gm[e];
+        bm[e] = bt[e] - s_mr[2 * g] * am[e];
+    }
     const int r0 = chunk * rows_per_chunk;
     const int nrows = min(S, r0 + rows_per_chunk) - r0;
-    const int O = C >> 3;
-    constexpr int U = 4;
-    for (int o0 = 0; o0 < O; o0 += 256) {
-        const int ow = min(256, O - o0);
-        const int rpp = 256 / ow;
-        const int my_r = tid / ow, my_o = o0 + tid - my_r * ow;
-        if (my_r >= rpp) continue;
-        const int c0 = my_o * 8;
-        float am[8], bm[8];
+    constexpr int U = 32 / sizeof(T) / 2;        // 4 (fp32) or 8 (bf16) rows in flight
+    const size_t row0 = static_cast<size_t>(n) * S + r0 + my_r;
+    const T* src = x + row0 * C + c0;
+    const size_t step = static_cast<size_t>(rpp) * C;
+    __nv_bfloat16* dst = y + row0 * C + c0;
+    for (int r = my_r; r < nrows; r += rpp * U) {
+        float v[U][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { am[e] = s_ab[c0 + e]; bm[e] = s_ab[C + c0 + e]; }
-        const size_t row0 = static_cast<size_t>(n) * S + r0 + my_r;
-        const T* src = x + row0 * C + c0;
-        const size_t step = static_cast<size_t>(rpp) * C;
-        __nv_bfloat16* dst = y + row0 * C + c0;
-        for (int r = my_r; r < nrows; r += rpp * U) {
-            float v[U][8];
+        for (int u = 0; u < U; ++u)
+            if (r + u * rpp < nrows) ld8(src + u * step, v[u]);
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (r + u * rpp < nrows) ld8(src + u * step, v[u]);
+        for (int u = 0; u < U; ++u) {
+            if (r + u * rpp < nrows) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (r + u * rpp < nrows) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float t = fmaf(v[u][e], am[e], bm[e]);
-                        v[u][e] = do_silu ? silu_fast(t) : t;
-                    }
-                    store8(dst + u * step, v[u]);
+                for (int e = 0; e < 8; ++e) {
+                    const float t = fmaf(v[u][e], am[e], bm[e]);
+                    v[u][e] = do_silu ? silu_fast(t) : t;
                 }
+                store8(dst + u * step, v[u]);
             }
-            src += U * step;
-            dst += U * step;
         }
+        src += U * step;
+        dst += U * step;
     }
 }
 
 template <typename T>
-static int launch_gn_stream_apply(const T* x, int C, int G, int S, const float* stats, const float* gamma, const float* beta,
-                                  int silu_act, void* y, cudaStream_t stream) {
-    // ~4 resident blocks' worth of chunks per SM, at least 4 rows each
-    int nch = (4 * num_sms() + G - 1) / G;
+static int launch_gn_stream_apply(const T* x, int C, int G, int S, const unsigned long long* acc, int upi, float eps,
+                                  const float* gamma, const float* beta, int silu_act, void* y, cudaStream_t stream) {
+    const int O = C / 8;
+    if (O > 512) return set_error(DCB_ERR_UNSUPPORTED, "group_norm_stream_apply: C=%d > 4096", C);
+    int rpp = 288 / O;                              // ~256-320 threads per block
+    if (rpp < 1) rpp = 1;
+    const int threads = O * rpp;
+    constexpr int U = 32 / sizeof(T) / 2;
+    // enough chunks for ~2 blocks per SM, but at least one full batch of U rows per thread
+    int nch = (2 * num_sms() + G - 1) / G;
     int rpc = (S + nch - 1) / nch;
-    const int min_rows = (8192 + C - 1) / C > 4 ? (8192 + C - 1) / C : 4;      // >= ~32 KB of fp32 input per block
-    if (rpc < min_rows) rpc = min_rows;
+    if (rpc < rpp * U) rpc = rpp * U;
+    rpc = (rpc + rpp - 1) / rpp * rpp;
     nch = (S + rpc - 1) / rpc;
-    const size_t smem = static_cast<size_t>(C) * 2 * sizeof(float);
-    launch_pdl(kPdlGnStream, gn_stream_apply_kernel<T>, dim3(nch, G), dim3(256), smem, stream, x, C, S, rpc, stats, gamma, beta,
-               silu_act, static_cast<__nv_bfloat16*>(y));
+    launch_pdl(kPdlGnStream, gn_stream_apply_kernel<T>, dim3(nch, G), dim3(threads), 0, stream, x, C, S, rpc, acc, upi, eps, gamma,
+               beta, silu_act, static_cast<__nv_bfloat16*>(y));
     return check_launch("group_norm_stream_apply");
 }
 
@@ -948,17 +944,19 @@ extern "C" int dcb_group_norm_fused_bf16(const void* x, int C, int G, int S, flo
                                           silu_act, y_bf16, nullptr, workspace, counters, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int dcb_group_norm_stream_apply(const void* x, int x_is_bf16, int C, int G, int S, const float* stats,
-                                           const float* gamma, const float* beta, int silu_act, void* y_bf16, void* stream) {
-    if (x == nullptr || y_bf16 == nullptr || stats == nullptr || gamma == nullptr || beta == nullptr)
+extern "C" int dcb_group_norm_stream_apply(const void* x, int x_is_bf16, int C, int G, int S, const unsigned long long* gn_acc,
+                                           int units_per_instance, float eps, const float* gamma, const float* beta,
+                                           int silu_act, void* y_bf16, void* stream) {
+    if (x == nullptr || y_bf16 == nullptr || gn_acc == nullptr || gamma == nullptr || beta == nullptr)
         return set_error(DCB_ERR_INVALID, "group_norm_stream_apply: null argument");
-    if (C % kGroups != 0 || (C & 7) || G < 1 || S < 1 || C > kMaxC || G > 65535)
+    if (C % kGroups != 0 || (C & 7) || G < 1 || S < 1 || C > kMaxC || G > 65535 || units_per_instance < 1)
         return set_error(DCB_ERR_INVALID, "group_norm_stream_apply: C=%d G=%d S=%d", C, G, S);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (x_is_bf16)
-        return launch_gn_stream_apply<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), C, G, S, stats, gamma, beta, silu_act,
-                                                     y_bf16, s);
-    return launch_gn_stream_apply<float>(static_cast<const float*>(x), C, G, S, stats, gamma, beta, silu_act, y_bf16, s);
+        return launch_gn_stream_apply<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), C, G, S, gn_acc, units_per_instance, eps,
+                                                     gamma, beta, silu_act, y_bf16, s);
+    return launch_gn_stream_apply<float>(static_cast<const float*>(x), C, G, S, gn_acc, units_per_instance, eps, gamma, beta,
+                                         silu_act, y_bf16, s);
 }
 
 extern "C" int dcb_layer_norm(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,

@@ -190,20 +190,23 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
     p.geglu = a->geglu;
     p.out_bf16 = obf ? 1 : 0;
     p.out_scale = a->out_scale;
-    p.colsum = a->colsum;
-    p.colsum_ld = a->colsum_ld;
+    p.gn_acc = a->gn_acc;
+    p.gn_cg = a->gn_cg;
+    p.gn_unit_mode = a->gn_unit_mode;
     p.seg_rows = a->b1 * a->b2;                                   // tile rows per D3 slice
-    p.seg_lw = p.seg_rows < 32 ? p.seg_rows : 32;                 // rows reduced inside one warp
-    p.seg_sub = p.seg_rows <= 32 ? 1 : p.seg_rows / 32;           // 32-row sub-partials per (slice, spatial tile)
-    if (a->colsum != nullptr) {
-        if (a->geglu || (p.seg_rows != 8 && p.seg_rows != 16 && p.seg_rows % 32 != 0) || p.seg_rows * a->b3 != p.rows_per_tile ||
-            a->colsum_ld < n_out)
-            return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: colsum needs b1*b2 in {8,16,32k} (got %d) and no geglu", p.seg_rows);
+    p.seg_lw = p.seg_rows < 32 ? p.seg_rows : 32;                 // rows folded inside one warp per unit
+    if (a->gn_acc != nullptr) {
+        const bool seg_ok = p.seg_rows == 8 || p.seg_rows == 16 || p.seg_rows % 32 == 0 || (a->b3 == 1 && !a->gn_unit_mode);
+        if (a->geglu || !seg_ok || (a->gn_unit_mode && a->b2 != 1) || a->gn_cg < 1 || n_out % a->gn_cg != 0 ||
+            n_out / a->gn_cg != 32 || (reinterpret_cast<uintptr_t>(a->gn_acc) & 7))
+            return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: fused GroupNorm statistics need 32 groups of gn_cg columns, no geglu and "
+                             "warp segments inside one unit (b1*b2 = %d, b3 = %d, mode %d)", p.seg_rows, a->b3, a->gn_unit_mode);
+        if (p.seg_rows != 8 && p.seg_rows != 16) p.seg_lw = 32;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (a->geglu && !obf) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: geglu writes bf16 only");
     if (a->geglu && a->residual != nullptr) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: geglu takes no residual");
-    if (a->colsum != nullptr) return tap_gemm_launch_cs(bn, obf, pair, tmA, tmB, tmOut, tmRes, p, s);
+    if (a->gn_acc != nullptr) return tap_gemm_launch_cs(bn, obf, pair, tmA, tmB, tmOut, tmRes, p, s);
     return launch_all<false>(bn, obf, pair, tmA, tmB, tmOut, tmRes, p, s);
 }
 

@@ -86,8 +86,8 @@ struct TapGemmParams {
     int ld_residual;
     float out_scale;
     uint32_t stage_bytes, res_bytes;
-    float* colsum;                 // fused GroupNorm statistics: per-(slice, sub-tile, column) partial (sum, sumsq), or null
-    int colsum_ld, seg_rows, seg_sub, seg_lw;
+    unsigned long long* gn_acc;    // fused GroupNorm statistics: int64 fixed-point [units][32][2] accumulator, or null
+    int gn_cg, gn_unit_mode, seg_rows, seg_lw;
 };
 
 // Exact (erf-based) GELU, attention.py:422.  erfc(z) via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, i.e. fp32
@@ -109,54 +109,83 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaxf(x, 0.f) - a * (e * poly);
 }
 
-// Fused GroupNorm statistics: column sums / sums of squares of one staged epilogue chunk (128 rows x 64 bytes in the
+// Fused GroupNorm statistics: (sum, sum of squares) of one staged epilogue chunk (128 rows x 64 bytes in the
 // SWIZZLE_64B slot, fp32 x16 or bf16 x32 columns) over the 32 rows of the calling warp, read back from shared memory
-// AFTER the group barrier (no shuffles on the accumulator path: 16 conflict-free 4-byte loads per lane).  Half-warp
-// h takes rows 2i + h, lane w the 4-byte word w of the row; the halves are folded with one shuffle per value.
-// Rows that share a GroupNorm slice: lw = 32 (whole warp), 16 or 8 consecutive rows -> 1, 2 or 4 partial rows, written
-// as (sum, sumsq) float2 per column at dst + seg * seg_stride.  Deterministic: fixed order, one writer per partial.
+// AFTER the group barrier (no shuffles on the accumulator path: 16 conflict-free 4-byte loads per lane).  Half-warp h
+// takes rows 2i + h, lane w the 4-byte word w of the row; the halves are folded with one shuffle per value, the columns
+// of one GroupNorm group (consecutive lanes) with a segmented shuffle reduction, and the first lane of every group adds
+// the result to the per-(unit, group) int64 fixed-point accumulator (integer atomics commute: bitwise reproducible).
+// Rows that share a unit: kSeg = 32 (whole warp), 16 or 8 consecutive rows -> 1, 2 or 4 units per warp.
+constexpr double kGnFixScale = 1048576.0;          // 2^20
 template <bool kF32, int kSeg>
-__device__ __forceinline__ void colsum_from_slot(const uint8_t* slot, int q, int lane, float* __restrict__ dst_seg0,
-                                                 long long seg_stride, int col0, int n_out, const bool* seg_ok) {
-    constexpr int NSEG = 32 / kSeg;                   // partial rows produced by this warp
+__device__ __forceinline__ void gn_acc_from_slot(const uint8_t* slot, int q, int lane, unsigned long long* __restrict__ acc,
+                                                 const long long* unit, int col0, int n_out, int cg) {
+    constexpr int NSEG = 32 / kSeg;                   // units covered by this warp
     constexpr int IPS = 16 / NSEG;                    // loop iterations (row pairs) per segment
+    constexpr int NV = kF32 ? 1 : 2;                  // columns per lane
     const int h = lane >> 4, w = lane & 15;
     const uint8_t* base = slot + (q * 32 + h) * 64 + ((w & 3) << 2);
-    float sx[NSEG][2], sq[NSEG][2];
+    float sx[NSEG], sq[NSEG];
 #pragma unroll
-    for (int sg = 0; sg < NSEG; ++sg) { sx[sg][0] = sx[sg][1] = sq[sg][0] = sq[sg][1] = 0.f; }
+    for (int sg = 0; sg < NSEG; ++sg) { sx[sg] = 0.f; sq[sg] = 0.f; }
+    const int col = col0 + w * NV;
+    // a bf16 lane holds two adjacent columns: they are in the same group unless the boundary falls between them
+    const bool split = !kF32 && ((col + 1) % cg == 0);
+    float sx2[NSEG], sq2[NSEG];                       // second column when it starts a new group
+#pragma unroll
+    for (int sg = 0; sg < NSEG; ++sg) { sx2[sg] = 0.f; sq2[sg] = 0.f; }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         // row q*32 + 2i + h: SWIZZLE_64B chunk index ^= (row / 2) % 4 = i % 4
         const uint32_t u = *reinterpret_cast<const uint32_t*>(base + i * 128 + ((((w >> 2) ^ (i & 3))) << 4));
-        constexpr int dummy = 0; (void)dummy;
         const int sg = i / IPS;
         if constexpr (kF32) {
             const float v = __uint_as_float(u);
-            sx[sg][0] += v;
-            sq[sg][0] = fmaf(v, v, sq[sg][0]);
+            sx[sg] += v;
+            sq[sg] = fmaf(v, v, sq[sg]);
         } else {
             const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
-            sx[sg][0] += v.x; sx[sg][1] += v.y;
-            sq[sg][0] = fmaf(v.x, v.x, sq[sg][0]); sq[sg][1] = fmaf(v.y, v.y, sq[sg][1]);
+            sx[sg] += v.x;
+            sq[sg] = fmaf(v.x, v.x, sq[sg]);
+            if (split) { sx2[sg] += v.y; sq2[sg] = fmaf(v.y, v.y, sq2[sg]); }
+            else { sx[sg] += v.y; sq[sg] = fmaf(v.y, v.y, sq[sg]); }
         }
     }
-    constexpr int NV = kF32 ? 1 : 2;
-#pragma unroll
-    for (int sg = 0; sg < NSEG; ++sg)
-#pragma unroll
-        for (int e = 0; e < NV; ++e) {
-            sx[sg][e] += __shfl_xor_sync(0xffffffffu, sx[sg][e], 16);
-            sq[sg][e] += __shfl_xor_sync(0xffffffffu, sq[sg][e], 16);
-        }
-    if (h != 0) return;
-    const int col = col0 + w * NV;
+    // group of my (first) column; columns past n_out (ragged N tiles) contribute nothing and join no group
+    const bool in0 = col < n_out, in1 = !kF32 && (col + 1 < n_out);
+    const int gid = in0 ? col / cg : -1 - w;
 #pragma unroll
     for (int sg = 0; sg < NSEG; ++sg) {
-        if (!seg_ok[sg]) continue;
-        float* d = dst_seg0 + sg * seg_stride + 2 * col;
-        if (col < n_out) *reinterpret_cast<float2*>(d) = make_float2(sx[sg][0], sq[sg][0]);
-        if (NV == 2 && col + 1 < n_out) *reinterpret_cast<float2*>(d + 2) = make_float2(sx[sg][1], sq[sg][1]);
+        float a = sx[sg] + __shfl_xor_sync(0xffffffffu, sx[sg], 16);
+        float b = sq[sg] + __shfl_xor_sync(0xffffffffu, sq[sg], 16);
+        float a2 = 0.f, b2 = 0.f;
+        if constexpr (!kF32) {
+            a2 = sx2[sg] + __shfl_xor_sync(0xffffffffu, sx2[sg], 16);
+            b2 = sq2[sg] + __shfl_xor_sync(0xffffffffu, sq2[sg], 16);
+            if (!in1 && !split) { /* second column out of range: its (zero-filled) values were added to a: harmless */ }
+        }
+        // segmented reduction over the 16 column lanes (group ids are non-decreasing with the lane)
+#pragma unroll
+        for (int off = 1; off < 16; off <<= 1) {
+            const float ta = __shfl_down_sync(0xffffffffu, a, off, 16);
+            const float tb = __shfl_down_sync(0xffffffffu, b, off, 16);
+            const int tg = __shfl_down_sync(0xffffffffu, gid, off, 16);
+            if (w + off < 16 && tg == gid) { a += ta; b += tb; }
+        }
+        const int gprev = __shfl_up_sync(0xffffffffu, gid, 1, 16);
+        const bool head = (w == 0) || (gprev != gid);
+        if (h == 0 && unit[sg] >= 0) {
+            if (head && in0) {
+                unsigned long long* d = acc + (unit[sg] * 32 + gid) * 2;
+                atomicAdd(d, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(a) * kGnFixScale)));
+                atomicAdd(d + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(b) * kGnFixScale)));
+            }
+            if (!kF32 && split && in1) {
+                unsigned long long* d = acc + (unit[sg] * 32 + (col + 1) / cg) * 2;
+                atomicAdd(d, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(a2) * kGnFixScale)));
+                atomicAdd(d + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(b2) * kGnFixScale)));
+            }
+        }
     }
 }
 
@@ -352,20 +381,16 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (!kF32 && p.has_residual) res_row = p.residual + grow * p.ld_residual;
                 }
             }
-            // fused GroupNorm statistics: this warp's 32 rows are 32 / seg_lw segments (slices of D3) or part of one
-            float* cs_dst = nullptr;
-            bool cs_seg_ok[4] = {false, false, false, false};
-            long long cs_stride = 0;
+            // fused GroupNorm statistics: this warp's 32 rows are 32 / seg_lw segments, each inside one unit (-1: no rows)
+            long long cs_unit[4] = {-1, -1, -1, -1};
             if constexpr (kCS) {
-                const int st = (m_tile % (p.t1 * p.t2));                  // spatial tile inside the D3 slice
                 const int rb = q * 32;                                    // first tile row of this warp
-                const int seg0 = rb / p.seg_rows;                         // D3 offset of the warp's first segment
-                const int sub = (rb % p.seg_rows) / 32;                   // 32-row sub-partial inside a long segment
-                const long long per_slice = static_cast<long long>(p.t1) * p.t2 * p.seg_sub;
-                cs_stride = per_slice * p.colsum_ld * 2;
-                cs_dst = p.colsum + ((static_cast<long long>(o3 + seg0) * p.t1 * p.t2 + st) * p.seg_sub + sub) * p.colsum_ld * 2;
-                for (int sg = 0; sg < 32 / p.seg_lw; ++sg)
-                    cs_seg_ok[sg] = (rb + sg * p.seg_lw < p.rows_per_tile) && (o3 + seg0 + sg < p.D3);
+                for (int sg = 0; sg < 32 / p.seg_lw; ++sg) {
+                    const int row = rb + sg * p.seg_lw;                   // first row of the segment
+                    const int g2 = o2 + (row / p.b1) % p.b2, g3 = o3 + row / (p.b1 * p.b2);
+                    if (row < p.rows_per_tile && g2 < p.D2 && g3 < p.D3)
+                        cs_unit[sg] = p.gn_unit_mode ? static_cast<long long>(g3) * p.D2 + g2 : g3;
+                }
             }
             const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
             bool acc_ready = false;
@@ -517,9 +542,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 if constexpr (kCS) {
                     // the slot now holds the final values of all 128 rows: fold this warp's 32 rows per column
-                    if (p.seg_lw == 32) colsum_from_slot<kF32, 32>(slot, q, lane, cs_dst, cs_stride, col0, p.N_out, cs_seg_ok);
-                    else if (p.seg_lw == 16) colsum_from_slot<kF32, 16>(slot, q, lane, cs_dst, cs_stride, col0, p.N_out, cs_seg_ok);
-                    else colsum_from_slot<kF32, 8>(slot, q, lane, cs_dst, cs_stride, col0, p.N_out, cs_seg_ok);
+                    if (p.seg_lw == 32) gn_acc_from_slot<kF32, 32>(slot, q, lane, p.gn_acc, cs_unit, col0, p.N_out, p.gn_cg);
+                    else if (p.seg_lw == 16) gn_acc_from_slot<kF32, 16>(slot, q, lane, p.gn_acc, cs_unit, col0, p.N_out, p.gn_cg);
+                    else gn_acc_from_slot<kF32, 8>(slot, q, lane, p.gn_acc, cs_unit, col0, p.N_out, p.gn_cg);
                     // the leader's next residual prefetch (TMA write into a slot) must not overtake these reads
                     if (tma_res) named_bar_sync(bar_id, 128);
                 }

@@ -90,7 +90,8 @@ class AutoencoderKL(PackedModule):
         with use_precision("bf16"):
             p = self.packed()
             n, c, hh, ww = x.shape
-            h, H, W = self.encoder._fwd_rows(ops.nchw_to_rows(x, 64), n, hh, ww)          # fp32 [n*H*W, 2z]
+            with ops.stats_scope(x.device):
+                h, H, W = self.encoder._fwd_rows(ops.nchw_to_rows(x, 64), n, hh, ww)      # fp32 [n*H*W, 2z]
             hb = ops.cast_bf16(h.contiguous())
             m = ops.linear(hb, p["wq"], bias=p["bq"], f32=True, bf16=False)             # 1x1 quant_conv
             moments = ops.rows_to_nchw(m, n, m.shape[1], 1, H, W, five_d=False).to(x.dtype)
@@ -108,7 +109,8 @@ class AutoencoderKL(PackedModule):
             zr = ops.nchw_to_rows(z, 64)
             pq = torch.zeros((n * hh * ww, 64), dtype=torch.bfloat16, device=z.device)
             ops.linear(zr, p["w"], bias=p["b"], out=pq)      # 1x1 post_quant_conv, written into the padded operand
-            o, H, W = self.decoder._fwd_rows(pq, n, hh, ww)
+            with ops.stats_scope(z.device):
+                o, H, W = self.decoder._fwd_rows(pq, n, hh, ww)
             return ops.rows_to_nchw(o, n, self.decoder.out_ch, 1, H, W, five_d=False).to(z.dtype)
 
     def forward(self, input, sample_posterior=True):

@@ -232,7 +232,8 @@ class Encoder(PackedModule):
         if not x.is_cuda:
             raise RuntimeError("dcb200 Encoder runs on CUDA tensors only (no CPU path)")
         n, c, hh, ww = x.shape
-        o, H, W = self._fwd_rows(ops.nchw_to_rows(x, 64), n, hh, ww)
+        with ops.stats_scope(x.device):
+            o, H, W = self._fwd_rows(ops.nchw_to_rows(x, 64), n, hh, ww)
         return ops.rows_to_nchw(o, n, self.out_channels, 1, H, W, five_d=False).to(x.dtype)
 
 
@@ -306,5 +307,6 @@ class Decoder(PackedModule):
         if not z.is_cuda:
             raise RuntimeError("dcb200 Decoder runs on CUDA tensors only (no CPU path)")
         n, c, hh, ww = z.shape
-        o, H, W = self._fwd_rows(ops.nchw_to_rows(z, 64), n, hh, ww)
+        with ops.stats_scope(z.device):
+            o, H, W = self._fwd_rows(ops.nchw_to_rows(z, 64), n, hh, ww)
         return ops.rows_to_nchw(o, n, self.out_ch, 1, H, W, five_d=False).to(z.dtype)

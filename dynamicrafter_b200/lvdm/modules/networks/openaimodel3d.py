@@ -454,6 +454,10 @@ class UNetModel(PackedModule):
         return sy.clone()
 
     def _forward_impl(self, x, timesteps, context, fs):
+        with ops.stats_scope(x.device):          # fused GroupNorm statistics accumulators: one memset per forward
+            return self._forward_body(x, timesteps, context, fs)
+
+    def _forward_body(self, x, timesteps, context, fs):
         pk = self.packed()
         shard = getattr(self, "frame_shard", None)      # parallel.FrameShard: this rank denoises frames t0..t1 only
         if shard is not None:

@@ -51,23 +51,30 @@ def choose_box(D1, D2, D3):
 
 
 class ColSums:
-    """Per-column (sum, sumsq) partials of a GEMM output, written by the GEMM epilogue (fused GroupNorm statistics).
-    partial: fp32 [units * rows_per_unit, C, 2]; a unit = `unit_rows` consecutive activation rows (one frame when the
-    producer's tiles never span frames, else one D3 slice) owning `rows_per_unit` consecutive partial rows."""
-    __slots__ = ("partial", "rows_per_unit", "unit_rows", "C")
+    """Fused GroupNorm statistics of a GEMM output, accumulated by the GEMM epilogue: acc = int64 [units, 32, 2] fixed-point
+    (sum, sumsq) per unit and group; a unit = `unit_rows` consecutive activation rows (one frame, or one video when the
+    producer's tiles span frames).  mode: dcb_tap_gemm_args.gn_unit_mode."""
+    __slots__ = ("acc", "unit_rows", "C", "mode")
 
-    def __init__(self, partial, rows_per_unit, unit_rows, C):
-        self.partial, self.rows_per_unit, self.unit_rows, self.C = partial, rows_per_unit, unit_rows, C
+    def __init__(self, acc, unit_rows, C, mode):
+        self.acc, self.unit_rows, self.C, self.mode = acc, unit_rows, C, mode
 
     def fits(self, S, C):
-        """Can a GroupNorm over instances of S rows x C channels be finalised from these partials?"""
+        """Can a GroupNorm over instances of S rows x C channels be served from these sums?"""
         return C == self.C and S % self.unit_rows == 0
 
 
-def colsum_supported(dims):
+def _unit_mode(dims, b):
+    """1: a tile never spans D2 (temporal conv with one frame per tile) -> units = (D3, D2) = frames; else units = D3."""
+    return 1 if (dims[1] > 1 and b[1] == 1 and b[2] == 1) else 0
+
+
+def colsum_supported(dims, N=None):
     b = choose_box(*dims)
     seg = b[0] * b[1]
-    return seg in (8, 16) or seg % 32 == 0
+    if N is not None and N % 32:
+        return False
+    return seg in (8, 16) or seg % 32 == 0 or b[2] == 1
 
 
 def stats_enabled():
@@ -76,15 +83,60 @@ def stats_enabled():
     return _packing.FUSED_GN_STATS and not fp32_mode() and _SHARDED_GN[0] is None
 
 
+class _StatsArena:
+    """Pre-zeroed int64 pool the per-launch accumulators are carved from: one memset per forward instead of one per GEMM.
+    Buffers that are outgrown are retired, not freed (captured CUDA graphs keep their addresses)."""
+
+    def __init__(self):
+        self.buf, self.off, self.high, self.active, self.retired = None, 0, 0, False, []
+
+
+_ARENAS = {}
+
+
+class stats_scope:
+    """with stats_scope(device): every fused-statistics accumulator allocated inside comes from the device's arena, which
+    is re-zeroed (its used prefix) once on entry.  Not re-entrant: an inner scope is a no-op."""
+
+    def __init__(self, dev):
+        self.ar = _ARENAS.setdefault(dev.index, _StatsArena())
+        self.owner = False
+
+    def __enter__(self):
+        ar = self.ar
+        if not ar.active:
+            self.owner, ar.active, ar.off = True, True, 0
+            if ar.buf is not None and ar.high > 0:
+                ar.buf[:ar.high].zero_()
+        return self
+
+    def __exit__(self, *exc):
+        if self.owner:
+            self.ar.high = max(self.ar.high, self.ar.off)
+            self.ar.active = False
+
+
+def _alloc_acc(units, dev):
+    n = units * 64
+    ar = _ARENAS.get(dev.index)
+    if ar is not None and ar.active:
+        if ar.buf is None or ar.off + n > ar.buf.numel():
+            if ar.buf is not None:
+                ar.retired.append(ar.buf)
+            cap = max(2 * (ar.buf.numel() if ar.buf is not None else 0), 1 << 20, n)
+            ar.buf, ar.off, ar.high = torch.zeros(cap, dtype=torch.int64, device=dev), 0, 0
+        out = ar.buf[ar.off:ar.off + n].view(units, 32, 2)
+        ar.off += n
+        return out
+    return torch.zeros((units, 32, 2), dtype=torch.int64, device=dev)
+
+
 def _make_colsums(dims, N, dev):
     b = choose_box(*dims)
-    seg = b[0] * b[1]
-    t1, t2 = -(-dims[0] // b[0]), -(-dims[1] // b[1])
-    sub = max(1, seg // 32)
-    part = torch.empty((dims[2] * t1 * t2 * sub, N, 2), dtype=F32, device=dev)
-    if b[1] == 1 and b[2] == 1:            # a tile never spans D2: partial rows are frame-major, unit = D1 rows
-        return ColSums(part, t1 * sub, dims[0], N)
-    return ColSums(part, t1 * t2 * sub, dims[0] * dims[1], N)
+    mode = _unit_mode(dims, b)
+    if mode:
+        return ColSums(_alloc_acc(dims[1] * dims[2], dev), dims[0], N, 1)
+    return ColSums(_alloc_acc(dims[2], dev), dims[0] * dims[1], N, 0)
 
 
 def tap_gemm(a, dims, strides, adims, taps, w, N, *, bias=None, group_bias=None, rows_per_group=0,
@@ -133,8 +185,9 @@ def tap_gemm(a, dims, strides, adims, taps, w, N, *, bias=None, group_bias=None,
     args.out_bf16 = None if out_bf16 is None else out_bf16.data_ptr()
     args.ld_out = ld_out
     args.out_scale = out_scale
-    args.colsum = None if colsum is None else colsum.partial.data_ptr()
-    args.colsum_ld = 0 if colsum is None else colsum.C
+    args.gn_acc = None if colsum is None else colsum.acc.data_ptr()
+    args.gn_cg = 0 if colsum is None else colsum.C // 32
+    args.gn_unit_mode = 0 if colsum is None else colsum.mode
     check(_lib.lib().dcb_tap_gemm(ctypes.byref(args), _stream()), "dcb_tap_gemm")
 
 
@@ -189,7 +242,7 @@ def linear(a, w, *, bias=None, residual=None, geglu=False, f32=False, bf16=True,
         # same GEMM over a (rows per frame, 1, frames) domain so that the statistics partials are frame aligned
         assert M % stats_rows == 0 and not geglu
         dims = (stats_rows, 1, M // stats_rows)
-        cs = _make_colsums(dims, n_out, a.device) if (stats_enabled() and colsum_supported(dims)) else None
+        cs = _make_colsums(dims, n_out, a.device) if (stats_enabled() and colsum_supported(dims, n_out)) else None
         tap_gemm(a, dims, (s1, s1 * stats_rows, s1 * stats_rows), dims, [(0, 0, 0)], w, N, bias=bias, residual=residual,
                  out_f32=of, out_bf16=ob, ld_out=ld, group_bias=group_bias, rows_per_group=rows_per_group,
                  out_scale=out_scale, block_n=block_n, colsum=cs)
@@ -211,7 +264,7 @@ def conv3x3(a, nf, H, W, w, *, bias=None, residual=None, group_bias=None, rows_p
     assert a.stride(1) == 1 and a.stride(0) == C and w.shape[1] == (27 if a.dtype == F32 else 9) * C
     N = N or w.shape[0]
     of, ob, ld = _outputs(nf * H * W, N, out, f32, bf16, a.device)
-    cs = _make_colsums((W, H, nf), N, a.device) if (stats and stats_enabled() and colsum_supported((W, H, nf))) else None
+    cs = _make_colsums((W, H, nf), N, a.device) if (stats and stats_enabled() and colsum_supported((W, H, nf), N)) else None
     tap_gemm(a, (W, H, nf), (C, C * W, C * W * H), (W, H, nf), TAPS_3X3, w, N, bias=bias, residual=residual,
              group_bias=group_bias, rows_per_group=rows_per_group, out_f32=of, out_bf16=ob, ld_out=ld, colsum=cs)
     res = of if of is not None else ob
@@ -224,7 +277,7 @@ def tconv3(a, B, T, HW, w, *, bias=None, residual=None, f32=True, bf16=False, ou
     assert a.stride(1) == 1 and a.stride(0) == C and w.shape[1] == (9 if a.dtype == F32 else 3) * C
     N = w.shape[0]
     of, ob, ld = _outputs(B * T * HW, N, out, f32, bf16, a.device)
-    cs = _make_colsums((HW, T, B), N, a.device) if (stats and stats_enabled() and colsum_supported((HW, T, B))) else None
+    cs = _make_colsums((HW, T, B), N, a.device) if (stats and stats_enabled() and colsum_supported((HW, T, B), N)) else None
     tap_gemm(a, (HW, T, B), (C, C * HW, C * HW * T), (HW, T, B), TAPS_T3, w, N, bias=bias, residual=residual,
              out_f32=of, out_bf16=ob, ld_out=ld, colsum=cs)
     res = of if of is not None else ob
@@ -274,25 +327,25 @@ def _c_f(v):
 
 
 def _stats_from_colsums(cs, G, S, C, eps, dev):
-    """Finalise fused statistics: instance g owns S / unit_rows consecutive units of the partial buffer."""
+    """(mean, rstd) [G, 32, 2] from a fused-statistics accumulator (tests / inspection)."""
     assert cs.fits(S, C)
-    rpi = (S // cs.unit_rows) * cs.rows_per_unit
-    assert cs.partial.shape[0] == G * rpi, (cs.partial.shape, G, rpi)
+    upi = S // cs.unit_rows
+    assert cs.acc.shape[0] == G * upi, (cs.acc.shape, G, upi)
     stats = torch.empty((G, 32, 2), dtype=F32, device=dev)
-    check(_lib.lib().dcb_group_norm_finalize(ptr(cs.partial), _c_i(C), _c_i(rpi), _c_i(C), _c_i(G),
-                                             ctypes.c_double(float(S) * (C // 32)), _c_f(eps), ptr(stats), _stream()),
-          "dcb_group_norm_finalize")
+    check(_lib.lib().dcb_group_norm_stats_from_acc(ptr(cs.acc), _c_i(upi), _c_i(G), ctypes.c_double(float(S) * (C // 32)),
+                                                   _c_f(eps), ptr(stats), _stream()), "dcb_group_norm_stats_from_acc")
     return stats
 
 
 def _group_norm_from_colsums(x, G, S, gamma, beta, eps, silu, cs):
-    """Producer-fused path: finalize (tiny) + one streaming apply pass; no statistics pass over x, no grid barrier."""
+    """Producer-fused path: ONE streaming apply pass; no statistics pass over x, no finalize launch, no grid barrier."""
     C, dev = x.shape[1], x.device
-    stats = _stats_from_colsums(cs, G, S, C, eps, dev)
+    upi = S // cs.unit_rows
+    assert cs.acc.shape[0] == G * upi, (cs.acc.shape, G, upi)
     y = torch.empty((G * S, C), dtype=BF16, device=dev)
     check(_lib.lib().dcb_group_norm_stream_apply(ptr(x), _c_i(1 if x.dtype == BF16 else 0), _c_i(C), _c_i(G), _c_i(S),
-                                                 ptr(stats), ptr(gamma), ptr(beta), _c_i(1 if silu else 0), ptr(y),
-                                                 _stream()), "dcb_group_norm_stream_apply")
+                                                 ptr(cs.acc), _c_i(upi), _c_f(eps), ptr(gamma), ptr(beta),
+                                                 _c_i(1 if silu else 0), ptr(y), _stream()), "dcb_group_norm_stream_apply")
     return y
 
 
@@ -601,7 +654,7 @@ def conv3x3_s2(planes, nf, H, W, w, *, bias=None, f32=True, bf16=False, asym=Fal
             taps.append((ox, oy, (py * 2 + px) * nf))
     N = w.shape[0]
     of, ob, ld = _outputs(nf * Ho * Wo, N, None, f32, bf16, planes.device)
-    cs = _make_colsums((Wo, Ho, nf), N, planes.device) if (stats and stats_enabled() and colsum_supported((Wo, Ho, nf))) else None
+    cs = _make_colsums((Wo, Ho, nf), N, planes.device) if (stats and stats_enabled() and colsum_supported((Wo, Ho, nf), N)) else None
     tap_gemm(planes, (Wo, Ho, nf), (C, C * Wp, C * Wp * Hp), (Wp, Hp, 4 * nf), taps, w, N, bias=bias,
              out_f32=of, out_bf16=ob, ld_out=ld, colsum=cs)
     res = of if (of is not None and ob is None) else (ob if of is None else (of, ob))

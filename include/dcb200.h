@@ -82,12 +82,16 @@ typedef struct {
     void* out_bf16;
     int32_t ld_out;
     float out_scale;          /* applied to acc before bias (1.0 = none) */
-    /* Optional fused GroupNorm statistics of the OUTPUT (NULL = off): per (D3 slice d, spatial tile st of the t1*t2
-     * tiles of a slice, 32-row sub-tile u) the kernel writes (sum, sum of squares) of every output column to
-     * colsum[(((d * t1*t2 + st) * sub) + u) * colsum_ld + n] as float2, sub = max(1, b1*b2/32).  Requires
-     * b1*b2 in {8, 16, 32, 64, 96, 128}.  dcb_group_norm_finalize turns them into (mean, rstd). */
-    float* colsum;
-    int32_t colsum_ld;
+    /* Optional fused GroupNorm statistics of the OUTPUT (NULL = off).  gn_acc: int64 [units, 32, 2], zero-initialised by
+     * the caller; the epilogue adds, per unit and per group of gn_cg consecutive output columns, (sum, sum of squares) of
+     * the stored values as fixed-point integers (value * 2^20, rounded): integer atomics commute, so the totals are bitwise
+     * reproducible.  gn_unit_mode 0: unit = D3 index (a frame of a 2-D conv / linear, a video of a temporal conv);
+     * 1: unit = D3 index * D2 + D2 index (a frame of a temporal conv; needs b2 == 1).  Requires every 32-row warp segment
+     * of a tile to lie inside one unit: b1*b2 in {8, 16} or a multiple of 32, or b3 == 1 with mode 0.
+     * dcb_group_norm_stream_apply consumes the accumulator directly (no statistics pass, no finalize launch). */
+    unsigned long long* gn_acc;
+    int32_t gn_cg;
+    int32_t gn_unit_mode;
 } dcb_tap_gemm_args;
 
 int dcb_tap_gemm(const dcb_tap_gemm_args* args, void* stream);
@@ -109,15 +113,17 @@ int dcb_group_norm_stats(const float* x1, const float* x2, int C1, int C2, int G
 int dcb_group_norm_apply(const float* x1, const float* x2, int C1, int C2, int G, int S,
                          const float* stats, const float* gamma, const float* beta, int silu_act,
                          void* y_bf16, void* raw_bf16, void* stream);
-/* (mean, rstd) from the column-sum partials a dcb_tap_gemm launch wrote (colsum): instance g owns
- * `rows_per_instance` consecutive partial rows; count = elements per (instance, group). */
-int dcb_group_norm_finalize(const float* colsum, int colsum_ld, int rows_per_instance, int C, int G, double count,
-                            float eps, float* stats, void* stream);
-/* y = silu?(x * rstd * gamma + beta - mean * rstd * gamma) with given statistics [G, 32, 2]: one streaming pass, x fp32 or
- * bf16 [G*S, C], y bf16; the consumer half of the producer-fused GroupNorm (statistics from dcb_tap_gemm's colsum epilogue
- * + dcb_group_norm_finalize).  Replaces the apply half of basics.py:76-87 / openaimodel3d.py:210-236,255-266. */
-int dcb_group_norm_stream_apply(const void* x, int x_is_bf16, int C, int G, int S, const float* stats, const float* gamma,
-                                const float* beta, int silu_act, void* y_bf16, void* stream);
+/* (mean, rstd) [G, 32, 2] from the fixed-point accumulator a dcb_tap_gemm launch filled (gn_acc): instance g owns
+ * `units_per_instance` consecutive units; count = elements per (instance, group).  Inspection / tests only -- the
+ * streaming apply below reads the accumulator itself. */
+int dcb_group_norm_stats_from_acc(const unsigned long long* gn_acc, int units_per_instance, int G, double count, float eps,
+                                  float* stats, void* stream);
+/* y = silu?((x - mean) * rstd * gamma + beta) with the statistics taken from gn_acc (see dcb_tap_gemm): ONE streaming pass,
+ * x fp32 or bf16 [G*S, C], y bf16; instance g owns units [g * units_per_instance, (g+1) * units_per_instance).  The
+ * consumer half of the producer-fused GroupNorm.  Replaces basics.py:76-87 / openaimodel3d.py:210-236,255-266. */
+int dcb_group_norm_stream_apply(const void* x, int x_is_bf16, int C, int G, int S, const unsigned long long* gn_acc,
+                                int units_per_instance, float eps, const float* gamma, const float* beta, int silu_act,
+                                void* y_bf16, void* stream);
 /* Same statistics / apply for a bf16 source (block-internal activations the producer GEMM wrote as bf16):
  * single source, C % 8 == 0. */
 int dcb_group_norm_stats_bf16(const void* x, int C, int G, int S, float eps, float* stats, void* workspace,
