@@ -770,6 +770,10 @@ extern "C" int dcb_group_norm_apply_bf16(const void* x, int C, int G, int S, con
 // (a few hundred bytes from L2).  grid = (chunks, G); blockDim = (C / 8) * rpp threads: a thread owns an 8-channel column
 // and walks down the rows of its chunk with U rows in flight (U = 4 fp32 / 8 bf16: >= 128 bytes per thread).
 // ---------------------------------------------------------------------------------------------
+#ifndef DCB_GN_STREAM_U
+#define DCB_GN_STREAM_U 4
+#endif
+constexpr int kStreamU = DCB_GN_STREAM_U;
 template <typename T>
 __global__ void __launch_bounds__(512)
 gn_stream_apply_kernel(const T* __restrict__ x, int C, int S, int rows_per_chunk, const unsigned long long* __restrict__ acc,
@@ -808,7 +812,7 @@ gn_stream_apply_kernel(const T* __restrict__ x, int C, int S, int rows_per_chunk
     }
     const int r0 = chunk * rows_per_chunk;
     const int nrows = min(S, r0 + rows_per_chunk) - r0;
-    constexpr int U = 32 / sizeof(T) / 2;        // 4 (fp32) or 8 (bf16) rows in flight
+    constexpr int U = kStreamU;                  // rows in flight per thread
     const size_t row0 = static_cast<size_t>(n) * S + r0 + my_r;
     const T* src = x + row0 * C + c0;
     const size_t step = static_cast<size_t>(rpp) * C;
@@ -842,9 +846,23 @@ static int launch_gn_stream_apply(const T* x, int C, int G, int S, const unsigne
     int rpp = 288 / O;                              // ~256-320 threads per block
     if (rpp < 1) rpp = 1;
     const int threads = O * rpp;
-    constexpr int U = 32 / sizeof(T) / 2;
-    // enough chunks for ~2 blocks per SM, but at least one full batch of U rows per thread
-    int nch = (2 * num_sms() + G - 1) / G;
+    constexpr int U = kStreamU;
+    // ONE wave of co-resident blocks with equal work (no tail): chunks per instance = resident capacity / G, but at least
+    // one full batch of U rows per thread
+    static int occ_cache[16][3] = {};                  // [device][threads class] resident blocks per SM
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int cls = threads <= 256 ? 0 : (threads <= 320 ? 1 : 2);
+    int occ = (dev >= 0 && dev < 16) ? occ_cache[dev][cls] : 0;
+    if (occ == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_stream_apply_kernel<T>, cls == 0 ? 256 : (cls == 1 ? 320 : 512), 0) !=
+                cudaSuccess || occ < 1)
+            occ = 2;
+        if (dev >= 0 && dev < 16) occ_cache[dev][cls] = occ;
+    }
+    const int capacity = occ * num_sms();
+    int nch = capacity / G;
+    if (nch < 1) nch = 1;
     int rpc = (S + nch - 1) / nch;
     if (rpc < rpp * U) rpc = rpp * U;
     rpc = (rpc + rpp - 1) / rpp * rpp;

@@ -203,6 +203,13 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
                              "warp segments inside one unit (b1*b2 = %d, b3 = %d, mode %d)", p.seg_rows, a->b3, a->gn_unit_mode);
         if (p.seg_rows != 8 && p.seg_rows != 16) p.seg_lw = 32;
     }
+    p.fd_ntiles = FastDiv::make(p.num_n_tiles);
+    p.fd_t1 = FastDiv::make(p.t1);
+    p.fd_t2 = FastDiv::make(p.t2);
+    p.fd_b1 = FastDiv::make(a->b1);
+    p.fd_b2 = FastDiv::make(a->b2);
+    p.fd_rpg = FastDiv::make(a->rows_per_group > 0 ? a->rows_per_group : 1);
+    p.fd_cg = FastDiv::make(a->gn_cg > 0 ? a->gn_cg : 1);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (a->geglu && !obf) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: geglu writes bf16 only");
     if (a->geglu && a->residual != nullptr) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: geglu takes no residual");

@@ -31,6 +31,30 @@
 
 namespace dcb {
 
+// Division by a launch-constant divisor as multiply-high + shift (valid for dividends < 2^31): the tile loops of all
+// 18 warps decompose tile / row indices every tile, and a hardware-less 32-bit division costs ~25 issue slots each.
+struct FastDiv {
+    uint32_t mul, shr, d;
+    __host__ static FastDiv make(uint32_t d) {
+        FastDiv f;
+        f.d = d;
+        if (d <= 1) { f.mul = 0; f.shr = 0; f.d = 1; return f; }
+        uint32_t lg = 0;
+        while ((1u << lg) < d) ++lg;
+        const uint32_t p = 31 + lg;
+        f.mul = static_cast<uint32_t>(((1ull << p) + d - 1) / d);
+        f.shr = p - 32;
+        return f;
+    }
+    __device__ __forceinline__ int div(int n) const {
+        return d == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul) >> shr);
+    }
+    __device__ __forceinline__ void divmod(int n, int& q, int& r) const {
+        q = div(n);
+        r = n - q * static_cast<int>(d);
+    }
+};
+
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 // epilogue groups of 4 warps (one warp per TMEM lane quarter): 4 groups in CTA-pair mode (576 threads), else 2
@@ -88,6 +112,7 @@ struct TapGemmParams {
     uint32_t stage_bytes, res_bytes;
     unsigned long long* gn_acc;    // fused GroupNorm statistics: int64 fixed-point [units][32][2] accumulator, or null
     int gn_cg, gn_unit_mode, seg_rows, seg_lw;
+    FastDiv fd_ntiles, fd_t1, fd_t2, fd_b1, fd_b2, fd_rpg, fd_cg;
 };
 
 // Exact (erf-based) GELU, attention.py:422.  erfc(z) via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, i.e. fp32
@@ -119,7 +144,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 constexpr double kGnFixScale = 1048576.0;          // 2^20
 template <bool kF32, int kSeg>
 __device__ __forceinline__ void gn_acc_from_slot(const uint8_t* slot, int q, int lane, unsigned long long* __restrict__ acc,
-                                                 const long long* unit, int col0, int n_out, int cg) {
+                                                 const long long* unit, int col0, int n_out, const FastDiv cg) {
     constexpr int NSEG = 32 / kSeg;                   // units covered by this warp
     constexpr int IPS = 16 / NSEG;                    // loop iterations (row pairs) per segment
     constexpr int NV = kF32 ? 1 : 2;                  // columns per lane
@@ -130,7 +155,9 @@ __device__ __forceinline__ void gn_acc_from_slot(const uint8_t* slot, int q, int
     for (int sg = 0; sg < NSEG; ++sg) { sx[sg] = 0.f; sq[sg] = 0.f; }
     const int col = col0 + w * NV;
     // a bf16 lane holds two adjacent columns: they are in the same group unless the boundary falls between them
-    const bool split = !kF32 && ((col + 1) % cg == 0);
+    int gid0, pos0;
+    cg.divmod(col, gid0, pos0);                       // group of my (first) column, position inside the group
+    const bool split = !kF32 && (pos0 + 1 == static_cast<int>(cg.d));
     float sx2[NSEG], sq2[NSEG];                       // second column when it starts a new group
 #pragma unroll
     for (int sg = 0; sg < NSEG; ++sg) { sx2[sg] = 0.f; sq2[sg] = 0.f; }
@@ -153,7 +180,7 @@ __device__ __forceinline__ void gn_acc_from_slot(const uint8_t* slot, int q, int
     }
     // group of my (first) column; columns past n_out (ragged N tiles) contribute nothing and join no group
     const bool in0 = col < n_out, in1 = !kF32 && (col + 1 < n_out);
-    const int gid = in0 ? col / cg : -1 - w;
+    const int gid = in0 ? gid0 : -1 - w;
 #pragma unroll
     for (int sg = 0; sg < NSEG; ++sg) {
         float a = sx[sg] + __shfl_xor_sync(0xffffffffu, sx[sg], 16);
@@ -164,24 +191,22 @@ __device__ __forceinline__ void gn_acc_from_slot(const uint8_t* slot, int q, int
             b2 = sq2[sg] + __shfl_xor_sync(0xffffffffu, sq2[sg], 16);
             if (!in1 && !split) { /* second column out of range: its (zero-filled) values were added to a: harmless */ }
         }
-        // segmented reduction over the 16 column lanes (group ids are non-decreasing with the lane)
+        // segmented reduction over the 16 column lanes: lane w + off is in my group iff it stays inside the group's columns
 #pragma unroll
         for (int off = 1; off < 16; off <<= 1) {
             const float ta = __shfl_down_sync(0xffffffffu, a, off, 16);
             const float tb = __shfl_down_sync(0xffffffffu, b, off, 16);
-            const int tg = __shfl_down_sync(0xffffffffu, gid, off, 16);
-            if (w + off < 16 && tg == gid) { a += ta; b += tb; }
+            if (w + off < 16 && pos0 + off * NV < static_cast<int>(cg.d) && col + off * NV < n_out) { a += ta; b += tb; }
         }
-        const int gprev = __shfl_up_sync(0xffffffffu, gid, 1, 16);
-        const bool head = (w == 0) || (gprev != gid);
+        const bool head = in0 && (w == 0 || pos0 < NV);       // first lane of a group inside this chunk
         if (h == 0 && unit[sg] >= 0) {
-            if (head && in0) {
+            if (head) {
                 unsigned long long* d = acc + (unit[sg] * 32 + gid) * 2;
                 atomicAdd(d, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(a) * kGnFixScale)));
                 atomicAdd(d + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(b) * kGnFixScale)));
             }
             if (!kF32 && split && in1) {
-                unsigned long long* d = acc + (unit[sg] * 32 + (col + 1) / cg) * 2;
+                unsigned long long* d = acc + (unit[sg] * 32 + gid0 + 1) * 2;
                 atomicAdd(d, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(a2) * kGnFixScale)));
                 atomicAdd(d + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(b2) * kGnFixScale)));
             }
@@ -227,7 +252,18 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int worker = k2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
     const int nworkers = k2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     const int kblocks = p.ntaps * p.kchunks;
-    auto m_tile_of = [&](int tile) { const int mt = tile / p.num_n_tiles; return k2 ? 2 * mt + static_cast<int>(rank) : mt; };
+    // tile -> (m tile, n tile) and m tile -> box origin (c1, c2, c3), all with multiply-high divisions
+    auto split_tile = [&](int tile, int& m_tile, int& n_tile) {
+        int mt;
+        p.fd_ntiles.divmod(tile, mt, n_tile);
+        m_tile = k2 ? 2 * mt + static_cast<int>(rank) : mt;
+    };
+    auto origin = [&](int m_tile, int& c1, int& c2, int& c3) {
+        int q1, i1, i2, i3;
+        p.fd_t1.divmod(m_tile, q1, i1);
+        p.fd_t2.divmod(q1, i3, i2);
+        c1 = i1 * p.b1; c2 = i2 * p.b2; c3 = i3 * p.b3;
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -261,11 +297,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // warp-uniform state; one elected lane issues, so operands stay in uniform registers)
         uint32_t it = 0;
         for (int tile = worker; tile < num_tiles; tile += nworkers) {
-            const int m_tile = m_tile_of(tile);
-            const int n_tile = tile % p.num_n_tiles;
-            const int i1 = (m_tile % p.t1) * p.b1;
-            const int i2 = ((m_tile / p.t1) % p.t2) * p.b2;
-            const int i3 = (m_tile / (p.t1 * p.t2)) * p.b3;
+            int m_tile, n_tile, i1, i2, i3;
+            split_tile(tile, m_tile, n_tile);
+            origin(m_tile, i1, i2, i3);
             for (int tap = 0; tap < p.ntaps; ++tap) {
                 const int c1 = i1 + p.taps[tap][0], c2 = i2 + p.taps[tap][1], c3 = i3 + p.taps[tap][2];
                 for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
@@ -350,12 +384,12 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint32_t pf_cnt = 0;
         auto prefetch_upto = [&](uint32_t last_cnt) {
             while (pf_cnt <= last_cnt && pf_tile < num_tiles) {
-                const int m_tile = m_tile_of(pf_tile);
-                const int n_tile = pf_tile % p.num_n_tiles;
+                int m_tile, n_tile, c1, c2, c3;
+                split_tile(pf_tile, m_tile, n_tile);
+                origin(m_tile, c1, c2, c3);
                 const int s = pf_cnt & (kSlots - 1);
                 mbar_arrive_expect_tx(&my_rfull[s], p.res_bytes);
-                tma_load_4d(slots + s * kSlotBytes, &tmRes, &my_rfull[s], n_tile * ncols + pf_ci * CW,
-                            (m_tile % p.t1) * p.b1, ((m_tile / p.t1) % p.t2) * p.b2, (m_tile / (p.t1 * p.t2)) * p.b3);
+                tma_load_4d(slots + s * kSlotBytes, &tmRes, &my_rfull[s], n_tile * ncols + pf_ci * CW, c1, c2, c3);
                 ++pf_cnt;
                 pf_ci += kG;
                 if (pf_ci >= nch) { pf_tile += nworkers; pf_ci = grp; }
@@ -363,31 +397,43 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         };
         if (my_nch == 0) pf_tile = num_tiles;
         const uint32_t tempty_addr0 = k2 ? mapa_cluster(smem_u32(&tempty[0]), 0) : 0u;   // leader's ring barriers
+        // box coordinates of this thread's tile row (the same for every tile)
+        int r_1, r_2, r_3;
+        {
+            int rq;
+            p.fd_b1.divmod(r, rq, r_1);
+            p.fd_b2.divmod(rq, r_3, r_2);
+        }
 
         for (int tile = worker; tile < num_tiles; tile += nworkers, ++tc) {
-            const int m_tile = m_tile_of(tile);
-            const int n_tile = tile % p.num_n_tiles;
-            const int o1 = (m_tile % p.t1) * p.b1, o2 = ((m_tile / p.t1) % p.t2) * p.b2;
-            const int o3 = (m_tile / (p.t1 * p.t2)) * p.b3;
+            int m_tile, n_tile, o1, o2, o3;
+            split_tile(tile, m_tile, n_tile);
+            origin(m_tile, o1, o2, o3);
             const float* gb = nullptr;
             const float* res_row = nullptr;        // bf16-out path: residual row read straight from global
             bool row_ok = false;
             if (p.group_bias != nullptr || (!kF32 && p.has_residual) || kCS) {
-                const int g1 = o1 + r % p.b1, g2 = o2 + (r / p.b1) % p.b2, g3 = o3 + r / (p.b1 * p.b2);
+                const int g1 = o1 + r_1, g2 = o2 + r_2, g3 = o3 + r_3;
                 if (r < p.rows_per_tile && g1 < p.D1 && g2 < p.D2 && g3 < p.D3) {
                     row_ok = true;
                     const long long grow = (static_cast<long long>(g3) * p.D2 + g2) * p.D1 + g1;
-                    if (p.group_bias != nullptr) gb = p.group_bias + (grow / p.rows_per_group) * p.ld_group_bias;
+                    if (p.group_bias != nullptr) gb = p.group_bias + p.fd_rpg.div(static_cast<int>(grow)) * p.ld_group_bias;
                     if (!kF32 && p.has_residual) res_row = p.residual + grow * p.ld_residual;
                 }
             }
             // fused GroupNorm statistics: this warp's 32 rows are 32 / seg_lw segments, each inside one unit (-1: no rows)
             long long cs_unit[4] = {-1, -1, -1, -1};
+            bool warp_ragged = false;
             if constexpr (kCS) {
+                warp_ragged = __any_sync(0xffffffffu, !row_ok);
                 const int rb = q * 32;                                    // first tile row of this warp
-                for (int sg = 0; sg < 32 / p.seg_lw; ++sg) {
+                const int nseg = p.seg_lw == 32 ? 1 : (p.seg_lw == 16 ? 2 : 4);
+                for (int sg = 0; sg < nseg; ++sg) {
                     const int row = rb + sg * p.seg_lw;                   // first row of the segment
-                    const int g2 = o2 + (row / p.b1) % p.b2, g3 = o3 + row / (p.b1 * p.b2);
+                    int rq, ru, rg2, rg3;
+                    p.fd_b1.divmod(row, rq, ru);
+                    p.fd_b2.divmod(rq, rg3, rg2);
+                    const int g2 = o2 + rg2, g3 = o3 + rg3;
                     if (row < p.rows_per_tile && g2 < p.D2 && g3 < p.D3)
                         cs_unit[sg] = p.gn_unit_mode ? static_cast<long long>(g3) * p.D2 + g2 : g3;
                 }
@@ -505,10 +551,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     if constexpr (kCS) {
                         // rows outside the tensor are clipped by the TMA store; zero them so that the column sums read
-                        // back from the slot only see real rows
-                        if (!row_ok) {
+                        // back from the slot only see real rows (warp-uniform branch: only ragged tiles pay for it)
+                        if (warp_ragged) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) o[j] = 0.f;
+                            for (int j = 0; j < 16; ++j) o[j] = row_ok ? o[j] : 0.f;
                         }
                     }
                     if constexpr (kF32) {
@@ -542,9 +588,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 if constexpr (kCS) {
                     // the slot now holds the final values of all 128 rows: fold this warp's 32 rows per column
-                    if (p.seg_lw == 32) gn_acc_from_slot<kF32, 32>(slot, q, lane, p.gn_acc, cs_unit, col0, p.N_out, p.gn_cg);
-                    else if (p.seg_lw == 16) gn_acc_from_slot<kF32, 16>(slot, q, lane, p.gn_acc, cs_unit, col0, p.N_out, p.gn_cg);
-                    else gn_acc_from_slot<kF32, 8>(slot, q, lane, p.gn_acc, cs_unit, col0, p.N_out, p.gn_cg);
+                    if (p.seg_lw == 32) gn_acc_from_slot<kF32, 32>(slot, q, lane, p.gn_acc, cs_unit, col0, p.N_out, p.fd_cg);
+                    else if (p.seg_lw == 16) gn_acc_from_slot<kF32, 16>(slot, q, lane, p.gn_acc, cs_unit, col0, p.N_out, p.fd_cg);
+                    else gn_acc_from_slot<kF32, 8>(slot, q, lane, p.gn_acc, cs_unit, col0, p.N_out, p.fd_cg);
                     // the leader's next residual prefetch (TMA write into a slot) must not overtake these reads
                     if (tma_res) named_bar_sync(bar_id, 128);
                 }
