@@ -41,6 +41,19 @@ def load_peaks():
     return dict(tflops=1400.0, burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def load_traffic():
+    """roofline.traffic: DRAM bytes per launch of the dominant kernel from the committed ncu captures (null if absent)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        return {"traffic": None}
+    d = json.load(open(p))
+    w, c = d["gemm_res"], d["gemm_conv"]
+    return {"traffic": w["traffic"], "traffic_algorithmic": w["traffic_algorithmic"],
+            "traffic_unit": "bytes/launch, " + w["what"] + " (" + w["capture"] + ")",
+            "traffic_other_shape": {"what": c["what"], "traffic": c["traffic"], "traffic_algorithmic": c["traffic_algorithmic"],
+                                    "capture": c["capture"]}}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -321,6 +334,119 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------- N > 1 extras
+def run_shard_check(dev, rank, world):
+    """Frame-sharded forward of a tiny UNet (every temporal block behind an all-to-all, 5-D GroupNorm sums all-reduced)
+    against the same forward on one GPU, in the fp32 parity mode where no bf16 rounding noise hides a wrong transpose:
+    {rel_l2, identical (all ranks hold the same bits), frames}."""
+    import torch.distributed as dist
+    from dynamicrafter_b200.lvdm.modules.networks.openaimodel3d import UNetModel
+    from dynamicrafter_b200.parallel import FrameShard
+    from dynamicrafter_b200.precision import use_precision
+    from dynamicrafter_b200.synth import synth_state_dict, synth_input
+    cfg = dict(in_channels=8, out_channels=4, model_channels=64, attention_resolutions=[1, 2], num_res_blocks=1,
+               channel_mult=[1, 2], num_head_channels=64, context_dim=64, use_linear=True, temporal_length=16,
+               use_relative_position=False, temporal_conv=True, temporal_attention=True, image_cross_attention=True,
+               fs_condition=True, default_fs=10)
+    T, h, w = 16, 8, 8
+    m = UNetModel(**cfg)
+    m.load_state_dict(synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, SEED))
+    m = m.to(dev).eval()
+    x = synth_input("x", (2, 8, T, h, w), SEED).to(dev)
+    ctx = synth_input("context", (2, 77 + 16 * T, 64), SEED).to(dev)
+    ts = torch.tensor([500, 493], dtype=torch.long, device=dev)
+    res = {}
+    for mode in ("fp32", "bf16"):
+        with use_precision(mode):
+            m.frame_shard = None
+            y1 = m(x, ts, context=ctx)
+            m.frame_shard = FrameShard()
+            yN = m(x, ts, context=ctx)
+            torch.cuda.synchronize()
+        e = float((yN.double() - y1.double()).norm() / y1.double().norm())
+        same = [torch.empty_like(yN) for _ in range(world)]
+        dist.all_gather(same, yN)
+        res[mode] = {"rel_l2_vs_single_gpu": e, "identical_on_all_ranks": all(torch.equal(t, same[0]) for t in same)}
+    m.frame_shard = None
+    res["frames_per_rank"] = T // world
+    res["pass"] = bool(res["fp32"]["rel_l2_vs_single_gpu"] < 1e-4 and res["fp32"]["identical_on_all_ranks"]
+                       and res["bf16"]["rel_l2_vs_single_gpu"] < 2.5e-2 and res["bf16"]["identical_on_all_ranks"])
+    return res
+
+
+def run_strong(host, dev, rank, world, args):
+    """ONE 576x1024 video (BASELINE.json configs[3], latent 72x128) over all GPUs: frames sharded over the ranks (x the
+    two guidance branches from 4 GPUs on), against the same step on one GPU.  UNet + update only, eager sharded mode."""
+    import torch.distributed as dist
+    from dynamicrafter_b200.configs import SAMPLER
+    from dynamicrafter_b200.lvdm.models.samplers.ddim import DDIMSampler
+    from dynamicrafter_b200.parallel import FrameShard, BranchShard
+    from dynamicrafter_b200.synth import synth_input
+    B, T, h, w = 1, 16, 72, 128
+    sm = SAMPLER["1024"]
+    x0 = synth_input("x_T", (B, 4, T, h, w), SEED).to(dev)
+    concat = synth_input("concat", (B, 4, T, h, w), SEED).to(dev)
+    cond = {"c_crossattn": [synth_input("cond", (B, 77 + 16 * T, 1024), SEED).to(dev)], "c_concat": [concat]}
+    uc = {"c_crossattn": [synth_input("uncond", (B, 77 + 16 * T, 1024), SEED).to(dev)], "c_concat": [concat]}
+    fs = torch.tensor([sm["fs"]] * B, dtype=torch.long, device=dev)
+
+    def timed(smp, n_warm=2, n=3):
+        smp.make_schedule(sm["S"], ddim_discretize=sm["timestep_spacing"], ddim_eta=sm["eta"], verbose=False)
+        steps = list(reversed(list(smp.ddim_timesteps)))
+
+        def one(x, i):
+            ts = torch.full((B,), int(steps[i]), device=dev, dtype=torch.long)
+            return smp.p_sample_ddim(x, cond, ts, index=len(steps) - i - 1, unconditional_guidance_scale=sm["cfg"],
+                                     unconditional_conditioning=uc, fs=fs, guidance_rescale=sm["guidance_rescale"])[0]
+        torch.manual_seed(SEED)
+        x = x0.clone()
+        for i in range(n_warm):
+            x = one(x, i)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            x = one(x, n_warm + i)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert torch.isfinite(x).all()
+        return float(t)
+
+    graph = host.unet.use_cuda_graph
+    ms1 = timed(DDIMSampler(host))                               # every rank runs the whole video on its own GPU
+    host.unet.__dict__.pop("_graphs", None)                      # free the 1024-shaped single-GPU graph
+    torch.cuda.empty_cache()
+    nf, fgroup, bgroup = world, None, None
+    if world >= 4 and world % 2 == 0:                            # rank r: guidance branch r % 2, frame shard r // 2
+        nf = world // 2
+        for br in range(2):
+            g = dist.new_group([r for r in range(world) if r % 2 == br])
+            if rank % 2 == br:
+                fgroup = g
+        for fi in range(nf):
+            g = dist.new_group([2 * fi, 2 * fi + 1])
+            if rank // 2 == fi:
+                bgroup = g
+    smp = DDIMSampler(host)
+    host.unet.frame_shard = FrameShard(fgroup)
+    if bgroup is not None:
+        smp.branch_shard = BranchShard(bgroup)
+    try:
+        msN = timed(smp)
+    finally:
+        host.unet.frame_shard = None
+        host.unet.use_cuda_graph = graph
+    return {"workload": "ONE 576x1024x16f video (latent 72x128), CFG DDIM step, UNet + update",
+            "mode": f"frames sharded x{nf}" + (" x 2 guidance branches" if bgroup is not None else ""),
+            "ms_per_step_1gpu": round(ms1, 2), "ms_per_step": round(msN, 2), "speedup": round(ms1 / msN, 3),
+            "n_gpus": world, "scaling": "strong", "timing": "CUDA events, max over ranks, 2 warm-up + 3 timed steps"}
+
+
 # ------------------------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
@@ -338,6 +464,8 @@ def main():
     ap.add_argument("--branch-shard", action="store_true",
                     help="N=2: ONE video, cond branch on rank 0 and uncond on rank 1, predictions all-gathered every step "
                          "(strong scaling of single-video latency)")
+    ap.add_argument("--no-strong", action="store_true", help="N>1: skip the sharded-vs-single check and the strong-scaling "
+                    "(one 576x1024 video over all GPUs) measurement appended to the line")
     ap.add_argument("--frame-shard", action="store_true",
                     help="N>1: ONE video, its 16 frames sharded over the ranks (all-to-all around the temporal blocks); "
                          "strong scaling of single-video latency (BASELINE.json configs[3])")
@@ -492,11 +620,11 @@ def main():
     roofline = {"bound": "tensor", "kernel": "tap_gemm_kernel (tcgen05 implicit GEMM: linear + conv3x3 + temporal conv)",
                 "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": round(achieved / peaks["tflops"], 4),
-                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from the committed
-                # `ncu --set full` capture (profiles/r01b_tap_gemm_pair_160_f32_raw.csv): the 81920x640x5760
-                # conv-as-GEMM, fp32 out; algorithmic bytes of that launch = A 943.7 MB + W 7.4 MB + out 209.7 MB
-                "traffic": 1.240e9, "traffic_unit": "bytes/launch (captured 81920x640x5760 launch)",
-                "traffic_algorithmic": 1.161e9, "peak_source": peaks["source"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel, from the committed
+                # `ncu --set full` captures of the current code (profiles/r02_traffic.json: the worst shape of the
+                # step -- the HBM-bound 81920x320x320 + fp32 residual -- and a typical 3x3 conv)
+                **load_traffic(),
+                "peak_source": peaks["source"],
                 "launches_per_step": n_gemm, "avg_launch_us": round(gemm_ms * 1e3 / max(n_gemm, 1), 2),
                 "kernel_share_of_step": round(gemm_ms / max(sum(by.values()), 1e-9), 4),
                 "whole_step_tflops": round(step_tflop / (ms_per_step * 1e-3), 1),
@@ -534,6 +662,16 @@ def main():
             frames = host.decode_first_stage(samples, frames_per_call=8)
         torch.cuda.synchronize()
         t_d = time.perf_counter() - t1
+        # VAE decode on its own: CUDA events around 3 repeated warm decodes of this rank's frames
+        dz = (samples[:, :, f0:f1] if (fshard or bshard) else samples).contiguous()
+        de0, de1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        de0.record()
+        for _ in range(3):
+            host.decode_first_stage(dz, frames_per_call=8)
+        de1.record()
+        torch.cuda.synchronize()
+        dec_ms = de0.elapsed_time(de1) / 3
+        dec_tflop = VAE_TFLOP[args.config] * dz.shape[0] * dz.shape[2] / 16.0
         tv = torch.tensor([t_s + t_d, t_s, t_d], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tv, op=dist.ReduceOp.MAX)
@@ -541,7 +679,19 @@ def main():
         video = {"s_per_video": round(float(tv[0]), 3), "sample_s": round(float(tv[1]), 3), "decode_s": round(float(tv[2]), 3),
                  "videos_per_s_all_gpus": round(units / float(tv[0]), 4), "tflops": round(vid_tflop / float(tv[0]), 1),
                  "frac_of_peak": round(vid_tflop / float(tv[0]) / peaks["tflops"] / (world if (fshard or bshard) else 1), 4),
-                 "finite": bool(torch.isfinite(frames).all())}
+                 "finite": bool(torch.isfinite(frames).all()),
+                 "vae_decode": {"ms": round(dec_ms, 2), "frames": int(dz.shape[0] * dz.shape[2]), "tflops": round(dec_tflop / (dec_ms * 1e-3), 1),
+                                "frac_of_peak": round(dec_tflop / (dec_ms * 1e-3) / peaks["tflops"], 4),
+                                "timing": "CUDA events, mean of 3 warm decodes (conv + GroupNorm + d=512 attention)"}}
+
+    # ---------------- N > 1: sharded-vs-single check on a tiny UNet and the strong-scaling (single video) numbers
+    shard_check = strong = None
+    if world > 1 and not (fshard or bshard) and not args.no_strong:
+        try:
+            shard_check = run_shard_check(dev, rank, world)
+            strong = run_strong(host, dev, rank, world, args)
+        except Exception as exc:                     # never lose the headline line to the auxiliary measurements
+            strong = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---------------- CPU baseline (rank 0, N=1): the unmodified reference (oracle/_ref) on a bounded sample
     cpu = None
@@ -585,6 +735,10 @@ def main():
                 "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
                 "clocks": clk, "roofline": roofline, "breakdown_ms": {k: round(v, 3) for k, v in sorted(by.items())},
                 "video": video, "cpu_baseline": cpu}
+        if shard_check is not None:
+            line["shard_check"] = shard_check
+        if strong is not None:
+            line["strong"] = strong
         print(json.dumps(line), flush=True)
     if world > 1:
         from dynamicrafter_b200.lvdm import _packing

@@ -28,6 +28,8 @@ class TapGemmArgs(ctypes.Structure):
         ("residual", c_vp), ("ld_residual", c_int), ("geglu", c_int),
         ("out_f32", c_vp), ("out_bf16", c_vp), ("ld_out", c_int), ("out_scale", c_f),
         ("gn_acc", c_vp), ("gn_cg", c_int), ("gn_unit_mode", c_int),
+        ("ln_acc", c_vp), ("ln_x_bf16", c_vp), ("ld_ln_x", c_int), ("ln_channels", c_int),
+        ("ln_colsum", c_vp), ("ln_eps", c_f), ("reserved0", c_int),
     ]
 
 

@@ -14,7 +14,10 @@ namespace dcb {
 
 // statistics-emitting instantiations live in their own translation unit (tap_gemm_cs.cu): the plain kernels carry
 // no code or register cost for the fused GroupNorm statistics
-int tap_gemm_launch_cs(int bn, bool out_bf16, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB,
+int tap_gemm_launch_cs(int bn, bool out_bf16, bool pair, const CUtensorMap& tmA, const CUtensorMap* tmB,
+                       const CUtensorMap& tmOut, const CUtensorMap& tmRes, TapGemmParams& p, cudaStream_t s);
+
+int tap_gemm_launch_ln(int bn, bool out_bf16, bool pair, const CUtensorMap& tmA, const CUtensorMap* tmB,
                        const CUtensorMap& tmOut, const CUtensorMap& tmRes, TapGemmParams& p, cudaStream_t s);
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -95,8 +98,20 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
         // wider N tiles cut shared-memory bytes per MMA (the 1-CTA limiter) but need enough tiles to fill the SMs
         const long long m_tiles = static_cast<long long>((a->D1 + a->b1 - 1) / a->b1) * ((a->D2 + a->b2 - 1) / a->b2) *
                                   ((a->D3 + a->b3 - 1) / a->b3);
+        // 256-wide tiles are the only ones whose operand fill (16 KB of A + 64 B per column per 64-deep stage, against
+        // ~64 B/clk of L2 -> SM bandwidth per SM) keeps up with the tensor pipe.  N need not be a multiple of 256: a ragged
+        // last tile runs a narrower UMMA and stages fewer B rows.  Measured (tools/bench_shapes.py, r02e): N = 960 / 1920
+        // gain 11-13 %, N = 640 (256 + 256 + 128) is neutral to -4 %, N = 320 (256 + 64) loses: the narrow tile still pays
+        // the full A stage.  Hence: at least three full tiles and a last tile of >= 128 columns.
+        // DCB_GEMM_RAGGED256=0 restores the N % 256 rule, DCB_GEMM_RAGGED_MIN / _MIN_N move the thresholds.
+        static int ragged = -1, ragged_min = -1, ragged_min_n = -1;
+        if (ragged < 0) { const char* e = getenv("DCB_GEMM_RAGGED256"); ragged = e ? atoi(e) : 1; }
+        if (ragged_min < 0) { const char* e = getenv("DCB_GEMM_RAGGED_MIN"); ragged_min = e ? atoi(e) : 128; }
+        if (ragged_min_n < 0) { const char* e = getenv("DCB_GEMM_RAGGED_MIN_N"); ragged_min_n = e ? atoi(e) : 768; }
+        const long long n256 = (a->N + 255) / 256;
+        const bool ragged_ok = ragged && a->N >= ragged_min_n && (a->N % 256) >= ragged_min;
         if (a->geglu) bn = (a->N % 256 == 0) ? 256 : 128;
-        else if (a->N % 256 == 0 && m_tiles * (a->N / 256) >= 1LL * num_sms()) bn = 256;   // >= one round of CTA pairs
+        else if ((a->N % 256 == 0 || ragged_ok) && m_tiles * n256 >= 1LL * num_sms()) bn = 256;   // >= one round of CTA pairs
         else bn = (a->N % 160 == 0) ? 160 : 128;
     }
     if (bn != 128 && bn != 160 && bn != 256) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: block_n must be 128, 160 or 256");
@@ -127,7 +142,8 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
         return set_error(DCB_ERR_INVALID, "tap_gemm: residual needs a 16-byte aligned base and row pitch");
     const int n_out = a->geglu ? a->N / 2 : a->N;
 
-    CUtensorMap tmA, tmB, tmOut, tmRes;
+    CUtensorMap tmA, tmBs[2], tmOut, tmRes;
+    CUtensorMap& tmB = tmBs[0];
     {
         const uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->A1, (uint64_t)a->A2, (uint64_t)a->A3};
         const uint64_t str[4] = {1, (uint64_t)a->a_s1, (uint64_t)a->a_s2, (uint64_t)a->a_s3};
@@ -143,6 +159,15 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
         const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)(pair ? bn / 2 : bn)};
         int rc = encode_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, CU_TENSOR_MAP_SWIZZLE_128B, a->w, 2, dims, str, box,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (rc) return rc;
+        // the (possibly narrow) last N tile: same layout, fewer rows per box (mirrors launch<>: n_eff = valid columns
+        // rounded up to 32, full width for GEGLU)
+        const int rem = a->N - ((a->N + bn - 1) / bn - 1) * bn;
+        int n_eff = (rem + 31) / 32 * 32;
+        if (n_eff > bn || a->geglu) n_eff = bn;
+        const uint32_t box2[2] = {(uint32_t)kBlockK, (uint32_t)(pair ? n_eff / 2 : n_eff)};
+        rc = encode_map(&tmBs[1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, CU_TENSOR_MAP_SWIZZLE_128B, a->w, 2, dims, str, box2,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
     }
     {
@@ -203,7 +228,6 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
                              "warp segments inside one unit (b1*b2 = %d, b3 = %d, mode %d)", p.seg_rows, a->b3, a->gn_unit_mode);
         if (p.seg_rows != 8 && p.seg_rows != 16) p.seg_lw = 32;
     }
-    p.fd_ntiles = FastDiv::make(p.num_n_tiles);
     p.fd_t1 = FastDiv::make(p.t1);
     p.fd_t2 = FastDiv::make(p.t2);
     p.fd_b1 = FastDiv::make(a->b1);
@@ -213,8 +237,29 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (a->geglu && !obf) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: geglu writes bf16 only");
     if (a->geglu && a->residual != nullptr) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: geglu takes no residual");
-    if (a->gn_acc != nullptr) return tap_gemm_launch_cs(bn, obf, pair, tmA, tmB, tmOut, tmRes, p, s);
-    return launch_all<false>(bn, obf, pair, tmA, tmB, tmOut, tmRes, p, s);
+    p.ln_acc = a->ln_acc;
+    p.ln_x = static_cast<__nv_bfloat16*>(a->ln_x_bf16);
+    p.ld_ln_x = a->ld_ln_x;
+    p.ln_colsum = a->ln_colsum;
+    p.ln_inv_c = a->ln_channels > 0 ? 1.0f / static_cast<float>(a->ln_channels) : 0.f;
+    p.ln_eps = a->ln_eps;
+    if (a->ln_acc != nullptr) {
+        if (a->gn_acc != nullptr || (reinterpret_cast<uintptr_t>(a->ln_acc) & 15))
+            return set_error(DCB_ERR_INVALID, "tap_gemm: LayerNorm folding excludes GroupNorm statistics; ln_acc must be 16-byte aligned");
+        if (!obf) {                                   // producer
+            if (a->ln_x_bf16 == nullptr || (reinterpret_cast<uintptr_t>(a->ln_x_bf16) & 15) || a->ld_ln_x % 8 != 0 ||
+                a->ld_ln_x < n_out)
+                return set_error(DCB_ERR_INVALID, "tap_gemm: LayerNorm producer needs a 16-byte aligned bf16 copy buffer");
+        } else {                                      // consumer
+            if (a->ln_colsum == nullptr || a->bias == nullptr || a->ln_channels < 1 || a->residual != nullptr ||
+                a->group_bias != nullptr || a->out_scale != 1.0f)
+                return set_error(DCB_ERR_INVALID, "tap_gemm: LayerNorm consumer needs ln_colsum, the folded bias and ln_channels, "
+                                 "and takes no residual / group bias / out_scale");
+        }
+        return tap_gemm_launch_ln(bn, obf, pair, tmA, tmBs, tmOut, tmRes, p, s);
+    }
+    if (a->gn_acc != nullptr) return tap_gemm_launch_cs(bn, obf, pair, tmA, tmBs, tmOut, tmRes, p, s);
+    return launch_all<0>(bn, obf, pair, tmA, tmBs, tmOut, tmRes, p, s);
 }
 
 #ifdef DCB_TRACE

@@ -4,9 +4,9 @@
 
 namespace dcb {
 
-int tap_gemm_launch_cs(int bn, bool out_bf16, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB,
+int tap_gemm_launch_cs(int bn, bool out_bf16, bool pair, const CUtensorMap& tmA, const CUtensorMap* tmB,
                        const CUtensorMap& tmOut, const CUtensorMap& tmRes, TapGemmParams& p, cudaStream_t s) {
-    return launch_all<true>(bn, out_bf16, pair, tmA, tmB, tmOut, tmRes, p, s);
+    return launch_all<1>(bn, out_bf16, pair, tmA, tmB, tmOut, tmRes, p, s);
 }
 
 }  // namespace dcb

@@ -112,7 +112,24 @@ struct TapGemmParams {
     uint32_t stage_bytes, res_bytes;
     unsigned long long* gn_acc;    // fused GroupNorm statistics: int64 fixed-point [units][32][2] accumulator, or null
     int gn_cg, gn_unit_mode, seg_rows, seg_lw;
-    FastDiv fd_ntiles, fd_t1, fd_t2, fd_b1, fd_b2, fd_rpg, fd_cg;
+    // LayerNorm folding (see dcb200.h): producer = fp32-out kernel that also writes a bf16 copy + per-row (sum, sumsq);
+    // consumer = bf16-out kernel whose epilogue applies rstd * acc - rstd * mean * colsum[n] + bias[n]
+    unsigned long long* ln_acc;
+    __nv_bfloat16* ln_x;
+    int ld_ln_x;
+    const float* ln_colsum;
+    float ln_inv_c, ln_eps;
+    // ragged last N tile: the UMMA runs at N = n_eff_last (the valid columns rounded up to 32) and each CTA stages only
+    // b_rows_last rows of B (second tensor map), so a partial tile costs tensor time and fill bandwidth for what it holds
+    uint32_t idesc_last, stage_bytes_last;
+    int b_rows_last;
+    // work order.  sched_wave = 0 (default): N fastest, tile = m item * NT + n tile -- neighbouring workers share an A
+    // tile at the same time.  sched_wave = 1 (opt-in, DCB_GEMM_ORDER=1): groups of `sched_w` consecutive M items, N tile
+    // major inside a group, so one worker walks over all N tiles of ONE M item and every worker of a wave runs the same
+    // N tile (equal cost per wave with a narrow last tile); measured slower, kept for experiments
+    int sched_w, sched_full_groups, sched_wave;
+    FastDiv fd_gsz, fd_w, fd_r, fd_ntiles;
+    FastDiv fd_t1, fd_t2, fd_b1, fd_b2, fd_rpg, fd_cg;
 };
 
 // Exact (erf-based) GELU, attention.py:422.  erfc(z) via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, i.e. fp32
@@ -142,6 +159,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // the result to the per-(unit, group) int64 fixed-point accumulator (integer atomics commute: bitwise reproducible).
 // Rows that share a unit: kSeg = 32 (whole warp), 16 or 8 consecutive rows -> 1, 2 or 4 units per warp.
 constexpr double kGnFixScale = 1048576.0;          // 2^20
+constexpr float kLnFixSum = 16777216.0f;           // 2^24: per-row sum
+constexpr float kLnFixSq = 268435456.0f;           // 2^28: per-row sum of squares
 template <bool kF32, int kSeg>
 __device__ __forceinline__ void gn_acc_from_slot(const uint8_t* slot, int q, int lane, unsigned long long* __restrict__ acc,
                                                  const long long* unit, int col0, int n_out, const FastDiv cg) {
@@ -214,11 +233,15 @@ __device__ __forceinline__ void gn_acc_from_slot(const uint8_t* slot, int q, int
     }
 }
 
-template <int BN, bool kF32, bool k2, bool kCS>
+// kMode: 0 plain, 1 fused GroupNorm statistics of the output, 2 LayerNorm folding (producer if kF32, else consumer)
+template <int BN, bool kF32, bool k2, int kMode>
 __global__ void __launch_bounds__(Threads<k2>::value, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
-                const TapGemmParams p) {
+                const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut,
+                const __grid_constant__ CUtensorMap tmRes, const TapGemmParams p) {
+    constexpr bool kCS = kMode == 1;
+    constexpr bool kLNP = kMode == 2 && kF32;             // LayerNorm producer: bf16 copy + per-row statistics
+    constexpr bool kLNC = kMode == 2 && !kF32;            // LayerNorm consumer: per-row scale / shift in the epilogue
     constexpr int kStages = StageCount<BN, k2>::value;
     constexpr int kSlots = EpiSlots<k2>::value;
     constexpr int kG = EpiGroups<k2>::value;
@@ -255,7 +278,14 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // tile -> (m tile, n tile) and m tile -> box origin (c1, c2, c3), all with multiply-high divisions
     auto split_tile = [&](int tile, int& m_tile, int& n_tile) {
         int mt;
-        p.fd_ntiles.divmod(tile, mt, n_tile);
+        if (p.sched_wave) {
+            int g, u, ml;
+            p.fd_gsz.divmod(tile, g, u);
+            if (g < p.sched_full_groups) p.fd_w.divmod(u, n_tile, ml); else p.fd_r.divmod(u, n_tile, ml);
+            mt = g * p.sched_w + ml;
+        } else {
+            p.fd_ntiles.divmod(tile, mt, n_tile);
+        }
         m_tile = k2 ? 2 * mt + static_cast<int>(rank) : mt;
     };
     auto origin = [&](int m_tile, int& c1, int& c2, int& c3) {
@@ -268,6 +298,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmB2);
         tma_prefetch_desc(&tmOut);
         if (p.has_residual) tma_prefetch_desc(&tmRes);
         for (int s = 0; s < kStages; ++s) {
@@ -300,6 +331,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int m_tile, n_tile, i1, i2, i3;
             split_tile(tile, m_tile, n_tile);
             origin(m_tile, i1, i2, i3);
+            const bool last_n = n_tile == p.num_n_tiles - 1;
+            const CUtensorMap* tb = last_n ? &tmB2 : &tmB;
+            const uint32_t tx_bytes = last_n ? p.stage_bytes_last : p.stage_bytes;
+            const int b_row0 = n_tile * BN + (k2 ? static_cast<int>(rank) * (last_n ? p.b_rows_last : kBRows) : 0);
             for (int tap = 0; tap < p.ntaps; ++tap) {
                 const int c1 = i1 + p.taps[tap][0], c2 = i2 + p.taps[tap][1], c3 = i3 + p.taps[tap][2];
                 for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
@@ -310,14 +345,13 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         uint8_t* sa = smem + s * kStageBytes;
                         if constexpr (k2) {
                             const uint32_t lfull = mapa_cluster(smem_u32(&full[s]), 0);      // leader's barrier
-                            mbar_arrive_expect_tx_cluster(lfull, p.stage_bytes);
+                            mbar_arrive_expect_tx_cluster(lfull, tx_bytes);
                             tma_load_4d_pair(sa, &tmA, lfull, kc * kBlockK, c1, c2, c3);
-                            tma_load_2d_pair(sa + kABytes, &tmB, lfull, (tap * p.kchunks + kc) * kBlockK,
-                                             n_tile * BN + static_cast<int>(rank) * kBRows);
+                            tma_load_2d_pair(sa + kABytes, tb, lfull, (tap * p.kchunks + kc) * kBlockK, b_row0);
                         } else {
-                            mbar_arrive_expect_tx(&full[s], p.stage_bytes);
+                            mbar_arrive_expect_tx(&full[s], tx_bytes);
                             tma_load_4d(sa, &tmA, &full[s], kc * kBlockK, c1, c2, c3);
-                            tma_load_2d(sa + kABytes, &tmB, &full[s], (tap * p.kchunks + kc) * kBlockK, n_tile * BN);
+                            tma_load_2d(sa + kABytes, tb, &full[s], (tap * p.kchunks + kc) * kBlockK, b_row0);
                         }
                     }
                     __syncwarp();
@@ -334,6 +368,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tc_fence_after();
                 if (lane == 0) DCB_TR(1, 2, tc);
                 const uint32_t d_tmem = tmem_base + a * kAccStride;
+                int m_tile_, n_tile_;
+                split_tile(tile, m_tile_, n_tile_);
+                const uint32_t idesc = (n_tile_ == p.num_n_tiles - 1) ? p.idesc_last : kIdesc;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                     mbar_wait(&full[s], ph);
@@ -346,8 +383,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
                             // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
-                            if constexpr (k2) umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
-                            else umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+                            if constexpr (k2) umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                            else umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                         }
                         // frees the smem stage (in both CTAs of a pair) when these MMAs retire
                         if constexpr (k2) umma_commit_pair(&empty[s]); else umma_commit(&empty[s]);
@@ -372,7 +409,11 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint64_t* my_rfull = rfull + grp * kSlots;
         const int ncols = p.geglu ? BN / 2 : BN;   // output columns per tile
         const int nch = ncols / CW;
-        const int my_nch = grp < nch ? (nch - grp + kG - 1) / kG : 0;    // chunks grp, grp+kG, ...
+        // chunks of a tile that hold real columns (the last N tile may be narrow): this group takes grp, grp+kG, ...
+        auto nch_of = [&](int n_tile) {
+            const int vc = p.N_out - n_tile * ncols;
+            return vc >= ncols ? nch : (vc + CW - 1) / CW;
+        };
         const bool tma_res = kF32 && p.has_residual;          // fp32 out: residual chunk prefetched in place by TMA
         const int swz = (r >> 1) & 3;              // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
         uint8_t* const row_base = nullptr;
@@ -386,16 +427,15 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             while (pf_cnt <= last_cnt && pf_tile < num_tiles) {
                 int m_tile, n_tile, c1, c2, c3;
                 split_tile(pf_tile, m_tile, n_tile);
+                if (pf_ci >= nch_of(n_tile)) { pf_tile += nworkers; pf_ci = grp; continue; }
                 origin(m_tile, c1, c2, c3);
                 const int s = pf_cnt & (kSlots - 1);
                 mbar_arrive_expect_tx(&my_rfull[s], p.res_bytes);
                 tma_load_4d(slots + s * kSlotBytes, &tmRes, &my_rfull[s], n_tile * ncols + pf_ci * CW, c1, c2, c3);
                 ++pf_cnt;
                 pf_ci += kG;
-                if (pf_ci >= nch) { pf_tile += nworkers; pf_ci = grp; }
             }
         };
-        if (my_nch == 0) pf_tile = num_tiles;
         const uint32_t tempty_addr0 = k2 ? mapa_cluster(smem_u32(&tempty[0]), 0) : 0u;   // leader's ring barriers
         // box coordinates of this thread's tile row (the same for every tile)
         int r_1, r_2, r_3;
@@ -412,11 +452,13 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const float* gb = nullptr;
             const float* res_row = nullptr;        // bf16-out path: residual row read straight from global
             bool row_ok = false;
-            if (p.group_bias != nullptr || (!kF32 && p.has_residual) || kCS) {
+            long long grow_ = 0;
+            if (p.group_bias != nullptr || (!kF32 && p.has_residual) || kCS || kMode == 2) {
                 const int g1 = o1 + r_1, g2 = o2 + r_2, g3 = o3 + r_3;
                 if (r < p.rows_per_tile && g1 < p.D1 && g2 < p.D2 && g3 < p.D3) {
                     row_ok = true;
                     const long long grow = (static_cast<long long>(g3) * p.D2 + g2) * p.D1 + g1;
+                    grow_ = grow;
                     if (p.group_bias != nullptr) gb = p.group_bias + p.fd_rpg.div(static_cast<int>(grow)) * p.ld_group_bias;
                     if (!kF32 && p.has_residual) res_row = p.residual + grow * p.ld_residual;
                 }
@@ -441,8 +483,20 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
             bool acc_ready = false;
             const uint32_t t_row = tmem_base + a * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+            float ln_ra = 0.f, ln_rb = 0.f;            // consumer: rstd and -rstd * mean of this thread's row
+            float ln_s = 0.f, ln_q = 0.f;              // producer: sum / sum of squares of the row's columns seen here
+            if constexpr (kLNC) {
+                if (row_ok) {
+                    const longlong2 sq = __ldg(reinterpret_cast<const longlong2*>(p.ln_acc + 2 * grow_));
+                    const float mean = static_cast<float>(sq.x) * (1.0f / kLnFixSum) * p.ln_inv_c;
+                    const float ex2 = static_cast<float>(sq.y) * (1.0f / kLnFixSq) * p.ln_inv_c;
+                    ln_ra = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + p.ln_eps);
+                    ln_rb = -ln_ra * mean;
+                }
+            }
 
-            for (int ci = grp; ci < nch; ci += kG, ++cnt) {
+            const int nch_t = nch_of(n_tile);
+            for (int ci = grp; ci < nch_t; ci += kG, ++cnt) {
                 const int s = cnt & (kSlots - 1);
                 uint8_t* slot = slots + s * kSlotBytes;
                 const int col0 = n_tile * ncols + ci * CW;              // first output column of this chunk
@@ -489,6 +543,23 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         tmem_ld_wait();
                         const int wn = n_tile * BN + ci * CW + hf * 16;   // packed weight column of the value half
                         const float s_ = p.out_scale;
+                        if constexpr (kLNC) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + wn + j));
+                                const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + wn + BN / 2 + j));
+                                const float4 sv = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + wn + j));
+                                const float4 sg = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + wn + BN / 2 + j));
+                                o[j] = fmaf(__uint_as_float(v[j]), ln_ra, fmaf(ln_rb, sv.x, bv.x)) *
+                                       gelu_erf(fmaf(__uint_as_float(g[j]), ln_ra, fmaf(ln_rb, sg.x, bg.x)));
+                                o[j + 1] = fmaf(__uint_as_float(v[j + 1]), ln_ra, fmaf(ln_rb, sv.y, bv.y)) *
+                                           gelu_erf(fmaf(__uint_as_float(g[j + 1]), ln_ra, fmaf(ln_rb, sg.y, bg.y)));
+                                o[j + 2] = fmaf(__uint_as_float(v[j + 2]), ln_ra, fmaf(ln_rb, sv.z, bv.z)) *
+                                           gelu_erf(fmaf(__uint_as_float(g[j + 2]), ln_ra, fmaf(ln_rb, sg.z, bg.z)));
+                                o[j + 3] = fmaf(__uint_as_float(v[j + 3]), ln_ra, fmaf(ln_rb, sv.w, bv.w)) *
+                                           gelu_erf(fmaf(__uint_as_float(g[j + 3]), ln_ra, fmaf(ln_rb, sg.w, bg.w)));
+                            }
+                        } else
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
                             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
@@ -500,6 +571,24 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             o[j + 1] = (__uint_as_float(v[j + 1]) * s_ + bv.y) * gelu_erf(__uint_as_float(g[j + 1]) * s_ + bg.y);
                             o[j + 2] = (__uint_as_float(v[j + 2]) * s_ + bv.z) * gelu_erf(__uint_as_float(g[j + 2]) * s_ + bg.z);
                             o[j + 3] = (__uint_as_float(v[j + 3]) * s_ + bv.w) * gelu_erf(__uint_as_float(g[j + 3]) * s_ + bg.w);
+                        }
+                    } else if constexpr (kLNC) {
+                        tmem_ld_wait();
+                        if (cb + 16 <= p.N_out) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + cb + j));
+                                const float4 ss = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + cb + j));
+                                o[j] = fmaf(__uint_as_float(v[j]), ln_ra, fmaf(ln_rb, ss.x, bb.x));
+                                o[j + 1] = fmaf(__uint_as_float(v[j + 1]), ln_ra, fmaf(ln_rb, ss.y, bb.y));
+                                o[j + 2] = fmaf(__uint_as_float(v[j + 2]), ln_ra, fmaf(ln_rb, ss.z, bb.z));
+                                o[j + 3] = fmaf(__uint_as_float(v[j + 3]), ln_ra, fmaf(ln_rb, ss.w, bb.w));
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                o[j] = cb + j < p.N_out ? fmaf(__uint_as_float(v[j]), ln_ra, fmaf(ln_rb, __ldg(p.ln_colsum + cb + j),
+                                                                                                    __ldg(p.bias + cb + j))) : 0.f;
                         }
                     } else {
                         tmem_ld_wait();
@@ -557,6 +646,36 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             for (int j = 0; j < 16; ++j) o[j] = row_ok ? o[j] : 0.f;
                         }
                     }
+                    if constexpr (kLNP) {
+                        // LayerNorm folding, producer side: this row's statistics and the bf16 operand copy of the
+                        // final fp32 values (one full 32-byte sector per thread and chunk)
+                        if (row_ok) {
+                            if (cb + 16 <= p.N_out) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) { ln_s += o[j]; ln_q = fmaf(o[j], o[j], ln_q); }
+                                uint4 pk[2];
+#pragma unroll
+                                for (int c = 0; c < 2; ++c) {
+                                    __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * c], o[8 * c + 1]);
+                                    __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * c + 2], o[8 * c + 3]);
+                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * c + 4], o[8 * c + 5]);
+                                    __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * c + 6], o[8 * c + 7]);
+                                    pk[c].x = *reinterpret_cast<uint32_t*>(&h0); pk[c].y = *reinterpret_cast<uint32_t*>(&h1);
+                                    pk[c].z = *reinterpret_cast<uint32_t*>(&h2); pk[c].w = *reinterpret_cast<uint32_t*>(&h3);
+                                }
+                                uint4* dst = reinterpret_cast<uint4*>(p.ln_x + grow_ * p.ld_ln_x + cb);
+                                dst[0] = pk[0];
+                                dst[1] = pk[1];
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (cb + j < p.N_out) {
+                                        ln_s += o[j]; ln_q = fmaf(o[j], o[j], ln_q);
+                                        p.ln_x[grow_ * p.ld_ln_x + cb + j] = __float2bfloat16_rn(o[j]);
+                                    }
+                            }
+                        }
+                    }
                     if constexpr (kF32) {
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
@@ -595,6 +714,12 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (tma_res) named_bar_sync(bar_id, 128);
                 }
             }
+            if constexpr (kLNP) {
+                if (row_ok && grp < nch_t) {
+                    atomicAdd(p.ln_acc + 2 * grow_, static_cast<unsigned long long>(__float2ll_rn(ln_s * kLnFixSum)));
+                    atomicAdd(p.ln_acc + 2 * grow_ + 1, static_cast<unsigned long long>(__float2ll_rn(ln_q * kLnFixSq)));
+                }
+            }
             if (!acc_ready) {                                            // group without chunks still tracks the ring
                 mbar_wait(&tfull[a], aph);
                 tc_fence_after();
@@ -619,9 +744,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------ host
-template <int BN, bool kF32, bool k2, bool kCS>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
-                  TapGemmParams& p, cudaStream_t stream) {
+template <int BN, bool kF32, bool k2, int kMode>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2, const CUtensorMap& tmOut,
+                  const CUtensorMap& tmRes, TapGemmParams& p, cudaStream_t stream) {
     constexpr int kBRows = k2 ? BN / 2 : BN;
     constexpr int kStageBytes = kABytes + kBRows * kBlockK * 2;
     constexpr int smem_bytes = StageCount<BN, k2>::value * kStageBytes + StageCount<BN, k2>::epi_bytes + 1024 + 256;
@@ -630,20 +755,46 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     static_assert((2 * StageCount<BN, k2>::value + 4 + EpiGroups<k2>::value * EpiSlots<k2>::value) * 8 + 4 <= 256, "barrier area");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BN, kF32, k2, kCS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BN, kF32, k2, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              smem_bytes);
         if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     p.stage_bytes = static_cast<uint32_t>(p.rows_per_tile * kBlockK * 2 + kBRows * kBlockK * 2);
     p.res_bytes = static_cast<uint32_t>(p.rows_per_tile * 64);
+    {   // ragged last N tile (see TapGemmParams): UMMA N and the staged B rows shrink to what the tile holds
+        const int rem = p.N - (p.num_n_tiles - 1) * BN;                  // 1 .. BN valid accumulator columns
+        int n_eff = (rem + 31) / 32 * 32;
+        if (n_eff > BN || p.geglu) n_eff = BN;
+        p.idesc_last = make_idesc_bf16(k2 ? 2 * kBlockM : kBlockM, n_eff);
+        p.b_rows_last = k2 ? n_eff / 2 : n_eff;
+        p.stage_bytes_last = static_cast<uint32_t>(p.rows_per_tile * kBlockK * 2 + p.b_rows_last * kBlockK * 2);
+    }
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[2];
     cfg.blockDim = dim3(Threads<k2>::value);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
+    const int m_items = k2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
+    {
+        const int cap = k2 ? num_sms() / 2 : num_sms();
+        const int items = m_items * p.num_n_tiles;
+        const int workers = items < cap ? items : cap;
+        p.sched_w = workers;
+        p.sched_full_groups = m_items / workers;
+        const int r = m_items % workers;
+        p.fd_gsz = FastDiv::make(static_cast<uint32_t>(workers) * p.num_n_tiles);
+        p.fd_w = FastDiv::make(workers);
+        p.fd_r = FastDiv::make(r > 0 ? r : 1);
+        p.fd_ntiles = FastDiv::make(p.num_n_tiles);
+        // DCB_GEMM_ORDER=1 selects the wave-major order.  Measured (r02e): never faster than N-fastest, up to 35 % slower
+        // (20480x640x2560): neighbouring workers sharing an A tile at the same time beats one worker re-reading it
+        static int wave = -1;
+        if (wave < 0) { const char* e = getenv("DCB_GEMM_ORDER"); wave = e ? atoi(e) : 0; }
+        p.sched_wave = wave;
+    }
     if (k2) {
-        const int items = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+        const int items = m_items * p.num_n_tiles;
         const int pairs = items < num_sms() / 2 ? items : num_sms() / 2;
         cfg.gridDim = dim3(2 * pairs);
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -663,30 +814,30 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
         attr[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
         ++cfg.numAttrs;
     }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tap_gemm_kernel<BN, kF32, k2, kCS>, tmA, tmB, tmOut, tmRes, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tap_gemm_kernel<BN, kF32, k2, kMode>, tmA, tmB, tmB2, tmOut, tmRes, p);
     if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "tap_gemm launch: %s", cudaGetErrorString(e));
     return DCB_OK;
 }
 
-template <int BN, bool kF32, bool kCS>
-static int launch_mode(bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+template <int BN, bool kF32, int kMode>
+static int launch_mode(bool pair, const CUtensorMap& tmA, const CUtensorMap* tmBs, const CUtensorMap& tmOut,
                        const CUtensorMap& tmRes, TapGemmParams& p, cudaStream_t s) {
-    return pair ? launch<BN, kF32, true, kCS>(tmA, tmB, tmOut, tmRes, p, s)
-                : launch<BN, kF32, false, kCS>(tmA, tmB, tmOut, tmRes, p, s);
+    return pair ? launch<BN, kF32, true, kMode>(tmA, tmBs[0], tmBs[1], tmOut, tmRes, p, s)
+                : launch<BN, kF32, false, kMode>(tmA, tmBs[0], tmBs[1], tmOut, tmRes, p, s);
 }
 
 // all tile-shape / dtype / pair variants of one statistics mode
-template <bool kCS>
-static int launch_all(int bn, bool out_bf16, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB,
+template <int kMode>
+static int launch_all(int bn, bool out_bf16, bool pair, const CUtensorMap& tmA, const CUtensorMap* tmB,
                       const CUtensorMap& tmOut, const CUtensorMap& tmRes, TapGemmParams& p, cudaStream_t s) {
     if (out_bf16) {
-        if (bn == 256) return launch_mode<256, false, kCS>(pair, tmA, tmB, tmOut, tmRes, p, s);
-        return bn == 160 ? launch_mode<160, false, kCS>(pair, tmA, tmB, tmOut, tmRes, p, s)
-                         : launch_mode<128, false, kCS>(pair, tmA, tmB, tmOut, tmRes, p, s);
+        if (bn == 256) return launch_mode<256, false, kMode>(pair, tmA, tmB, tmOut, tmRes, p, s);
+        return bn == 160 ? launch_mode<160, false, kMode>(pair, tmA, tmB, tmOut, tmRes, p, s)
+                         : launch_mode<128, false, kMode>(pair, tmA, tmB, tmOut, tmRes, p, s);
     }
-    if (bn == 256) return launch_mode<256, true, kCS>(pair, tmA, tmB, tmOut, tmRes, p, s);
-    return bn == 160 ? launch_mode<160, true, kCS>(pair, tmA, tmB, tmOut, tmRes, p, s)
-                     : launch_mode<128, true, kCS>(pair, tmA, tmB, tmOut, tmRes, p, s);
+    if (bn == 256) return launch_mode<256, true, kMode>(pair, tmA, tmB, tmOut, tmRes, p, s);
+    return bn == 160 ? launch_mode<160, true, kMode>(pair, tmA, tmB, tmOut, tmRes, p, s)
+                     : launch_mode<128, true, kMode>(pair, tmA, tmB, tmOut, tmRes, p, s);
 }
 
 

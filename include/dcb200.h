@@ -92,6 +92,23 @@ typedef struct {
     unsigned long long* gn_acc;
     int32_t gn_cg;
     int32_t gn_unit_mode;
+    /* Optional LayerNorm folding (NULL = off): the LayerNorm between two GEMMs (attention.py:242-246: norm1 -> to_q/k/v,
+     * norm2 -> to_q, norm3 -> GEGLU) never runs as a kernel of its own.
+     *   producer (out_f32 given, ln_acc != NULL): besides the fp32 output the epilogue writes a bf16 copy of it to ln_x_bf16
+     *     (row stride ld_ln_x) and adds, per output row, (sum * 2^24, sum of squares * 2^28) of the stored fp32 values to
+     *     ln_acc (int64 [rows, 2], zero-initialised by the caller; integer atomics: bitwise reproducible).
+     *   consumer (out_bf16 given, ln_acc != NULL): A is the producer's raw bf16 copy, W must hold gamma-scaled weights
+     *     W'[n,k] = W[n,k] * gamma[k], bias the folded bias b[n] + sum_k W[n,k] beta[k], ln_colsum[n] = sum_k W'[n,k];
+     *     the epilogue evaluates  rstd_r * acc[r,n] - rstd_r * mean_r * ln_colsum[n] + bias[n]  with (mean, rstd) of row r
+     *     from ln_acc (ln_channels = row length of the normalised tensor, ln_eps as in nn.LayerNorm), then GEGLU if set.
+     *     No residual / group_bias / out_scale in this mode. */
+    unsigned long long* ln_acc;
+    void* ln_x_bf16;
+    int32_t ld_ln_x;
+    int32_t ln_channels;
+    const float* ln_colsum;
+    float ln_eps;
+    int32_t reserved0;
 } dcb_tap_gemm_args;
 
 int dcb_tap_gemm(const dcb_tap_gemm_args* args, void* stream);

@@ -26,7 +26,9 @@ def _no_tf32():
 # the last three rows: short-K, large-M launches of the 40x64 level (one of them ragged in M)
 @pytest.mark.parametrize("M,K,N", [(300, 320, 320), (128, 64, 128), (1000, 1280, 512), (77, 1024, 640), (4096, 320, 960),
                                    (40000, 128, 1280), (20480, 640, 512), (20480, 320, 320), (19000, 320, 960),
-                                   (40960, 256, 640)])
+                                   (40960, 256, 640),
+                                   # 256-wide tiles with a narrow last tile (UMMA N = 64 / 128 / 192 / 96, fewer B rows)
+                                   (19000, 320, 1920), (9600, 640, 640), (20480, 128, 352), (12000, 192, 448)])
 def test_linear_bias_residual(M, K, N):
     from dynamicrafter_b200 import ops
     a, w = _mk((M, K), 1), _mk((N, K), 2, K ** -0.5)
