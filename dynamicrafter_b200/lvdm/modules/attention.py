@@ -23,6 +23,24 @@ def _default(v, d):
     return d if v is None else v
 
 
+def _fold_ln_weights(norm, w, b):
+    """LayerNorm affine folded into the Linear behind it: W'[n,k] = W[n,k] gamma[k], b'[n] = b[n] + sum_k W[n,k] beta[k]."""
+    w = w.detach().float()
+    wf = w * norm.weight.detach().float()[None, :]
+    bf = w @ norm.bias.detach().float()
+    if b is not None:
+        bf = bf + b.detach().float()
+    return wf, bf
+
+
+def fold_layer_norm(norm, w, b):
+    """-> ops.LnFold: bf16 gamma-scaled weights, folded bias, and the row sums of the weights AS ROUNDED to bf16 (what the
+    tensor core multiplies with), so that subtracting mean * rowsum removes the mean exactly."""
+    wf, bf = _fold_ln_weights(norm, w, b)
+    wq = wf.to(torch.bfloat16).contiguous()
+    return ops.LnFold(wq, bf.contiguous(), wq.float().sum(1).contiguous(), float(norm.eps))
+
+
 class CrossAttentionContext:
     """Per-forward conditioning in kernel layout: bf16 token matrices + how frames map onto them."""
 
@@ -79,35 +97,44 @@ class CrossAttention(PackedModule):
         return p
 
     # ---- kernel-layout entry points -------------------------------------------------------------
-    def _attend_self_spatial(self, xn, nbatch, ntok, residual, out_bf16=False):
-        """xn: bf16 [nbatch*ntok, C] (already layer-normed).  Returns to_out(attn) + residual (fp32)."""
+    def _attend_self_spatial(self, xn, nbatch, ntok, residual, out_bf16=False, ln=None, ln_stats=False):
+        """xn: bf16 [nbatch*ntok, C] (already layer-normed), or an ops.LnSrc with ln = the folded LayerNorm.
+        Returns to_out(attn) + residual (fp32); with ln_stats also the LnSrc of that result for the next LayerNorm."""
         p = self.packed()
         inner = self.inner_dim
-        qkv = ops.linear(xn, p["wqkv"])
+        qkv = ops.linear(xn, p["wqkv"]) if ln is None else ops.linear(xn, None, ln=ln)
         a = ops.flash_attention(qkv[:, :inner], [(qkv[:, inner:2 * inner], qkv[:, 2 * inner:], ntok, 1, 1.0)],
                                 nbatch, self.heads, ntok, self.scale)
-        return ops.linear(a, p["wo"], bias=p["bo"], residual=residual, f32=not out_bf16, bf16=out_bf16)
+        return ops.linear(a, p["wo"], bias=p["bo"], residual=residual, f32=not out_bf16, bf16=out_bf16, ln_stats=ln_stats)
 
-    def _attend_self_temporal(self, xn, B, T, HW, residual):
+    def _attend_self_temporal(self, xn, B, T, HW, residual, ln=None, ln_stats=False):
         p = self.packed()
         inner = self.inner_dim
-        qkv = ops.linear(xn, p["wqkv"])
+        qkv = ops.linear(xn, p["wqkv"]) if ln is None else ops.linear(xn, None, ln=ln)
         a = ops.temporal_attention(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], B, T, HW,
                                    self.heads, self.scale)
-        return ops.linear(a, p["wo"], bias=p["bo"], residual=residual, f32=True, bf16=False)
+        return ops.linear(a, p["wo"], bias=p["bo"], residual=residual, f32=True, bf16=False, ln_stats=ln_stats)
 
-    def _attend_cross(self, xn, nbatch, ntok, ctx, residual):
+    def _attend_cross(self, xn, nbatch, ntok, ctx, residual, ln=None, ln_stats=False):
         """ctx: CrossAttentionContext.  Text and image keys get independent softmaxes (attention.py:129-142)."""
         p = self.packed()
         inner = self.inner_dim
-        q = ops.linear(xn, p["wq"])
+        q = ops.linear(xn, p["wq"]) if ln is None else ops.linear(xn, None, ln=ln)
         kv = ops.linear(ctx.text, p["wkv"])
         segs = [(kv[:, :inner], kv[:, inner:], ctx.n_text, ctx.text_div, 1.0)]
         if self.image_cross_attention and ctx.image is not None and ctx.n_image > 0:
             kv_ip = ops.linear(ctx.image, p["wkv_ip"])
             segs.append((kv_ip[:, :inner], kv_ip[:, inner:], ctx.n_image, ctx.image_div, p["ip_scale"]))
         a = ops.flash_attention(q, segs, nbatch, self.heads, ntok, self.scale)
-        return ops.linear(a, p["wo"], bias=p["bo"], residual=residual, f32=True, bf16=False)
+        return ops.linear(a, p["wo"], bias=p["bo"], residual=residual, f32=True, bf16=False, ln_stats=ln_stats)
+
+    def _ln_fold(self, norm):
+        """LnFold of `norm` followed by this attention's query-side projection (fused q/k/v for self-attention)."""
+        if self.is_self:
+            w = torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], 0)
+        else:
+            w = self.to_q.weight
+        return fold_layer_norm(norm, w, None)
 
     # ---- reference signature ----------------------------------------------------------------------
     def forward(self, x, context=None, mask=None):
@@ -163,10 +190,20 @@ class FeedForward(PackedModule):
         return {"w1": w1, "b1": b1, "bn": bn, "w2": pack_linear(self.net[2].weight),
                 "b2": self.net[2].bias.detach().float().contiguous()}
 
-    def _fwd(self, xn, residual, out_bf16):
+    def _fwd(self, xn, residual, out_bf16, ln=None):
         p = self.packed()
-        g = ops.linear(xn, p["w1"], bias=p["b1"], geglu=True, block_n=p["bn"])
+        if ln is None:
+            g = ops.linear(xn, p["w1"], bias=p["b1"], geglu=True, block_n=p["bn"])
+        else:
+            g = ops.linear(xn, None, geglu=True, block_n=p["bn"], ln=ln)
         return ops.linear(g, p["w2"], bias=p["b2"], residual=residual, f32=not out_bf16, bf16=out_bf16)
+
+    def _ln_fold(self, norm):
+        """LnFold of `norm` followed by the GEGLU projection (rows interleaved per output tile like w1)."""
+        proj = self.net[0].proj
+        wf, bf = _fold_ln_weights(norm, proj.weight, proj.bias)
+        w1, b1, _ = pack_geglu(wf, bf)
+        return ops.LnFold(w1, b1, w1.float().sum(1).contiguous(), float(norm.eps))
 
     def forward(self, x):
         shp = x.shape
@@ -197,18 +234,36 @@ class BasicTransformerBlock(PackedModule):
         self.checkpoint = checkpoint
 
     def _pack(self):
-        return {}
+        """Folded LayerNorms (bf16 mode): norm1 -> attn1 q/k/v, norm2 -> attn2 q (or q/k/v), norm3 -> GEGLU."""
+        if not ops.ln_fold_enabled():
+            return {}
+        return {"ln1": self.attn1._ln_fold(self.norm1), "ln2": self.attn2._ln_fold(self.norm2),
+                "ln3": self.ff._ln_fold(self.norm3)}
+
+    def _own_version(self):
+        return sum(q._version for q in self.parameters())          # the folds read the attention / FF weights too
 
     def _ln(self, norm, x):
         return ops.layer_norm(x, norm.weight, norm.bias, norm.eps)
 
-    def _fwd_spatial(self, x, nbatch, ntok, ctx):
-        """x: fp32 [nbatch*ntok, dim] residual stream -> bf16 (the only consumer is proj_out)."""
+    def _fwd_spatial(self, x, nbatch, ntok, ctx, ls=None):
+        """x: fp32 [nbatch*ntok, dim] residual stream -> bf16 (the only consumer is proj_out).  ls: ops.LnSrc of x from
+        the GEMM that produced it -> the three LayerNorms are folded into their neighbour GEMMs (no layer_norm launch)."""
+        if ls is not None:
+            p = self.packed()
+            x, ls = self.attn1._attend_self_spatial(ls, nbatch, ntok, x, ln=p["ln1"], ln_stats=True)
+            x, ls = self.attn2._attend_cross(ls, nbatch, ntok, ctx, x, ln=p["ln2"], ln_stats=True)
+            return self.ff._fwd(ls, x, True, ln=p["ln3"])
         x = self.attn1._attend_self_spatial(self._ln(self.norm1, x), nbatch, ntok, x)
         x = self.attn2._attend_cross(self._ln(self.norm2, x), nbatch, ntok, ctx, x)
         return self.ff._fwd(self._ln(self.norm3, x), x, True)
 
-    def _fwd_temporal(self, x, B, T, HW):
+    def _fwd_temporal(self, x, B, T, HW, ls=None):
+        if ls is not None:
+            p = self.packed()
+            x, ls = self.attn1._attend_self_temporal(ls, B, T, HW, x, ln=p["ln1"], ln_stats=True)
+            x, ls = self.attn2._attend_self_temporal(ls, B, T, HW, x, ln=p["ln2"], ln_stats=True)
+            return self.ff._fwd(ls, x, True, ln=p["ln3"])
         x = self.attn1._attend_self_temporal(self._ln(self.norm1, x), B, T, HW, x)
         x = self.attn2._attend_self_temporal(self._ln(self.norm2, x), B, T, HW, x)
         return self.ff._fwd(self._ln(self.norm3, x), x, True)
@@ -269,8 +324,11 @@ class SpatialTransformer(PackedModule):
         p = self.packed()
         nf, S = h.B * h.T, h.H * h.W
         y = ops.group_norm(h.x, nf, S, self.norm.weight, self.norm.bias, self.norm.eps, silu=False, colsums=h.cs)
-        x = ops.linear(y, p["w_in"], bias=p["b_in"], f32=True, bf16=False)
-        xb = self.transformer_blocks[0]._fwd_spatial(x, nf, S, ctx)
+        if ops.ln_fold_enabled():
+            x, ls = ops.linear(y, p["w_in"], bias=p["b_in"], f32=True, bf16=False, ln_stats=True)
+        else:
+            x, ls = ops.linear(y, p["w_in"], bias=p["b_in"], f32=True, bf16=False), None
+        xb = self.transformer_blocks[0]._fwd_spatial(x, nf, S, ctx, ls)
         out, cs = ops.linear(xb, p["w_out"], bias=p["b_out"], residual=h.x, f32=True, bf16=False, stats_rows=S)
         return h.like(out, cs=cs)
 
@@ -326,8 +384,11 @@ class TemporalTransformer(PackedModule):
         if T > 16:
             raise NotImplementedError("temporal attention kernel handles at most 16 frames")
         y = ops.group_norm(h.x, B, T * S, self.norm.weight, self.norm.bias, self.norm.eps, silu=False, colsums=h.cs)
-        x = ops.linear(y, p["w_in"], bias=p["b_in"], f32=True, bf16=False)
-        xb = self.transformer_blocks[0]._fwd_temporal(x, B, T, S)
+        if ops.ln_fold_enabled():
+            x, ls = ops.linear(y, p["w_in"], bias=p["b_in"], f32=True, bf16=False, ln_stats=True)
+        else:
+            x, ls = ops.linear(y, p["w_in"], bias=p["b_in"], f32=True, bf16=False), None
+        xb = self.transformer_blocks[0]._fwd_temporal(x, B, T, S, ls)
         out, cs = ops.linear(xb, p["w_out"], bias=p["b_out"], residual=h.x, f32=True, bf16=False, stats_rows=S)
         return h.like(out, cs=cs)
 

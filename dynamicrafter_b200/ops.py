@@ -84,19 +84,21 @@ def stats_enabled():
 
 
 class _StatsArena:
-    """Pre-zeroed int64 pool the per-launch accumulators are carved from: one memset per forward instead of one per GEMM.
+    """Zeroed int64 pool the per-launch accumulators are carved from: one memset per forward instead of one per GEMM.
     Buffers that are outgrown are retired, not freed (captured CUDA graphs keep their addresses)."""
 
     def __init__(self):
-        self.buf, self.off, self.high, self.active, self.retired = None, 0, 0, False, []
+        self.buf, self.off, self.active, self.retired = None, 0, False, []
 
 
 _ARENAS = {}
 
 
 class stats_scope:
-    """with stats_scope(device): every fused-statistics accumulator allocated inside comes from the device's arena, which
-    is re-zeroed (its used prefix) once on entry.  Not re-entrant: an inner scope is a no-op."""
+    """with stats_scope(device): every fused-statistics accumulator allocated inside comes from the device's arena.  The
+    arena is clean on entry (fresh buffers are zero-filled) and the prefix a forward used is re-zeroed when its scope
+    closes -- stream ordered behind the last consumer -- so the memset a CUDA graph captures always covers exactly what
+    that forward allocated, also when the arena grew during the warm-up runs.  Not re-entrant: an inner scope is a no-op."""
 
     def __init__(self, dev):
         self.ar = _ARENAS.setdefault(dev.index, _StatsArena())
@@ -106,29 +108,62 @@ class stats_scope:
         ar = self.ar
         if not ar.active:
             self.owner, ar.active, ar.off = True, True, 0
-            if ar.buf is not None and ar.high > 0:
-                ar.buf[:ar.high].zero_()
         return self
 
     def __exit__(self, *exc):
         if self.owner:
-            self.ar.high = max(self.ar.high, self.ar.off)
-            self.ar.active = False
+            ar = self.ar
+            if ar.buf is not None and ar.off > 0:
+                ar.buf[:ar.off].zero_()
+            ar.off, ar.active = 0, False
 
 
 def _alloc_acc(units, dev):
-    n = units * 64
+    return _alloc_i64(units * 64, dev).view(units, 32, 2)
+
+
+class LnSrc:
+    """LayerNorm folding: what the GEMM that produced an fp32 [rows, C] tensor leaves for the GEMM behind the LayerNorm:
+    xb = bf16 copy of the tensor, acc = int64 [rows, 2] fixed-point (sum, sum of squares) per row."""
+    __slots__ = ("xb", "acc", "C")
+
+    def __init__(self, xb, acc, C):
+        self.xb, self.acc, self.C = xb, acc, C
+
+
+class LnFold:
+    """Consumer side of a folded LayerNorm: w = bf16 [N, C] gamma-scaled weights, b = fp32 [N] folded bias,
+    s = fp32 [N] row sums of w (as rounded to bf16), eps."""
+    __slots__ = ("w", "b", "s", "eps")
+
+    def __init__(self, w, b, s, eps):
+        self.w, self.b, self.s, self.eps = w, b, s, eps
+
+
+def ln_fold_enabled():
+    """LayerNorm folded into its neighbour GEMMs (bf16 mode only).  OFF by default (DCB_LN_FOLD=1 enables it): measured on
+    B200 (tools/bench_ln_fold.py, profiles/r02_summary.md) the fold removes the layer_norm launches (2.4 ms per step)
+    but costs the HBM-bound producer GEMMs +8..20 us each (scattered bf16 copy + per-row atomics) and the issue-bound
+    K = 320 consumers +5..17 us: 34.84 vs 34.79 ms per step, i.e. nothing gained."""
+    return _LN_FOLD and not fp32_mode()
+
+
+_LN_FOLD = os.environ.get("DCB_LN_FOLD", "0") == "1"
+
+
+def _alloc_i64(n, dev):
+    """n zeroed int64 (n even: 16-byte aligned) from the per-forward arena, or a fresh tensor outside a stats_scope."""
     ar = _ARENAS.get(dev.index)
     if ar is not None and ar.active:
         if ar.buf is None or ar.off + n > ar.buf.numel():
             if ar.buf is not None:
                 ar.retired.append(ar.buf)
             cap = max(2 * (ar.buf.numel() if ar.buf is not None else 0), 1 << 20, n)
-            ar.buf, ar.off, ar.high = torch.zeros(cap, dtype=torch.int64, device=dev), 0, 0
-        out = ar.buf[ar.off:ar.off + n].view(units, 32, 2)
+            ar.buf, ar.off = torch.zeros(cap, dtype=torch.int64, device=dev), 0
+        out = ar.buf[ar.off:ar.off + n]
         ar.off += n
         return out
-    return torch.zeros((units, 32, 2), dtype=torch.int64, device=dev)
+    return torch.zeros(n, dtype=torch.int64, device=dev)
 
 
 def _make_colsums(dims, N, dev):
@@ -141,7 +176,7 @@ def _make_colsums(dims, N, dev):
 
 def tap_gemm(a, dims, strides, adims, taps, w, N, *, bias=None, group_bias=None, rows_per_group=0,
              residual=None, geglu=False, out_f32=None, out_bf16=None, ld_out=None, out_scale=1.0,
-             block_n=0, box=None, colsum=None):
+             block_n=0, box=None, colsum=None, ln_acc=None, ln_x=None, ln_colsum=None, ln_channels=0, ln_eps=0.0):
     """Raw launch.  a: bf16 tensor; dims=(D1,D2,D3) output domain; strides=(s1,s2,s3) element strides
     of A; adims=(A1,A2,A3) extents of A; taps=[(o1,o2,o3),...]; w: bf16 [N, ntaps*C]."""
     require_cuda(a, w, bias, group_bias, residual, out_f32, out_bf16)
@@ -188,6 +223,12 @@ def tap_gemm(a, dims, strides, adims, taps, w, N, *, bias=None, group_bias=None,
     args.gn_acc = None if colsum is None else colsum.acc.data_ptr()
     args.gn_cg = 0 if colsum is None else colsum.C // 32
     args.gn_unit_mode = 0 if colsum is None else colsum.mode
+    args.ln_acc = None if ln_acc is None else ln_acc.data_ptr()
+    args.ln_x_bf16 = None if ln_x is None else ln_x.data_ptr()
+    args.ld_ln_x = 0 if ln_x is None else ln_x.stride(0)
+    args.ln_channels = ln_channels
+    args.ln_colsum = None if ln_colsum is None else ln_colsum.data_ptr()
+    args.ln_eps = ln_eps
     check(_lib.lib().dcb_tap_gemm(ctypes.byref(args), _stream()), "dcb_tap_gemm")
 
 
@@ -213,10 +254,34 @@ def _outputs(rows, n_out, out, want_f32, want_bf16, dev):
 
 
 def linear(a, w, *, bias=None, residual=None, geglu=False, f32=False, bf16=True, out=None, N=None,
-           group_bias=None, rows_per_group=0, out_scale=1.0, block_n=0, stats_rows=0):
+           group_bias=None, rows_per_group=0, out_scale=1.0, block_n=0, stats_rows=0, ln_stats=False, ln=None):
     """a: bf16 [M, K] (row stride may exceed K); w: bf16 [N, K] -> [M, N] (or N/2 for geglu).
-    stats_rows = rows per frame: also emit the per-frame column sums a consumer GroupNorm needs -> (out, ColSums)."""
+    stats_rows = rows per frame: also emit the per-frame column sums a consumer GroupNorm needs -> (out, ColSums).
+    ln_stats: fp32 output that feeds a LayerNorm -> (out, LnSrc) (bf16 copy + per-row statistics from the epilogue).
+    ln: LnFold, with a = LnSrc: the GEMM behind a folded LayerNorm (w / bias are taken from the LnFold)."""
+    if ln is not None:
+        src = a
+        assert isinstance(src, LnSrc) and not f32 and residual is None and out is None and not stats_rows
+        M, K = src.xb.shape
+        N = ln.w.shape[0]
+        n_out = N // 2 if geglu else N
+        of, ob, ld = _outputs(M, n_out, None, False, True, src.xb.device)
+        s1 = src.xb.stride(0)
+        tap_gemm(src.xb, (M, 1, 1), (s1, s1 * M, s1 * M), (M, 1, 1), [(0, 0, 0)], ln.w, N, bias=ln.b, geglu=geglu,
+                 out_bf16=ob, ld_out=ld, block_n=block_n, ln_acc=src.acc, ln_colsum=ln.s, ln_channels=src.C, ln_eps=ln.eps)
+        return ob
     M, K = a.shape
+    if ln_stats and not fp32_mode():
+        assert a.stride(1) == 1 and w.shape[1] == K and not geglu and out is None and not stats_rows
+        N = N or w.shape[0]
+        of, ob, ld = _outputs(M, N, None, True, False, a.device)
+        xb = torch.empty((M, N), dtype=BF16, device=a.device)
+        acc = _alloc_i64(2 * M, a.device)
+        s1 = a.stride(0)
+        tap_gemm(a, (M, 1, 1), (s1, s1 * M, s1 * M), (M, 1, 1), [(0, 0, 0)], w, N, bias=bias, residual=residual,
+                 out_f32=of, ld_out=ld, group_bias=group_bias, rows_per_group=rows_per_group, out_scale=out_scale,
+                 block_n=block_n, ln_acc=acc, ln_x=xb)
+        return of, LnSrc(xb, acc, N)
     if a.dtype == F32:                      # fp32 parity mode
         assert a.stride(1) == 1 and w.shape[1] == 3 * K
         N = N or w.shape[0]

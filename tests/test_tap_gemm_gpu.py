@@ -159,3 +159,54 @@ def test_fused_groupnorm_statistics_tconv(B, T, HW, C, N):
     mean, var = o.mean(-1), o.var(-1, unbiased=False)
     assert (stats[:, :, 0] - mean).abs().max().item() < 2e-5
     assert ((stats[:, :, 1] - (var + 1e-5).rsqrt()).abs() / (var + 1e-5).rsqrt()).max().item() < 1e-4
+
+
+@pytest.mark.parametrize("M,C,N,geglu", [(20480, 320, 960, False), (5000, 640, 640, False), (4096, 320, 2560, True),
+                                         (300, 1280, 10240, True), (20480, 512, 1536, False), (1000, 320, 320, False)])
+def test_layer_norm_folding(M, C, N, geglu):
+    """LayerNorm folded into its neighbour GEMMs (attention.py:242-246): the producer GEMM leaves a bf16 copy + per-row
+    (sum, sumsq), the consumer GEMM runs on gamma-scaled weights and normalises in its epilogue.  Checked against
+    LayerNorm -> Linear (-> GEGLU) in fp32 torch; rows get a non-zero mean so the mean correction matters."""
+    import torch.nn as nn
+    from dynamicrafter_b200 import ops
+    from dynamicrafter_b200.lvdm.modules.attention import fold_layer_norm, _fold_ln_weights
+    from dynamicrafter_b200.lvdm._packing import pack_geglu
+    torch.manual_seed(5)
+    a, w0 = _mk((M, C), 31), _mk((C, C), 32, C ** -0.5)
+    b0 = torch.randn(C, device="cuda") * 0.3 + 0.4
+    res = torch.randn(M, C, device="cuda") + 0.25
+    y_ref = a.float() @ w0.float().t() + b0 + res
+    y, src = ops.linear(a, w0, bias=b0, residual=res, f32=True, bf16=False, ln_stats=True)
+    _close(y, y_ref, 1e-4)
+    _close(src.xb, y_ref, 1e-2)
+    # per-row statistics
+    acc = src.acc.view(M, 2).double()
+    assert (acc[:, 0] / 2 ** 24 - y.double().sum(1)).abs().max().item() < 1e-3
+    assert ((acc[:, 1] / 2 ** 28 - (y.double() ** 2).sum(1)).abs() / (y.double() ** 2).sum(1)).max().item() < 1e-5
+    norm = nn.LayerNorm(C).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(torch.randn(C) * 0.2 + 1.0)
+        norm.bias.copy_(torch.randn(C) * 0.2)
+    w1 = torch.randn(N, C, device="cuda") * C ** -0.5
+    b1 = torch.randn(N, device="cuda") * 0.1
+    with torch.no_grad():
+        h = F.layer_norm(y_ref, (C,), norm.weight, norm.bias, norm.eps) @ w1.t() + b1
+    if geglu:
+        inner = N // 2
+        ref = h[:, :inner] * F.gelu(h[:, inner:])
+        wf, bf = _fold_ln_weights(norm, w1, b1)
+        wq, bq, bn = pack_geglu(wf, bf)
+        fold = ops.LnFold(wq, bq, wq.float().sum(1).contiguous(), norm.eps)
+        out = ops.linear(src, None, geglu=True, block_n=bn, ln=fold)
+    else:
+        ref = h
+        out = ops.linear(src, None, ln=fold_layer_norm(norm, w1, b1))
+    torch.cuda.synchronize()
+    _close(out, ref, 1.5e-2)
+    # and against the unfolded kernel path (layer_norm kernel + plain GEMM): same precision class
+    xn = ops.layer_norm(y, norm.weight, norm.bias, norm.eps)
+    if not geglu:
+        out2 = ops.linear(xn, w1.to(torch.bfloat16).contiguous(), bias=b1)
+        e_fold = (out.float() - ref).norm() / ref.norm()
+        e_plain = (out2.float() - ref).norm() / ref.norm()
+        assert e_fold < 2.0 * e_plain + 1e-3, (float(e_fold), float(e_plain))
