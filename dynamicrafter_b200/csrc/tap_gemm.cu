@@ -92,29 +92,43 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
     if (bn == 0 && !a->geglu) {
         static int env_bn = -1;                      // DCB_GEMM_BN: tuning override (tools/bench_kernels.py)
         if (env_bn < 0) { const char* e = getenv("DCB_GEMM_BN"); env_bn = e ? atoi(e) : 0; }
-        if (env_bn > 0 && a->N % env_bn == 0) bn = env_bn;
+        if (env_bn > 0 && (a->N % env_bn == 0 || env_bn == 192 || env_bn == 256) && a->N >= env_bn) bn = env_bn;
     }
     if (bn == 0) {
-        // wider N tiles cut shared-memory bytes per MMA (the 1-CTA limiter) but need enough tiles to fill the SMs
         const long long m_tiles = static_cast<long long>((a->D1 + a->b1 - 1) / a->b1) * ((a->D2 + a->b2 - 1) / a->b2) *
                                   ((a->D3 + a->b3 - 1) / a->b3);
-        // 256-wide tiles are the only ones whose operand fill (16 KB of A + 64 B per column per 64-deep stage, against
-        // ~64 B/clk of L2 -> SM bandwidth per SM) keeps up with the tensor pipe.  N need not be a multiple of 256: a ragged
-        // last tile runs a narrower UMMA and stages fewer B rows.  Measured (tools/bench_shapes.py, r02e): N = 960 / 1920
-        // gain 11-13 %, N = 640 (256 + 256 + 128) is neutral to -4 %, N = 320 (256 + 64) loses: the narrow tile still pays
-        // the full A stage.  Hence: at least three full tiles and a last tile of >= 128 columns.
-        // DCB_GEMM_RAGGED256=0 restores the N % 256 rule, DCB_GEMM_RAGGED_MIN / _MIN_N move the thresholds.
-        static int ragged = -1, ragged_min = -1, ragged_min_n = -1;
-        if (ragged < 0) { const char* e = getenv("DCB_GEMM_RAGGED256"); ragged = e ? atoi(e) : 1; }
-        if (ragged_min < 0) { const char* e = getenv("DCB_GEMM_RAGGED_MIN"); ragged_min = e ? atoi(e) : 128; }
-        if (ragged_min_n < 0) { const char* e = getenv("DCB_GEMM_RAGGED_MIN_N"); ragged_min_n = e ? atoi(e) : 768; }
-        const long long n256 = (a->N + 255) / 256;
-        const bool ragged_ok = ragged && a->N >= ragged_min_n && (a->N % 256) >= ragged_min;
-        if (a->geglu) bn = (a->N % 256 == 0) ? 256 : 128;
-        else if ((a->N % 256 == 0 || ragged_ok) && m_tiles * n256 >= 1LL * num_sms()) bn = 256;   // >= one round of CTA pairs
-        else bn = (a->N % 160 == 0) ? 160 : 128;
+        if (a->geglu) {
+            bn = (a->N % 256 == 0) ? 256 : 128;
+        } else {
+            // Tile-width model (CTA pairs, measured with tools/bench_shapes.py, profiles/r02_summary.md): a 64-deep stage
+            // costs a CTA ~(256 + BN) clk -- 16 KB of A plus 64 B per column of B against ~64 B/clk of L2 -> SM fill
+            // bandwidth; only BN = 256 keeps up with the tensor pipe -- and a launch runs ceil(items / pairs) rounds of
+            // such items.  Narrower tiles pay more fill per FLOP but can quantise better (M = 5120, N = 1280: 100 items
+            // of 256 columns are 2 rounds on 74 pairs, 140 items of 192 columns are 2 cheaper rounds: -12..18 %).  A
+            // ragged last tile (narrow UMMA, fewer B rows) makes every width legal for every N; it gets a 3 % handicap
+            // because the narrow tile still stages a full A tile.  DCB_GEMM_RAGGED256=0 restores the round-1 rule.
+            static int model = -1;
+            if (model < 0) { const char* e = getenv("DCB_GEMM_RAGGED256"); model = e ? atoi(e) : 1; }
+            const long long pairs = num_sms() / 2, m_items = (m_tiles + 1) / 2;
+            if (!model || m_items * ((a->N + 255) / 256) < 24) {
+                if (a->N % 256 == 0 && m_tiles * (a->N / 256) >= 1LL * num_sms()) bn = 256;
+                else bn = (a->N % 160 == 0) ? 160 : 128;
+            } else {
+                const int cand[4] = {256, 192, 160, 128};
+                double best = 0.0;
+                for (int i = 0; i < 4; ++i) {
+                    const int c = cand[i];
+                    if (c == 160 && a->N % 160 != 0) continue;                  // 160 only where it divides (320 / 640 / 960 ...)
+                    const long long items = m_items * ((a->N + c - 1) / c);
+                    double t = static_cast<double>((items + pairs - 1) / pairs) * (256 + c);
+                    if (a->N % c != 0) t *= 1.03;
+                    if (bn == 0 || t < best) { bn = c; best = t; }
+                }
+            }
+        }
     }
-    if (bn != 128 && bn != 160 && bn != 256) return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: block_n must be 128, 160 or 256");
+    if (bn != 128 && bn != 160 && bn != 192 && bn != 256)
+        return set_error(DCB_ERR_UNSUPPORTED, "tap_gemm: block_n must be 128, 160, 192 or 256");
     // CTA pairs (cta_group::2): each SM stages half of B, halving shared-memory traffic per MMA.  Measured on the
     // UNet's shapes: pairs win down to ~24 work items of 256 rows (M = 1280 layers: 40 items, +10..20 %; whole step -0.5 ms); below that
     // single 128-row tiles spread over more SMs.

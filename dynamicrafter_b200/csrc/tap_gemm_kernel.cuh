@@ -832,10 +832,12 @@ static int launch_all(int bn, bool out_bf16, bool pair, const CUtensorMap& tmA, 
                       const CUtensorMap& tmOut, const CUtensorMap& tmRes, TapGemmParams& p, cudaStream_t s) {
     if (out_bf16) {
         if (bn == 256) return launch_mode<256, false, kMode>(pair, tmA, tmB, tmOut, tmRes, p, s);
+        if (bn == 192) return launch_mode<192, false, kMode>(pair, tmA, tmB, tmOut, tmRes, p, s);
         return bn == 160 ? launch_mode<160, false, kMode>(pair, tmA, tmB, tmOut, tmRes, p, s)
                          : launch_mode<128, false, kMode>(pair, tmA, tmB, tmOut, tmRes, p, s);
     }
     if (bn == 256) return launch_mode<256, true, kMode>(pair, tmA, tmB, tmOut, tmRes, p, s);
+    if (bn == 192) return launch_mode<192, true, kMode>(pair, tmA, tmB, tmOut, tmRes, p, s);
     return bn == 160 ? launch_mode<160, true, kMode>(pair, tmA, tmB, tmOut, tmRes, p, s)
                      : launch_mode<128, true, kMode>(pair, tmA, tmB, tmOut, tmRes, p, s);
 }

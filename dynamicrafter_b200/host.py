@@ -73,7 +73,10 @@ class DiffusionHost(torch.nn.Module):
         if not isinstance(cond, dict):
             cond = {"c_crossattn": cond if isinstance(cond, list) else [cond]}
         xc = torch.cat([x_noisy] + list(cond.get("c_concat", [])), dim=1)
-        cc = torch.cat(cond["c_crossattn"], 1)
+        ca = cond["c_crossattn"]
+        # a single context tensor is passed through as the SAME object (torch.cat would copy it every step), so the UNet
+        # can recognise it and reuse the cross-attention keys / values projected from it
+        cc = ca[0] if len(ca) == 1 else torch.cat(ca, 1)
         return self.unet(xc, t, context=cc, **kwargs)
 
     def predict_start_from_z_and_v(self, x_t, t, v):

@@ -30,6 +30,11 @@ FUSED_GN_STATS = _os.environ.get("DCB_FUSED_GN_STATS", "1") == "1"
 GRAPH_COLLECTIVES = _os.environ.get("DCB_GRAPH_COLLECTIVES", "0") == "1"
 
 
+# Cross-attention keys / values depend on the conditioning only (attention.py:86-94): UNetModel projects them once per
+# context TENSOR (same object, same version) and reuses them over the DDIM steps.  DCB_CACHE_CROSS_KV=0: every forward.
+CACHE_CROSS_KV = _os.environ.get("DCB_CACHE_CROSS_KV", "1") == "1"
+
+
 from dynamicrafter_b200.precision import fp32_mode, get_precision
 
 

@@ -233,6 +233,33 @@ class DDIMSampler(object):
             return out
         return None
 
+    @staticmethod
+    def _cond_leaves(c):
+        if isinstance(c, torch.Tensor):
+            return [c]
+        if isinstance(c, dict):
+            out = []
+            for k in sorted(c):
+                v = c[k]
+                out += list(v) if isinstance(v, (list, tuple)) else [v]
+            return out
+        return [c]
+
+    def _cat_cond_cached(self, conds):
+        """_cat_cond, remembered while the caller keeps passing the SAME conditioning tensors (same objects, unchanged
+        versions) -- every step of a sampling loop does.  The batched conditioning is then the same tensor object from
+        step to step, which lets UNetModel reuse the cross-attention keys / values it projected from it."""
+        leaves = [t for c in conds for t in self._cond_leaves(c)]
+        if not all(isinstance(t, torch.Tensor) for t in leaves):
+            return self._cat_cond(*conds)
+        ent = getattr(self, "_cat_cache", None)
+        vers = [t._version for t in leaves]
+        if ent is not None and len(ent[0]) == len(leaves) and all(a is b for a, b in zip(ent[0], leaves)) and ent[1] == vers:
+            return ent[2]
+        allc = self._cat_cond(*conds)
+        self._cat_cache = (leaves, vers, allc)           # holds the leaves: their storage cannot be recycled meanwhile
+        return allc
+
     def _eval_branches(self, x, t, conds, kwargs):
         """One UNet forward over all guidance branches (same x, t; different conditioning) -> list of outputs."""
         b, n = x.shape[0], len(conds)
@@ -241,7 +268,7 @@ class DDIMSampler(object):
             if shard.world != n:
                 raise ValueError(f"branch sharding needs {n} ranks (one per guidance branch), got {shard.world}")
             return shard.gather(self.model.apply_model(x, t, conds[shard.rank], **kwargs))
-        allc = self._cat_cond(*conds) if self.batch_cfg else None
+        allc = self._cat_cond_cached(conds) if self.batch_cfg else None
         if allc is None:
             return [self.model.apply_model(x, t, c, **kwargs) for c in conds]
         kwn = {k: (torch.cat([v] * n, 0) if isinstance(v, torch.Tensor) and v.dim() >= 1 and v.shape[0] == b else v)

@@ -47,6 +47,7 @@ class CrossAttentionContext:
     def __init__(self, text, n_text, text_div, image=None, n_image=0, image_div=1):
         self.text, self.n_text, self.text_div = text, n_text, text_div
         self.image, self.n_image, self.image_div = image, n_image, image_div
+        self.kv = None          # {id(CrossAttention): (kv_text, kv_image)}: projected once per context (UNetModel._build_ctx)
 
 
 class CrossAttention(PackedModule):
@@ -120,13 +121,22 @@ class CrossAttention(PackedModule):
         p = self.packed()
         inner = self.inner_dim
         q = ops.linear(xn, p["wq"]) if ln is None else ops.linear(xn, None, ln=ln)
-        kv = ops.linear(ctx.text, p["wkv"])
+        kv, kv_ip = ctx.kv[id(self)] if (ctx.kv is not None and id(self) in ctx.kv) else self._project_context(ctx)
         segs = [(kv[:, :inner], kv[:, inner:], ctx.n_text, ctx.text_div, 1.0)]
-        if self.image_cross_attention and ctx.image is not None and ctx.n_image > 0:
-            kv_ip = ops.linear(ctx.image, p["wkv_ip"])
+        if kv_ip is not None:
             segs.append((kv_ip[:, :inner], kv_ip[:, inner:], ctx.n_image, ctx.image_div, p["ip_scale"]))
         a = ops.flash_attention(q, segs, nbatch, self.heads, ntok, self.scale)
         return ops.linear(a, p["wo"], bias=p["bo"], residual=residual, f32=True, bf16=False, ln_stats=ln_stats)
+
+    def _project_context(self, ctx):
+        """(to_k | to_v)(text) and (to_k_ip | to_v_ip)(image) of this layer (attention.py:86-94): functions of the context
+        only, so UNetModel projects them once per context tensor instead of once per denoising step."""
+        p = self.packed()
+        kv = ops.linear(ctx.text, p["wkv"])
+        kv_ip = None
+        if self.image_cross_attention and ctx.image is not None and ctx.n_image > 0:
+            kv_ip = ops.linear(ctx.image, p["wkv_ip"])
+        return kv, kv_ip
 
     def _ln_fold(self, norm):
         """LnFold of `norm` followed by this attention's query-side projection (fused q/k/v for self-attention)."""

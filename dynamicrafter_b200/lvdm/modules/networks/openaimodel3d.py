@@ -421,10 +421,50 @@ class UNetModel(PackedModule):
             return self._forward_impl(x, timesteps, context, fs)
         return self._forward_graphed(x, timesteps, context, fs)
 
-    def _forward_graphed(self, x, timesteps, context, fs):
-        """Replay a CUDA graph of the whole forward (static shapes; ~2.5k kernel launches collapse into one
-        graph launch).  Captured lazily per (shapes, weight version); inputs are copied into static buffers."""
+    # ---- cross-attention context: cast once, K/V of every cross-attention layer projected once per context tensor
+    def _cross_layers(self):
+        return [m.transformer_blocks[0].attn2 for m in self.modules() if isinstance(m, SpatialTransformer)]
+
+    def _build_ctx(self, context, b, t_full, shard):
+        """context [b, L, D] -> CrossAttentionContext with the text / image keys and values of all cross-attention layers
+        (attention.py:86-94: k, v depend on the context only, not on x or the timestep -> step invariant)."""
+        t = t_full
+        if shard is not None:
+            t0, t1 = shard.frames(t_full)
+            t = t1 - t0
+            if context.shape[1] == TEXT_CONTEXT_LEN + t_full * IMG_TOKENS_PER_FRAME:
+                i0 = TEXT_CONTEXT_LEN + t0 * IMG_TOKENS_PER_FRAME
+                i1 = TEXT_CONTEXT_LEN + t1 * IMG_TOKENS_PER_FRAME
+                context = torch.cat([context[:, :TEXT_CONTEXT_LEN], context[:, i0:i1]], 1)
+        ctx = self._context(context, b, t)
+        if _packing.CACHE_CROSS_KV:
+            ctx.kv = {id(a): a._project_context(ctx) for a in self._cross_layers()}
+        return ctx
+
+    def _ctx_key(self, context):
+        return (context._version, tuple(context.shape), self.__dict__["_packed_cache"][0],
+                sum(q._version for a in self._cross_layers() for q in a.parameters()))
+
+    def _cached_ctx(self, context, b, t_full, shard):
+        """Eager path: reuse the projected context while the caller passes the SAME tensor object (unchanged version) --
+        the DDIM loop does for all its steps.  The cache keeps the tensor alive, so its address cannot be recycled."""
         self.packed()
+        if not _packing.CACHE_CROSS_KV:
+            return self._build_ctx(context, b, t_full, shard)
+        ent = self.__dict__.get("_ctx_cache")
+        key = self._ctx_key(context) + (None if shard is None else (shard.rank, shard.world),)
+        if ent is None or ent[0] is not context or ent[1] != key:
+            ent = (context, key, self._build_ctx(context, b, t_full, shard))
+            self.__dict__["_ctx_cache"] = ent
+        return ent[2]
+
+    def _forward_graphed(self, x, timesteps, context, fs):
+        """Replay CUDA graphs of the whole forward (static shapes; ~800 kernel launches collapse into one graph launch).
+        Captured lazily per (shapes, weight version); inputs are copied into static buffers.  Two graphs: the context
+        graph (casts + the K/V projections of all cross-attention layers) is replayed only when a new context tensor
+        arrives, the main graph every call."""
+        self.packed()
+        shard = getattr(self, "frame_shard", None)
         key = (tuple(x.shape), tuple(context.shape), x.dtype, self.__dict__["_packed_cache"][0])
         cache = self.__dict__.setdefault("_graphs", {})
         ent = cache.get(key)
@@ -435,39 +475,46 @@ class UNetModel(PackedModule):
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):                         # warm-up: lazy packing, func attributes, scratch
-                    self._forward_impl(sx, st, sc, sf)
+                    self._forward_body(sx, st, self._build_ctx(sc, x.shape[0], x.shape[2], shard), sf)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            cgraph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cgraph):
+                sctx = self._build_ctx(sc, x.shape[0], x.shape[2], shard)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                sy = self._forward_impl(sx, st, sc, sf)
+                sy = self._forward_body(sx, st, sctx, sf)
             if len(cache) >= 4:
                 cache.clear()
-            ent = cache[key] = (graph, sx, st, sc, sf, sy)
-        graph, sx, st, sc, sf, sy = ent
+            ent = cache[key] = [graph, sx, st, sc, sf, sy, cgraph, sctx, None, None]
+        graph, sx, st, sc, sf, sy, cgraph = ent[:7]
         sx.copy_(x)
         st.copy_(timesteps)
-        sc.copy_(context)
+        ckey = self._ctx_key(context)
+        if not _packing.CACHE_CROSS_KV or ent[8] is not context or ent[9] != ckey:
+            sc.copy_(context)
+            cgraph.replay()
+            ent[8], ent[9] = context, ckey                 # keeps the tensor alive: its address cannot be recycled
         if sf is not None:
             sf.copy_(fs)
         graph.replay()
         return sy.clone()
 
     def _forward_impl(self, x, timesteps, context, fs):
-        with ops.stats_scope(x.device):          # fused GroupNorm statistics accumulators: one memset per forward
-            return self._forward_body(x, timesteps, context, fs)
+        shard = getattr(self, "frame_shard", None)
+        ctx = self._cached_ctx(context, x.shape[0], x.shape[2], shard)
+        return self._forward_body(x, timesteps, ctx, fs)
 
-    def _forward_body(self, x, timesteps, context, fs):
+    def _forward_body(self, x, timesteps, ctx, fs):
+        with ops.stats_scope(x.device):          # fused GroupNorm statistics accumulators: one memset per forward
+            return self._forward_steps(x, timesteps, ctx, fs)
+
+    def _forward_steps(self, x, timesteps, ctx, fs):
         pk = self.packed()
         shard = getattr(self, "frame_shard", None)      # parallel.FrameShard: this rank denoises frames t0..t1 only
         if shard is not None:
-            t_full = x.shape[2]
-            t0, t1 = shard.frames(t_full)
+            t0, t1 = shard.frames(x.shape[2])
             x = x[:, :, t0:t1].contiguous()
-            if context.shape[1] == TEXT_CONTEXT_LEN + t_full * IMG_TOKENS_PER_FRAME:
-                i0 = TEXT_CONTEXT_LEN + t0 * IMG_TOKENS_PER_FRAME
-                i1 = TEXT_CONTEXT_LEN + t1 * IMG_TOKENS_PER_FRAME
-                context = torch.cat([context[:, :TEXT_CONTEXT_LEN], context[:, i0:i1]], 1)
         b, cin, t, hh, ww = x.shape
         mc = self.model_channels
         dev = x.device
@@ -482,7 +529,6 @@ class UNetModel(PackedModule):
             f1 = ops.small_linear(ops.timestep_embedding(fs.to(dev), mc), fe[0], fe[1], silu_out=True)
             ops.small_linear(f1, fe[2], fe[3], out=emb, accumulate=True)
         emb_all = ops.small_linear(emb, pk["we_all"], pk["be_all"], silu_in=True)      # [b, sum(Cout)]
-        ctx = self._context(context.to(dev), b, t)
         # ---- input conv
         xr = ops.nchw_to_rows(x, 64 if cin <= 64 else (cin + 63) // 64 * 64)
         h0, cs0 = ops.conv3x3(xr, b * t, hh, ww, pk["w_in"], bias=pk["b_in"], stats=True)

@@ -464,3 +464,44 @@ def test_multicond_branches_batched_equals_one_by_one():
     err = max(rel_l2(outs[0][0].cpu(), outs[1][0].cpu()), rel_l2(outs[0][1].cpu(), outs[1][1].cpu()))
     print(f"\nmulti-condition step, batch-3 forward vs 3 forwards (fp32 mode): rel-L2 {err:.3e}")
     assert err < 5e-4       # fp32-mode forwards agree to ~2e-5; the 3-term guidance (7.5 / 2.0) amplifies that ~5x
+
+
+def test_cross_kv_cache_follows_the_context_tensor():
+    """Cross-attention K/V are projected once per context TENSOR (same object, same version) and reused over the steps
+    (attention.py:86-94 recomputes them every forward).  A new tensor, or an in-place change of the cached one, must
+    re-project: compare with a model that never caches (eager and CUDA-graph paths)."""
+    from dynamicrafter_b200.lvdm import _packing
+    from dynamicrafter_b200.lvdm.modules.networks.openaimodel3d import UNetModel
+    g = load_golden("unet_tiny512.pt")
+    cfg, h, w, seed = g["cfg"], g["h"], g["w"], g["seed"]
+    T = cfg["temporal_length"]
+    m = UNetModel(**cfg)
+    m.load_state_dict(synth_state_dict(g["shapes"], seed), strict=True)
+    m = m.cuda().eval()
+    x = synth_input("x", (1, cfg["in_channels"], T, h, w), seed).cuda()
+    ts = torch.tensor([g["t_val"]], dtype=torch.long).cuda()
+    ctx_a = synth_input("context", (1, 77 + 16 * T, cfg["context_dim"]), seed).cuda()
+    ctx_b = synth_input("context", (1, 77 + 16 * T, cfg["context_dim"]), seed + 1).cuda()
+
+    def fresh(ctx):
+        old = _packing.CACHE_CROSS_KV
+        _packing.CACHE_CROSS_KV = False
+        try:
+            m.use_cuda_graph = False
+            return m(x, ts, context=ctx.clone())
+        finally:
+            _packing.CACHE_CROSS_KV = old
+
+    ref_a, ref_b = fresh(ctx_a), fresh(ctx_b)
+    assert not torch.equal(ref_a, ref_b)
+    for graph in (False, True):
+        m.use_cuda_graph = graph
+        m.__dict__.pop("_ctx_cache", None)
+        assert torch.equal(m(x, ts, context=ctx_a), ref_a)
+        assert torch.equal(m(x, ts, context=ctx_a), ref_a)            # cache hit
+        assert torch.equal(m(x, ts, context=ctx_b), ref_b)            # another tensor
+        assert torch.equal(m(x, ts, context=ctx_a), ref_a)
+        c = ctx_a.clone()
+        assert torch.equal(m(x, ts, context=c), ref_a)
+        c.copy_(ctx_b)                                                # same object, new version
+        assert torch.equal(m(x, ts, context=c), ref_b)
