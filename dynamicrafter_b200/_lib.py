@@ -30,6 +30,7 @@ class TapGemmArgs(ctypes.Structure):
         ("gn_acc", c_vp), ("gn_cg", c_int), ("gn_unit_mode", c_int),
         ("ln_acc", c_vp), ("ln_x_bf16", c_vp), ("ld_ln_x", c_int), ("ln_channels", c_int),
         ("ln_colsum", c_vp), ("ln_eps", c_f), ("reserved0", c_int),
+        ("out_s1", c_i64), ("out_s2", c_i64), ("out_s3", c_i64),
     ]
 
 

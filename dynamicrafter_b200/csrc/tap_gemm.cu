@@ -186,8 +186,15 @@ extern "C" int dcb_tap_gemm(const dcb_tap_gemm_args* a, void* stream) {
     }
     {
         const uint64_t ld = (uint64_t)a->ld_out;
+        const bool strided = a->out_s1 != 0 || a->out_s2 != 0 || a->out_s3 != 0;
+        if (strided) {
+            if (a->out_s1 <= 0 || a->out_s2 <= 0 || a->out_s3 <= 0 || (a->out_s1 * oes) % 16 || (a->out_s2 * oes) % 16 ||
+                (a->out_s3 * oes) % 16 || a->residual != nullptr || a->ln_acc != nullptr)
+                return set_error(DCB_ERR_INVALID, "tap_gemm: output strides must be positive multiples of 16 bytes (no residual / LayerNorm folding)");
+        }
         const uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)a->D1, (uint64_t)a->D2, (uint64_t)a->D3};
-        const uint64_t str[4] = {1, ld, ld * a->D1, ld * a->D1 * a->D2};
+        const uint64_t str[4] = {1, strided ? (uint64_t)a->out_s1 : ld, strided ? (uint64_t)a->out_s2 : ld * a->D1,
+                                 strided ? (uint64_t)a->out_s3 : ld * a->D1 * a->D2};
         const uint32_t box[4] = {(uint32_t)(obf ? 32 : 16), (uint32_t)a->b1, (uint32_t)a->b2, (uint32_t)a->b3};
         int rc = encode_map(&tmOut, obf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, oes,
                             CU_TENSOR_MAP_SWIZZLE_64B, outp, 4, dims, str, box,

@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from dynamicrafter_b200 import ops
 from dynamicrafter_b200.lvdm import _packing
-from dynamicrafter_b200.lvdm._packing import PackedModule, Act, pack_linear, pack_conv3x3
+from dynamicrafter_b200.lvdm._packing import PackedModule, Act, pack_linear, pack_conv3x3, pack_conv3x3_up2
 
 
 def _f32(t):
@@ -38,11 +38,17 @@ class Upsample(PackedModule):
         self.conv = torch.nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
 
     def _pack(self):
+        if _packing.FOLD_UPSAMPLE:
+            return {"w4": pack_conv3x3_up2(self.conv.weight), "b": _f32(self.conv.bias)}
         return {"w": pack_conv3x3(self.conv.weight), "b": _f32(self.conv.bias)}
 
     def _fwd(self, h):
         p = self.packed()
         nf = h.B * h.T
+        if "w4" in p:            # nearest x2 folded into the conv (ae_modules.py:123-127): four 2x2-tap phase GEMMs
+            xb = h.x if h.x.dtype == torch.bfloat16 else ops.cast_bf16(h.x)
+            out, cs = ops.conv3x3_up2(xb, nf, h.H, h.W, p["w4"], bias=p["b"], stats=True)
+            return h.like(out, 2 * h.H, 2 * h.W, cs=cs)
         up = ops.upsample2x(h.x, nf, h.H, h.W)
         out, cs = ops.conv3x3(up, nf, 2 * h.H, 2 * h.W, p["w"], bias=p["b"], stats=True)
         return h.like(out, 2 * h.H, 2 * h.W, cs=cs)

@@ -176,7 +176,8 @@ def _make_colsums(dims, N, dev):
 
 def tap_gemm(a, dims, strides, adims, taps, w, N, *, bias=None, group_bias=None, rows_per_group=0,
              residual=None, geglu=False, out_f32=None, out_bf16=None, ld_out=None, out_scale=1.0,
-             block_n=0, box=None, colsum=None, ln_acc=None, ln_x=None, ln_colsum=None, ln_channels=0, ln_eps=0.0):
+             block_n=0, box=None, colsum=None, ln_acc=None, ln_x=None, ln_colsum=None, ln_channels=0, ln_eps=0.0,
+             out_strides=None):
     """Raw launch.  a: bf16 tensor; dims=(D1,D2,D3) output domain; strides=(s1,s2,s3) element strides
     of A; adims=(A1,A2,A3) extents of A; taps=[(o1,o2,o3),...]; w: bf16 [N, ntaps*C]."""
     require_cuda(a, w, bias, group_bias, residual, out_f32, out_bf16)
@@ -229,6 +230,7 @@ def tap_gemm(a, dims, strides, adims, taps, w, N, *, bias=None, group_bias=None,
     args.ln_channels = ln_channels
     args.ln_colsum = None if ln_colsum is None else ln_colsum.data_ptr()
     args.ln_eps = ln_eps
+    args.out_s1, args.out_s2, args.out_s3 = out_strides or (0, 0, 0)
     check(_lib.lib().dcb_tap_gemm(ctypes.byref(args), _stream()), "dcb_tap_gemm")
 
 
@@ -334,6 +336,36 @@ def conv3x3(a, nf, H, W, w, *, bias=None, residual=None, group_bias=None, rows_p
              group_bias=group_bias, rows_per_group=rows_per_group, out_f32=of, out_bf16=ob, ld_out=ld, colsum=cs)
     res = of if of is not None else ob
     return (res, cs) if stats else res
+
+
+# nearest-x2 upsample followed by a 3x3 conv (openaimodel3d.py:98-106, ae_modules.py:123-127) without the 4x tensor: the
+# output pixel (2j + py, 2i + px) only sees a 2x2 neighbourhood of the low-resolution input, so each of the four output
+# phases is a 2x2-tap conv of the ORIGINAL tensor with pre-summed weights (taps per axis: phase 0 reads offsets -1, 0 with
+# k0 and k1 + k2; phase 1 reads 0, +1 with k0 + k1 and k2): 16 instead of 36 MACs per output element and input channel.
+_UP2_OFFS = ((-1, 0), (0, 1))
+
+
+def conv3x3_up2(a, nf, H, W, w4, *, bias=None, f32=True, bf16=False, stats=False):
+    """a: bf16 [nf*H*W, C] low-resolution frames; w4: 4 packed phase weights (pack_conv3x3_up2), each bf16 [N, 4*C] ordered
+    (a_y, b_x, c).  -> [nf*2H*2W, N] (rows of the upsampled frames), optionally with fused GroupNorm statistics."""
+    C = a.shape[1]
+    assert a.stride(1) == 1 and a.stride(0) == C and len(w4) == 4
+    N = w4[0].shape[0]
+    of, ob, ld = _outputs(nf * 4 * H * W, N, None, f32, bf16, a.device)
+    full = of if of is not None else ob
+    dims = (W, H, nf)
+    cs = _make_colsums(dims, N, a.device) if (stats and stats_enabled() and colsum_supported(dims, N)) else None
+    if cs is not None:
+        cs.unit_rows *= 4                        # a unit (frame, or image row) of the OUTPUT holds the rows of all four phases
+    ostr = (2 * ld, 2 * 2 * W * ld, 4 * H * W * ld)
+    for py in range(2):
+        for px in range(2):
+            taps = [(_UP2_OFFS[px][b], _UP2_OFFS[py][a_], 0) for a_ in range(2) for b in range(2)]
+            o = full[(py * 2 * W + px):]
+            tap_gemm(a, dims, (C, C * W, C * W * H), dims, taps, w4[py * 2 + px], N, bias=bias,
+                     out_f32=None if of is None else o, out_bf16=None if ob is None else o, ld_out=ld, colsum=cs,
+                     out_strides=ostr)
+    return (full, cs) if stats else full
 
 
 def tconv3(a, B, T, HW, w, *, bias=None, residual=None, f32=True, bf16=False, out=None, stats=False):

@@ -109,6 +109,11 @@ typedef struct {
     const float* ln_colsum;
     float ln_eps;
     int32_t reserved0;
+    /* Optional output row strides in elements for the D1 / D2 / D3 steps of the output domain (0, 0, 0 = dense rows:
+     * ld_out, ld_out*D1, ld_out*D1*D2).  Lets a launch scatter its rows into a larger tensor -- the four phase GEMMs of
+     * the nearest-x2 upsample + 3x3 conv (openaimodel3d.py:98-106, ae_modules.py:123-127) each write every second pixel
+     * of every second row.  Each stride * element size must be a multiple of 16 bytes; no residual in this mode. */
+    int64_t out_s1, out_s2, out_s3;
 } dcb_tap_gemm_args;
 
 int dcb_tap_gemm(const dcb_tap_gemm_args* args, void* stream);

@@ -210,3 +210,30 @@ def test_layer_norm_folding(M, C, N, geglu):
         e_fold = (out.float() - ref).norm() / ref.norm()
         e_plain = (out2.float() - ref).norm() / ref.norm()
         assert e_fold < 2.0 * e_plain + 1e-3, (float(e_fold), float(e_plain))
+
+
+@pytest.mark.parametrize("nf,H,W,C,N", [(2, 5, 8, 128, 128), (3, 10, 16, 64, 320), (1, 40, 64, 64, 160), (2, 20, 128, 64, 64),
+                                        (4, 3, 2, 64, 64)])
+def test_conv3x3_upsample_folded(nf, H, W, C, N):
+    """Nearest-x2 upsample + 3x3 conv (openaimodel3d.py:98-106, ae_modules.py:123-127) as four 2x2-tap phase GEMMs on the
+    low-resolution tensor, against F.interpolate + F.conv2d; also the fused GroupNorm statistics of the scattered output."""
+    from dynamicrafter_b200 import ops
+    from dynamicrafter_b200.lvdm._packing import pack_conv3x3_up2
+    x = _mk((nf, H, W, C), 41)
+    wt = _mk((N, C, 3, 3), 42, (9 * C) ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, wt.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(nf * 4 * H * W, N)
+    w4 = pack_conv3x3_up2(wt.float())
+    out, cs = ops.conv3x3_up2(x.reshape(nf * H * W, C), nf, H, W, w4, bias=bias, stats=True)
+    torch.cuda.synchronize()
+    _close(out, ref, 4e-3)          # the pre-summed taps are rounded to bf16 once more than the 3x3 weights
+    ob = ops.conv3x3_up2(x.reshape(nf * H * W, C), nf, H, W, w4, bias=bias, f32=False, bf16=True)
+    _close(ob, ref, 1.5e-2)
+    if cs is not None and N % 32 == 0:
+        S = 4 * H * W
+        stats = ops._stats_from_colsums(cs, nf, S, N, 1e-5, out.device)
+        o = out.float().reshape(nf, S, 32, N // 32).permute(0, 2, 1, 3).reshape(nf, 32, -1)
+        mean, var = o.mean(-1), o.var(-1, unbiased=False)
+        assert (stats[:, :, 0] - mean).abs().max().item() < 2e-5 * (1 + mean.abs().max().item())
+        assert ((stats[:, :, 1] - (var + 1e-5).rsqrt()).abs() / (var + 1e-5).rsqrt()).max().item() < 1e-4
