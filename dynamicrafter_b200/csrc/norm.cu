@@ -817,24 +817,51 @@ gn_stream_apply_kernel(const T* __restrict__ x, int C, int S, int rows_per_chunk
     const T* src = x + row0 * C + c0;
     const size_t step = static_cast<size_t>(rpp) * C;
     __nv_bfloat16* dst = y + row0 * C + c0;
-    for (int r = my_r; r < nrows; r += rpp * U) {
-        float v[U][8];
+    if constexpr (sizeof(T) == 2) {
+        // bf16 rows are 16 bytes per thread: keep twice as many rows in flight (raw 16-byte registers, unpacked at use)
+        // so that a thread still has >= 128 bytes outstanding
+        constexpr int UB = 2 * U;
+        for (int r = my_r; r < nrows; r += rpp * UB) {
+            uint4 raw[UB];
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (r + u * rpp < nrows) ld8(src + u * step, v[u]);
+            for (int u = 0; u < UB; ++u)
+                if (r + u * rpp < nrows) raw[u] = __ldg(reinterpret_cast<const uint4*>(src + u * step));
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (r + u * rpp < nrows) {
+            for (int u = 0; u < UB; ++u) {
+                if (r + u * rpp < nrows) {
+                    float v[8];
+                    unpack16(raw[u], v, static_cast<const __nv_bfloat16*>(nullptr));
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float t = fmaf(v[u][e], am[e], bm[e]);
-                    v[u][e] = do_silu ? silu_fast(t) : t;
+                    for (int e = 0; e < 8; ++e) {
+                        const float t = fmaf(v[e], am[e], bm[e]);
+                        v[e] = do_silu ? silu_fast(t) : t;
+                    }
+                    store8(dst + u * step, v);
                 }
-                store8(dst + u * step, v[u]);
             }
+            src += UB * step;
+            dst += UB * step;
         }
-        src += U * step;
-        dst += U * step;
+    } else {
+        for (int r = my_r; r < nrows; r += rpp * U) {
+            float v[U][8];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (r + u * rpp < nrows) ld8(src + u * step, v[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (r + u * rpp < nrows) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float t = fmaf(v[u][e], am[e], bm[e]);
+                        v[u][e] = do_silu ? silu_fast(t) : t;
+                    }
+                    store8(dst + u * step, v[u]);
+                }
+            }
+            src += U * step;
+            dst += U * step;
+        }
     }
 }
 
@@ -864,7 +891,7 @@ static int launch_gn_stream_apply(const T* x, int C, int G, int S, const unsigne
     int nch = capacity / G;
     if (nch < 1) nch = 1;
     int rpc = (S + nch - 1) / nch;
-    if (rpc < rpp * U) rpc = rpp * U;
+    if (rpc < rpp * U) rpc = rpp * U;               // (bf16: up to 2U rows in flight, the tail slots are predicated)
     rpc = (rpc + rpp - 1) / rpp * rpp;
     nch = (S + rpc - 1) / rpc;
     launch_pdl(kPdlGnStream, gn_stream_apply_kernel<T>, dim3(nch, G), dim3(threads), 0, stream, x, C, S, rpc, acc, upi, eps, gamma,
