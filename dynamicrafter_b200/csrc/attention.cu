@@ -605,10 +605,11 @@ extern "C" int dcb_flash_attention(const dcb_attention_args* a, void* stream) {
         // mma.sync variant: all keys resident in shared memory, warps stream over the queries
         constexpr int NT0 = 10, NT1 = 2;
         constexpr int smem = (2 * (NT0 + NT1) * 8 + kCrossWarps * kCrossStages * 16) * kD * 2;
-        static bool cfg = false;
-        if (!cfg) {
+        static bool cfg[kMaxDevices] = {};
+        const int dv = current_device() & (kMaxDevices - 1);
+        if (!cfg[dv]) {
             cudaFuncSetAttribute(cross_attention_kernel<NT0, NT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            cfg = true;
+            cfg[dv] = true;
         }
         const int tiles = (a->nq + 15) / 16;
         int tpw = (tiles + kCrossWarps - 1) / kCrossWarps;
@@ -619,10 +620,11 @@ extern "C" int dcb_flash_attention(const dcb_attention_args* a, void* stream) {
     }
     if (a->nq >= 512) {
         constexpr int W = 8, smem = (W * 16 + 4 * 64) * kD * 2;
-        static bool cfg = false;
-        if (!cfg) {
+        static bool cfg[kMaxDevices] = {};
+        const int dv = current_device() & (kMaxDevices - 1);
+        if (!cfg[dv]) {
             cudaFuncSetAttribute(flash_attention_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            cfg = true;
+            cfg[dv] = true;
         }
         dim3 grid((a->nq + W * 16 - 1) / (W * 16), a->heads, a->batch);
         launch_pdl(kPdlAttention, flash_attention_kernel<W>, grid, dim3(W * 32), smem, st, p);

@@ -17,14 +17,20 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+
+// per-device caches: a process may drive several GPUs (cuda:0 for one model, cuda:1 for another)
 int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    static int n[kMaxDevices] = {};
+    const int dev = current_device() & (kMaxDevices - 1);
+    if (n[dev] == 0) {
+        if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, current_device()) != cudaSuccess || n[dev] <= 0) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
 // DCB_PDL: bit mask of the kernel classes launched with programmatic stream serialization

@@ -6,7 +6,9 @@
 
 namespace dcb {
 int set_error(int code, const char* fmt, ...);   // records a thread-local message, returns code
-int num_sms();                                    // SM count of the current device (cached)
+constexpr int kMaxDevices = 16;                   // per-device caches (function attributes, SM counts) are indexed by ordinal & 15
+int current_device();
+int num_sms();                                    // SM count of the current device (cached per device)
 int check_launch(const char* what);               // cudaGetLastError -> status
 bool pdl_enabled(int cls);                        // programmatic dependent launch per kernel class (DCB_PDL bit mask)
 constexpr int kPdlGemm = 1, kPdlLayerNorm = 2, kPdlGroupNorm = 4, kPdlAttention = 8, kPdlGnStream = 16;

@@ -225,7 +225,10 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tc_fence_after();
             if (lane == 0 && q == 2) FTR(2 + half, 6, j);
             float mx = -INFINITY;
-            // four round trips of 32 columns: two loads in flight per trip were measured slower (register spills)
+            // four round trips of 32 columns: two loads in flight per trip were measured slower (register spills).
+            // Also measured (round 2): each thread of a row taking the max of its own 64 keys and swapping it with its
+            // partner through shared memory (bf16, one 64-thread named barrier) halves the TMEM reads of this pass but is
+            // no faster (595 vs 609 TFLOP/s at 2560 keys): the pass is not what the softmax warps wait on.
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
                 uint32_t v0[32];
@@ -393,11 +396,12 @@ int flash_tc_launch(const dcb_attention_args* a, cudaStream_t stream) {
     if ((rc = encode3(&tk, a->k[0], a->ldk[0], cols, a->nq, a->batch))) return rc;
     if ((rc = encode3(&tv, a->v[0], a->ldv[0], cols, a->nq, a->batch))) return rc;
     if ((rc = encode3(&to, a->o, a->ldo, cols, a->nq, a->batch))) return rc;
-    static bool cfg = false;
-    if (!cfg) {
+    static bool cfg[kMaxDevices] = {};
+    const int dv = current_device() & (kMaxDevices - 1);
+    if (!cfg[dv]) {
         cudaError_t e = cudaFuncSetAttribute(flash_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem);
         if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "flash_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        cfg = true;
+        cfg[dv] = true;
     }
     FlashTcParams p;
     p.nk = a->nq;

@@ -753,12 +753,13 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     static_assert(smem_bytes <= 232448, "shared memory budget");
     static_assert(StageCount<BN, k2>::value >= 4, "pipeline depth");
     static_assert((2 * StageCount<BN, k2>::value + 4 + EpiGroups<k2>::value * EpiSlots<k2>::value) * 8 + 4 <= 256, "barrier area");
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};
+    const int dv = current_device() & (kMaxDevices - 1);
+    if (!configured[dv]) {
         cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BN, kF32, k2, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              smem_bytes);
         if (e != cudaSuccess) return set_error(DCB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = true;
+        configured[dv] = true;
     }
     p.stage_bytes = static_cast<uint32_t>(p.rows_per_tile * kBlockK * 2 + kBRows * kBlockK * 2);
     p.res_bytes = static_cast<uint32_t>(p.rows_per_tile * 64);

@@ -138,7 +138,7 @@ class DDIMSampler(object):
             raise NotImplementedError("ddim_use_original_steps is not used on the DynamiCrafter inference path")
         device = self.model.betas.device
         b = shape[0]
-        img = torch.randn(shape, device=device) if x_T is None else x_T
+        img = self._sync_noise(torch.randn(shape, device=device)) if x_T is None else x_T
         if precision is not None and precision == 16:
             raise NotImplementedError("precision=16 latents: dcb200 keeps the DDIM state in fp32")
         if timesteps is None:
@@ -233,6 +233,23 @@ class DDIMSampler(object):
             return out
         return None
 
+    def _sync_noise(self, noise):
+        """Single-video sharded modes (branch_shard / UNetModel.frame_shard): every rank applies the DDIM update to the
+        whole latent, so all ranks must use rank 0's random draws -- broadcast them instead of relying on the callers
+        having seeded every rank identically (with per-rank seeds the ranks would silently diverge)."""
+        groups = []
+        bs = getattr(self, "branch_shard", None)
+        if bs is not None:
+            groups.append(bs.group)
+        fs = getattr(getattr(self.model, "unet", None), "frame_shard", None)
+        if fs is not None:
+            groups.append(fs.group)
+        if groups:
+            import torch.distributed as dist
+            for g in groups:                     # branch x frame grids: the two broadcasts reach every rank from rank 0
+                dist.broadcast(noise, src=dist.get_global_rank(g, 0) if g is not None else 0, group=g)
+        return noise
+
     @staticmethod
     def _cond_leaves(c):
         if isinstance(c, torch.Tensor):
@@ -309,4 +326,6 @@ class DDIMSampler(object):
             noise = torch.randn((1, *x.shape[1:]), device=device).repeat(b, *((1,) * (x.dim() - 1)))
         else:
             noise = torch.randn(x.shape, device=device)              # drawn every step, like ddim.py:273
+        if coeffs.sigma_t != 0.0:
+            noise = self._sync_noise(noise)
         return ops.ddim_update(x, e_c, e_u, noise, coeffs)
