@@ -228,7 +228,9 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             // four round trips of 32 columns: two loads in flight per trip were measured slower (register spills).
             // Also measured (round 2): each thread of a row taking the max of its own 64 keys and swapping it with its
             // partner through shared memory (bf16, one 64-thread named barrier) halves the TMEM reads of this pass but is
-            // no faster (595 vs 609 TFLOP/s at 2560 keys): the pass is not what the softmax warps wait on.
+            // no faster (595 vs 609 TFLOP/s at 2560 keys): the pass is not what the softmax warps wait on.  Starting every
+            // second CTA of an SM 800 / 1500 / 2200 clk late (to put the MUFU-bound exponential phases of the two
+            // resident CTAs in anti-phase) changes nothing either (612 / 612 / 610 / 609 TFLOP/s).
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
                 uint32_t v0[32];
