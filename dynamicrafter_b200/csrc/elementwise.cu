@@ -103,6 +103,37 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, long long n8, __
     reinterpret_cast<uint4*>(dst)[i] = pack8_bf16(v);
 }
 
+// Batched block transpose: src [Z, A, B, inner] -> dst [Z, B, A, inner], moved as 16-byte vectors (inner16 per block).
+// The frame <-> pixel re-ordering of the frame-sharded mode: (t_loc, dst rank, pixels) <-> (rank, t_loc,
+// pixels) on either side of the all-to-all.  kAdd: src holds bf16 deltas (8 per vector) and the result is
+// out_f32[dst index] = residual_f32[dst index] + delta -- the residual add of a temporal block, applied where the
+// fp32 residual stream lives, so only bf16 crosses NVLink.
+template <bool kAdd>
+__global__ void block_transpose_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int A, int B, long long inner16,
+                                       long long total16, const float* __restrict__ residual, float* __restrict__ out) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total16;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long blk = i / inner16, v = i - blk * inner16;        // dst block index (z, b, a)
+        const long long zb = blk / A;
+        const int a = static_cast<int>(blk - zb * A);
+        const long long z = zb / B;
+        const int b = static_cast<int>(zb - z * B);
+        const uint4 u = __ldg(src + ((z * A + a) * B + b) * inner16 + v);
+        if constexpr (kAdd) {
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(residual) + 2 * i);
+            const float4 r1 = __ldg(reinterpret_cast<const float4*>(residual) + 2 * i + 1);
+            float2 f[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) f[k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+            reinterpret_cast<float4*>(out)[2 * i] = make_float4(r0.x + f[0].x, r0.y + f[0].y, r0.z + f[1].x, r0.w + f[1].y);
+            reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(r1.x + f[2].x, r1.y + f[2].y, r1.z + f[3].x, r1.w + f[3].y);
+        } else {
+            dst[i] = u;
+        }
+    }
+}
+
 // sinusoidal embedding, cos || sin (utils_diffusion.py:17-23), fp32.
 __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B, int dim, float* __restrict__ out) {
     const int half = dim / 2;
@@ -363,6 +394,27 @@ extern "C" int dcb_cast_bf16(const float* src, long long n, void* dst_bf16, void
     cast_bf16_kernel<<<blocks_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         src, n / 8, static_cast<__nv_bfloat16*>(dst_bf16));
     return check_launch("cast_bf16");
+}
+
+extern "C" int dcb_block_transpose(const void* src, void* dst, int Z, int A, int B, long long inner_bytes,
+                                   const float* residual_f32, float* out_f32, void* stream) {
+    if (!src || Z < 1 || A < 1 || B < 1 || inner_bytes < 16 || (inner_bytes & 15) || (reinterpret_cast<uintptr_t>(src) & 15))
+        return set_error(DCB_ERR_INVALID, "block_transpose: blocks must be 16-byte aligned multiples of 16 bytes");
+    const long long inner16 = inner_bytes / 16, total16 = static_cast<long long>(Z) * A * B * inner16;
+    const long long want = (total16 + 255) / 256;
+    const unsigned blocks = static_cast<unsigned>(want < 148LL * 16 ? want : 148LL * 16);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (residual_f32 != nullptr) {
+        if (!out_f32 || ((reinterpret_cast<uintptr_t>(residual_f32) | reinterpret_cast<uintptr_t>(out_f32)) & 15))
+            return set_error(DCB_ERR_INVALID, "block_transpose: residual / out must be 16-byte aligned fp32");
+        block_transpose_kernel<true><<<blocks, 256, 0, s>>>(static_cast<const uint4*>(src), nullptr, A, B, inner16, total16,
+                                                            residual_f32, out_f32);
+    } else {
+        if (!dst || (reinterpret_cast<uintptr_t>(dst) & 15)) return set_error(DCB_ERR_INVALID, "block_transpose: dst");
+        block_transpose_kernel<false><<<blocks, 256, 0, s>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), A, B,
+                                                             inner16, total16, nullptr, nullptr);
+    }
+    return check_launch("block_transpose");
 }
 
 extern "C" int dcb_timestep_embedding(const long long* t, int B, int dim, float* out, void* stream) {

@@ -28,6 +28,9 @@ FUSED_GN_STATS = _os.environ.get("DCB_FUSED_GN_STATS", "1") == "1"
 # frame-sharded mode: also capture the NCCL calls of a forward in the CUDA graph.  Works (94.4 vs 97.7 ms/step at the
 # 1024 config on 2 GPUs) but process-group teardown then hangs with torch 2.11 / NCCL 2.28 -> off by default.
 GRAPH_COLLECTIVES = _os.environ.get("DCB_GRAPH_COLLECTIVES", "0") == "1"
+# frame-sharded mode: DCB_SHARD_V1=1 transposes the fp32 residual stream both ways around every temporal block (round 1);
+# default: bf16 operand one way, bf16 delta back, residual add fused into the unpack (UNetModel._temporal).
+SHARD_V1 = _os.environ.get("DCB_SHARD_V1", "0") == "1"
 
 
 # Cross-attention keys / values depend on the conditioning only (attention.py:86-94): UNetModel projects them once per

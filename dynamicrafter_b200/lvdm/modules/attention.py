@@ -388,18 +388,28 @@ class TemporalTransformer(PackedModule):
         return {"w_in": pack_linear(self.proj_in.weight), "b_in": self.proj_in.bias.detach().float().contiguous(),
                 "w_out": pack_linear(self.proj_out.weight), "b_out": self.proj_out.bias.detach().float().contiguous()}
 
-    def _fwd(self, h):
+    def _pre_norm(self, h):
+        """GroupNorm over (t, h, w) per video (attention.py:367) -> operand rows."""
+        return ops.group_norm(h.x, h.B, h.T * h.H * h.W, self.norm.weight, self.norm.bias, self.norm.eps, silu=False,
+                              colsums=h.cs)
+
+    def _core(self, y, B, T, S, residual, delta=False):
+        """proj_in -> transformer block -> proj_out on normalised rows (b, t, pixel).  delta=True: the block output WITHOUT
+        the residual, as bf16 (frame-sharded mode: the add happens where the fp32 residual stream lives)."""
         p = self.packed()
-        B, T, S = h.B, h.T, h.H * h.W
         if T > 16:
             raise NotImplementedError("temporal attention kernel handles at most 16 frames")
-        y = ops.group_norm(h.x, B, T * S, self.norm.weight, self.norm.bias, self.norm.eps, silu=False, colsums=h.cs)
         if ops.ln_fold_enabled():
             x, ls = ops.linear(y, p["w_in"], bias=p["b_in"], f32=True, bf16=False, ln_stats=True)
         else:
             x, ls = ops.linear(y, p["w_in"], bias=p["b_in"], f32=True, bf16=False), None
         xb = self.transformer_blocks[0]._fwd_temporal(x, B, T, S, ls)
-        out, cs = ops.linear(xb, p["w_out"], bias=p["b_out"], residual=h.x, f32=True, bf16=False, stats_rows=S)
+        if delta:
+            return ops.linear(xb, p["w_out"], bias=p["b_out"], f32=ops.fp32_mode(), bf16=not ops.fp32_mode()), None
+        return ops.linear(xb, p["w_out"], bias=p["b_out"], residual=residual, f32=True, bf16=False, stats_rows=S)
+
+    def _fwd(self, h):
+        out, cs = self._core(self._pre_norm(h), h.B, h.T, h.H * h.W, h.x)
         return h.like(out, cs=cs)
 
     def forward(self, x, context=None):

@@ -145,20 +145,31 @@ class TemporalConvBlock(PackedModule):
         return {"w": [pack_tconv3(s[-1].weight) for s in self._stages()],
                 "b": [_f32(s[-1].bias) for s in self._stages()]}
 
-    def _fwd(self, h, colsums=None):
-        """colsums: fused statistics of h.x from the GEMM that produced it, or None.  Every stage's temporal conv emits
-        the column sums of its own output for the next GroupNorm (the last one for whoever consumes the block output)."""
+    def _pre_norm(self, h, colsums=None):
+        """GroupNorm + SiLU of the first stage (openaimodel3d.py:255-257) -> operand rows."""
+        gn = self.conv1[0]
+        return ops.group_norm(h.x, h.B, h.T * h.H * h.W, gn.weight, gn.bias, gn.eps, silu=True, colsums=colsums)
+
+    def _core(self, y, B, T, S, residual, delta=False):
+        """The four temporal convs on rows (b, t, pixel), starting from the normalised input of stage 1; every conv emits
+        the column sums the next GroupNorm needs.  delta=True: the block output WITHOUT the identity, as bf16
+        (frame-sharded mode)."""
         p = self.packed()
-        B, T, S = h.B, h.T, h.H * h.W
-        z = h.x
+        z = colsums = None
         for i, st in enumerate(self._stages()):
-            gn = st[0]
-            y = ops.group_norm(z, B, T * S, gn.weight, gn.bias, gn.eps, silu=True, colsums=colsums)
+            if i > 0:
+                gn = st[0]
+                y = ops.group_norm(z, B, T * S, gn.weight, gn.bias, gn.eps, silu=True, colsums=colsums)
             last = i == 3
-            lowp = _packing.BF16_TCONV and not last
-            z, colsums = ops.tconv3(y, B, T, S, p["w"][i], bias=p["b"][i], residual=h.x if last else None,
+            lowp = (_packing.BF16_TCONV and not last) or (last and delta and not ops.fp32_mode())
+            z, colsums = ops.tconv3(y, B, T, S, p["w"][i], bias=p["b"][i], residual=residual if (last and not delta) else None,
                                     f32=not lowp, bf16=lowp, stats=True)
-        return h.like(z, cs=colsums)
+        return z, colsums
+
+    def _fwd(self, h, colsums=None):
+        """colsums: fused statistics of h.x from the GEMM that produced it, or None."""
+        z, cs = self._core(self._pre_norm(h, colsums), h.B, h.T, h.H * h.W, h.x)
+        return h.like(z, cs=cs)
 
     def forward(self, x):
         """x: [b, c, t, h, w] (openaimodel3d.py:272)."""
@@ -394,15 +405,24 @@ class UNetModel(PackedModule):
 
     @staticmethod
     def _temporal(mod, h, shard):
-        """Frame-sharded mode: a temporal block needs every frame of a pixel -> transpose the residual stream
-        frames -> pixels (all-to-all), run the block on this rank's pixel columns with its 5-D GroupNorm statistics
-        all-reduced, transpose back."""
-        from dynamicrafter_b200.parallel import frames_to_pixels, pixels_to_frames
+        """Frame-sharded mode: a temporal block needs every frame of a pixel.  Its GroupNorm runs on this rank's frames
+        (statistics all-reduced), the normalised bf16 operand is transposed frames -> pixels (all-to-all), the block core
+        runs on this rank's pixel columns with all frames and returns its DELTA (no residual) as bf16, which is
+        transposed back and added to the fp32 residual stream by the unpack kernel.  Only bf16 crosses
+        NVLink; DCB_SHARD_V1=1 restores the round-1 flow (fp32 residual stream transposed both ways)."""
+        from dynamicrafter_b200 import parallel
         hw = h.H * h.W
-        hp = Act(frames_to_pixels(h.x, h.B, h.T, hw, shard), h.B, h.T * shard.world, 1, hw // shard.world)
+        if _packing.SHARD_V1:
+            hp = Act(parallel.frames_to_pixels(h.x, h.B, h.T, hw, shard), h.B, h.T * shard.world, 1, hw // shard.world)
+            with ops.sharded_group_norm(shard):
+                op = mod._fwd(hp)
+            return h.like(parallel.pixels_to_frames(op.x, h.B, hp.T, hp.W, shard))
         with ops.sharded_group_norm(shard):
-            op = mod._fwd(hp)
-        return h.like(pixels_to_frames(op.x, h.B, hp.T, hp.W, shard))
+            y = mod._pre_norm(h)                                     # frame side: rows (b, t_loc, p)
+        yp = parallel.frames_to_pixels_v2(y, h.B, h.T, hw, shard)    # pixel side: rows (b, t, p_loc)
+        with ops.sharded_group_norm(shard):
+            delta, _ = mod._core(yp, h.B, h.T * shard.world, hw // shard.world, None, delta=True)
+        return h.like(parallel.pixels_to_frames_add(delta, h.x, h.B, h.T * shard.world, hw // shard.world, shard))
 
     def _run(self, layers, h, emb_all, pk, ctx, skip=None, shard=None):
         for layer in layers:

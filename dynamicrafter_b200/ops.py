@@ -768,6 +768,24 @@ def cast_bf16(x):
     return out
 
 
+def block_transpose(src, Z, A, B, residual=None):
+    """src viewed as [Z, A, B, inner] -> [Z, B, A, inner] (same dtype), flat result of src's shape.  With residual (fp32, in
+    the RESULT's order) and bf16 src: fp32 residual + src."""
+    require_cuda(src, residual)
+    assert src.is_contiguous() and src.numel() % (Z * A * B) == 0
+    inner_bytes = src.numel() // (Z * A * B) * src.element_size()
+    if residual is not None:
+        assert src.dtype == BF16 and residual.dtype == F32 and residual.is_contiguous() and residual.numel() == src.numel()
+        out = torch.empty_like(residual)
+        check(_lib.lib().dcb_block_transpose(ptr(src), None, _c_i(Z), _c_i(A), _c_i(B), _c_ll(inner_bytes), ptr(residual),
+                                             ptr(out), _stream()), "dcb_block_transpose")
+        return out
+    out = torch.empty_like(src)
+    check(_lib.lib().dcb_block_transpose(ptr(src), ptr(out), _c_i(Z), _c_i(A), _c_i(B), _c_ll(inner_bytes), None, None,
+                                         _stream()), "dcb_block_transpose")
+    return out
+
+
 def timestep_embedding(t, dim):
     require_cuda(t)
     t = t.to(torch.int64).contiguous()

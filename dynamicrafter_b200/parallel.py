@@ -82,6 +82,45 @@ def pixels_to_frames(x, B, T, HW_loc, shard):
     return recv.permute(1, 2, 0, 3, 4).reshape(B * T_loc * N * HW_loc, C)                 # (b, t_loc, (src p_loc))
 
 
+# Version 2 of the transposes (round 2): the temporal blocks are split into "norm" (run on the frame side, statistics
+# all-reduced) and "core" (run on the pixel side, producing the block's DELTA without the residual), so what crosses
+# NVLink is the bf16 normalised operand one way and the bf16 delta the other way -- half the bytes of the fp32
+# residual stream -- and the fp32 residual add happens on the frame side inside the unpack kernel.  One all-to-all per
+# video: its receive buffer [src, t_loc, p_loc, c] IS the pixel-side row order (t, p_loc), and the pixel-side result
+# [dst, t_loc, p_loc, c] IS the send buffer of the way back, so only the frame side re-orders rows
+# (ops.block_transpose: one pack, one unpack fused with the residual add).
+def frames_to_pixels_v2(y, B, T_loc, HW, shard):
+    """y: [B*T_loc*HW, C] rows (b, t_loc, p) (bf16 operand; fp32 in the fp32 parity mode) -> [B*T*HW_loc, C] rows (b, t, p_loc)."""
+    from . import ops
+    N, C = shard.world, y.shape[1]
+    if HW % N:
+        raise ValueError(f"frame sharding needs H*W={HW} divisible by the {N} ranks")
+    send = ops.block_transpose(y, B, T_loc, N)                       # [b][dst][t_loc][p_loc, c]
+    recv = torch.empty_like(send)
+    per = send.numel() // B
+    sv, rv = send.view(-1), recv.view(-1)
+    for b in range(B):
+        dist.all_to_all_single(rv[b * per:(b + 1) * per], sv[b * per:(b + 1) * per], group=shard.group)
+    return recv.view(B * N * T_loc * (HW // N), C)                   # [b][src][t_loc][p_loc] = rows (b, t, p_loc)
+
+
+def pixels_to_frames_add(delta, x, B, T, HW_loc, shard):
+    """delta: [B*T*HW_loc, C] rows (b, t, p_loc) of the block output WITHOUT its residual; x: fp32 [B*T_loc*HW, C] residual
+    stream on the frame side -> x + delta in frame order (fp32)."""
+    from . import ops
+    N = shard.world
+    T_loc = T // N
+    delta = delta.contiguous()
+    recv = torch.empty_like(delta)
+    per = delta.numel() // B
+    sv, rv = delta.view(-1), recv.view(-1)
+    for b in range(B):
+        dist.all_to_all_single(rv[b * per:(b + 1) * per], sv[b * per:(b + 1) * per], group=shard.group)
+    if delta.dtype == torch.bfloat16:
+        return ops.block_transpose(recv, B, N, T_loc, residual=x)    # [b][src][t_loc][..] -> [b][t_loc][src][..] + x
+    return x + ops.block_transpose(recv, B, N, T_loc).view_as(x)      # fp32 parity mode
+
+
 def all_gather_frames(local, shard):
     """local: [B, C, T_loc, H, W] (this rank's frames) -> [B, C, T, H, W] on every rank."""
     bufs = [torch.empty_like(local) for _ in range(shard.world)]

@@ -218,6 +218,12 @@ int dcb_rows_to_nchw(const float* src, int ld, int B, int C, int T, int HW, floa
 int dcb_upsample2x(const float* src, int nf, int H, int W, int C, void* dst_bf16, void* stream);
 int dcb_space_to_depth(const float* src, int nf, int H, int W, int C, void* dst_bf16, void* stream);
 int dcb_cast_bf16(const float* src, long long n, void* dst_bf16, void* stream);
+/* Batched block transpose src [Z, A, B, inner_bytes] -> dst [Z, B, A, inner_bytes] (16-byte multiples): the frame <-> pixel
+ * re-ordering on either side of the all-to-all of the frame-sharded mode (parallel.py).  With
+ * residual_f32 != NULL the source holds bf16 values and out_f32[dst order] = residual_f32[dst order] + src (dst unused):
+ * the residual add of a temporal block (openaimodel3d.py:279, attention.py:412) where the fp32 stream lives. */
+int dcb_block_transpose(const void* src, void* dst, int Z, int A, int B, long long inner_bytes,
+                        const float* residual_f32, float* out_f32, void* stream);
 /* y = gelu(x), exact erf (nn.GELU of the Resampler feed-forward, resampler.py:27-34); contiguous, n % 8 == 0. */
 int dcb_gelu_bf16(const float* src, long long n, void* dst_bf16, void* stream);
 int dcb_timestep_embedding(const long long* t, int B, int dim, float* out, void* stream);

@@ -254,3 +254,19 @@ def test_cross_attention_bench_shape():
     ki = kv_i.float().reshape(nb, NI, 2, H, 64).permute(2, 0, 3, 1, 4)
     ref = _sdpa(qf, kt[0], kt[1], 0.125) + 0.8 * _sdpa(qf, ki[0], ki[1], 0.125)
     assert _rel(out, ref.permute(0, 2, 1, 3).reshape(nb * N, inner)) < 1e-2
+
+
+@pytest.mark.parametrize("Z,A,B,inner", [(2, 8, 2, 1152 * 320), (1, 4, 4, 40 * 64), (3, 2, 5, 8)])
+def test_block_transpose(Z, A, B, inner):
+    """[Z, A, B, inner] -> [Z, B, A, inner] (frame <-> pixel re-ordering of the frame-sharded mode), plain and fused with
+    the fp32 residual add of a bf16 delta."""
+    from dynamicrafter_b200 import ops
+    torch.manual_seed(0)
+    for dt in (torch.bfloat16, torch.float32):
+        src = torch.randn(Z, A, B, inner, device="cuda").to(dt)
+        out = ops.block_transpose(src, Z, A, B)
+        assert torch.equal(out.view(Z, B, A, inner), src.permute(0, 2, 1, 3).contiguous())
+    src = torch.randn(Z, A, B, inner, device="cuda").to(torch.bfloat16)
+    res = torch.randn(Z, B, A, inner, device="cuda")
+    out = ops.block_transpose(src, Z, A, B, residual=res)
+    assert torch.equal(out, res + src.permute(0, 2, 1, 3).float())
