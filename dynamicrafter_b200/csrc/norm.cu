@@ -776,8 +776,8 @@ extern "C" int dcb_group_norm_apply_bf16(const void* x, int C, int G, int S, con
 constexpr int kStreamU = DCB_GN_STREAM_U;
 template <typename T>
 __global__ void __launch_bounds__(512)
-gn_stream_apply_kernel(const T* __restrict__ x, int C, int S, int rows_per_chunk, const unsigned long long* __restrict__ acc,
-                       int upi, float eps, const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
+gn_stream_apply_kernel(const T* __restrict__ x, int C, int S, long long stat_rows, int rows_per_chunk,
+                       const unsigned long long* __restrict__ acc, int upi, float eps, const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
                        __nv_bfloat16* __restrict__ y) {
     __shared__ float s_mr[kGroups * 2];
     const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
@@ -798,7 +798,7 @@ gn_stream_apply_kernel(const T* __restrict__ x, int C, int S, int rows_per_chunk
     pdl_wait();
     if (tid < kGroups) {
         float m, r;
-        gn_stats_from_acc(acc, n, tid, upi, static_cast<double>(S) * cg, eps, m, r);
+        gn_stats_from_acc(acc, n, tid, upi, static_cast<double>(stat_rows) * cg, eps, m, r);
         s_mr[2 * tid] = m;
         s_mr[2 * tid + 1] = r;
     }
@@ -866,7 +866,7 @@ gn_stream_apply_kernel(const T* __restrict__ x, int C, int S, int rows_per_chunk
 }
 
 template <typename T>
-static int launch_gn_stream_apply(const T* x, int C, int G, int S, const unsigned long long* acc, int upi, float eps,
+static int launch_gn_stream_apply(const T* x, int C, int G, int S, long long stat_rows, const unsigned long long* acc, int upi, float eps,
                                   const float* gamma, const float* beta, int silu_act, void* y, cudaStream_t stream) {
     const int O = C / 8;
     if (O > 512) return set_error(DCB_ERR_UNSUPPORTED, "group_norm_stream_apply: C=%d > 4096", C);
@@ -894,7 +894,7 @@ static int launch_gn_stream_apply(const T* x, int C, int G, int S, const unsigne
     if (rpc < rpp * U) rpc = rpp * U;               // (bf16: up to 2U rows in flight, the tail slots are predicated)
     rpc = (rpc + rpp - 1) / rpp * rpp;
     nch = (S + rpc - 1) / rpc;
-    launch_pdl(kPdlGnStream, gn_stream_apply_kernel<T>, dim3(nch, G), dim3(threads), 0, stream, x, C, S, rpc, acc, upi, eps, gamma,
+    launch_pdl(kPdlGnStream, gn_stream_apply_kernel<T>, dim3(nch, G), dim3(threads), 0, stream, x, C, S, stat_rows, rpc, acc, upi, eps, gamma,
                beta, silu_act, static_cast<__nv_bfloat16*>(y));
     return check_launch("group_norm_stream_apply");
 }
@@ -989,19 +989,20 @@ extern "C" int dcb_group_norm_fused_bf16(const void* x, int C, int G, int S, flo
                                           silu_act, y_bf16, nullptr, workspace, counters, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int dcb_group_norm_stream_apply(const void* x, int x_is_bf16, int C, int G, int S, const unsigned long long* gn_acc,
-                                           int units_per_instance, float eps, const float* gamma, const float* beta,
-                                           int silu_act, void* y_bf16, void* stream) {
+extern "C" int dcb_group_norm_stream_apply(const void* x, int x_is_bf16, int C, int G, int S, long long stat_rows,
+                                           const unsigned long long* gn_acc, int units_per_instance, float eps,
+                                           const float* gamma, const float* beta, int silu_act, void* y_bf16, void* stream) {
     if (x == nullptr || y_bf16 == nullptr || gn_acc == nullptr || gamma == nullptr || beta == nullptr)
         return set_error(DCB_ERR_INVALID, "group_norm_stream_apply: null argument");
     if (C % kGroups != 0 || (C & 7) || G < 1 || S < 1 || C > kMaxC || G > 65535 || units_per_instance < 1)
         return set_error(DCB_ERR_INVALID, "group_norm_stream_apply: C=%d G=%d S=%d", C, G, S);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (stat_rows <= 0) stat_rows = S;
     if (x_is_bf16)
-        return launch_gn_stream_apply<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), C, G, S, gn_acc, units_per_instance, eps,
-                                                     gamma, beta, silu_act, y_bf16, s);
-    return launch_gn_stream_apply<float>(static_cast<const float*>(x), C, G, S, gn_acc, units_per_instance, eps, gamma, beta,
-                                         silu_act, y_bf16, s);
+        return launch_gn_stream_apply<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), C, G, S, stat_rows, gn_acc,
+                                                     units_per_instance, eps, gamma, beta, silu_act, y_bf16, s);
+    return launch_gn_stream_apply<float>(static_cast<const float*>(x), C, G, S, stat_rows, gn_acc, units_per_instance, eps, gamma,
+                                         beta, silu_act, y_bf16, s);
 }
 
 extern "C" int dcb_layer_norm(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,

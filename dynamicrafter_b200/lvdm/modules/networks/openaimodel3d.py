@@ -162,8 +162,11 @@ class TemporalConvBlock(PackedModule):
                 y = ops.group_norm(z, B, T * S, gn.weight, gn.bias, gn.eps, silu=True, colsums=colsums)
             last = i == 3
             lowp = (_packing.BF16_TCONV and not last) or (last and delta and not ops.fp32_mode())
-            z, colsums = ops.tconv3(y, B, T, S, p["w"][i], bias=p["b"][i], residual=residual if (last and not delta) else None,
-                                    f32=not lowp, bf16=lowp, stats=True)
+            if last and delta:             # nobody normalises the delta: no statistics
+                z, colsums = ops.tconv3(y, B, T, S, p["w"][i], bias=p["b"][i], f32=not lowp, bf16=lowp), None
+            else:
+                z, colsums = ops.tconv3(y, B, T, S, p["w"][i], bias=p["b"][i], residual=residual if last else None,
+                                        f32=not lowp, bf16=lowp, stats=True)
         return z, colsums
 
     def _fwd(self, h, colsums=None):

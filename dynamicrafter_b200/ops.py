@@ -78,9 +78,10 @@ def colsum_supported(dims, N=None):
 
 
 def stats_enabled():
-    """Producer-fused GroupNorm statistics are used in the bf16 mode, outside frame-sharded temporal blocks."""
+    """Producer-fused GroupNorm statistics are used in the bf16 mode (in frame-sharded temporal blocks the per-rank sums
+    are all-reduced as integers before the apply)."""
     from .lvdm import _packing
-    return _packing.FUSED_GN_STATS and not fp32_mode() and _SHARDED_GN[0] is None
+    return _packing.FUSED_GN_STATS and not fp32_mode()
 
 
 class _StatsArena:
@@ -434,14 +435,22 @@ def _stats_from_colsums(cs, G, S, C, eps, dev):
     return stats
 
 
-def _group_norm_from_colsums(x, G, S, gamma, beta, eps, silu, cs):
-    """Producer-fused path: ONE streaming apply pass; no statistics pass over x, no finalize launch, no grid barrier."""
+def _group_norm_from_colsums(x, G, S, gamma, beta, eps, silu, cs, shard=None):
+    """Producer-fused path: ONE streaming apply pass; no statistics pass over x, no finalize launch, no grid barrier.
+    shard: the instances are spread over the ranks of a FrameShard -> the per-instance int64 sums are all-reduced first
+    (integer sums: every rank gets bit-identical statistics)."""
     C, dev = x.shape[1], x.device
     upi = S // cs.unit_rows
     assert cs.acc.shape[0] == G * upi, (cs.acc.shape, G, upi)
+    acc, stat_rows = cs.acc, 0
+    if shard is not None:
+        from .parallel import all_reduce_sums
+        acc = cs.acc.view(G, upi, 64).sum(1) if upi > 1 else cs.acc.reshape(G, 64).clone()
+        all_reduce_sums(acc, shard)
+        upi, stat_rows = 1, S * shard.world
     y = torch.empty((G * S, C), dtype=BF16, device=dev)
     check(_lib.lib().dcb_group_norm_stream_apply(ptr(x), _c_i(1 if x.dtype == BF16 else 0), _c_i(C), _c_i(G), _c_i(S),
-                                                 ptr(cs.acc), _c_i(upi), _c_f(eps), ptr(gamma), ptr(beta),
+                                                 _c_ll(stat_rows), ptr(acc), _c_i(upi), _c_f(eps), ptr(gamma), ptr(beta),
                                                  _c_i(1 if silu else 0), ptr(y), _stream()), "dcb_group_norm_stream_apply")
     return y
 
@@ -502,6 +511,8 @@ def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False
     require_cuda(x1, x2, gamma, beta)
     if _SHARDED_GN[0] is not None:
         assert x2 is None and not want_raw and want_norm
+        if colsums is not None and not fp32_mode() and x1.shape[1] % 8 == 0 and x1.is_contiguous() and colsums.fits(S, x1.shape[1]):
+            return _group_norm_from_colsums(x1, G, S, gamma, beta, eps, silu, colsums, shard=_SHARDED_GN[0])
         return _group_norm_sharded(x1, G, S, gamma, beta, eps, silu, _SHARDED_GN[0])
     if colsums is not None and (fp32_mode() or x2 is not None or want_raw or not want_norm or x1.shape[1] % 8
                                 or not x1.is_contiguous() or not colsums.fits(S, x1.shape[1])):

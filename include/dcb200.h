@@ -142,10 +142,12 @@ int dcb_group_norm_stats_from_acc(const unsigned long long* gn_acc, int units_pe
                                   float* stats, void* stream);
 /* y = silu?((x - mean) * rstd * gamma + beta) with the statistics taken from gn_acc (see dcb_tap_gemm): ONE streaming pass,
  * x fp32 or bf16 [G*S, C], y bf16; instance g owns units [g * units_per_instance, (g+1) * units_per_instance).  The
- * consumer half of the producer-fused GroupNorm.  Replaces basics.py:76-87 / openaimodel3d.py:210-236,255-266. */
-int dcb_group_norm_stream_apply(const void* x, int x_is_bf16, int C, int G, int S, const unsigned long long* gn_acc,
-                                int units_per_instance, float eps, const float* gamma, const float* beta, int silu_act,
-                                void* y_bf16, void* stream);
+ * consumer half of the producer-fused GroupNorm.  Replaces basics.py:76-87 / openaimodel3d.py:210-236,255-266.
+ * stat_rows: rows per instance the statistics in gn_acc cover (0 = S); larger than S when the instance is spread over
+ * several GPUs and gn_acc holds the all-reduced sums (frame-sharded mode). */
+int dcb_group_norm_stream_apply(const void* x, int x_is_bf16, int C, int G, int S, long long stat_rows,
+                                const unsigned long long* gn_acc, int units_per_instance, float eps, const float* gamma,
+                                const float* beta, int silu_act, void* y_bf16, void* stream);
 /* Same statistics / apply for a bf16 source (block-internal activations the producer GEMM wrote as bf16):
  * single source, C % 8 == 0. */
 int dcb_group_norm_stats_bf16(const void* x, int C, int G, int S, float eps, float* stats, void* workspace,
