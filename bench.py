@@ -260,7 +260,26 @@ def _reference_available():
     return ref_host.ref_root() is not None
 
 
+class _StdoutToStderr:
+    """The reference prints while it builds ("AE working on z of shape ..."); stdout must carry the ONE JSON line only."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def time_reference_steps(config, steps, warmup, budget_s):
+    with _StdoutToStderr():
+        return _time_reference_steps(config, steps, warmup, budget_s)
+
+
+def _time_reference_steps(config, steps, warmup, budget_s):
     """Times the UNMODIFIED reference (oracle/_ref, staged by oracle/build_ref.py) on the host cores through its own
     public API: one step = DDIMSampler.p_sample_ddim at the full workload shape (cond forward + uncond forward +
     update; no frame or branch extrapolation).  K is honoured up to a wall-clock budget; returns the per-step times

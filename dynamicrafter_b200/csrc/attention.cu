@@ -564,8 +564,11 @@ extern "C" int dcb_flash_attention(const dcb_attention_args* a, void* stream) {
     if (a->head_dim != kD) return set_error(DCB_ERR_UNSUPPORTED, "flash_attention: head_dim must be 64");
     if (a->batch < 1 || a->heads < 1 || a->nq < 1 || (a->ldq & 7) || (a->ldo & 7))
         return set_error(DCB_ERR_INVALID, "flash_attention: shape/alignment");
-    if (a->nq >= 256) {
-        // long sequences (spatial self-attention at the two finest UNet levels): tcgen05 / TMEM kernel
+    static int tc_min_nq = -1;                  // DCB_FLASH_TC_MIN_NQ: shortest sequence on the tcgen05 kernel
+    if (tc_min_nq < 0) { const char* e = getenv("DCB_FLASH_TC_MIN_NQ"); tc_min_nq = e ? atoi(e) : 129; }
+    if (a->nq >= tc_min_nq) {
+        // spatial self-attention of every UNet level with more than one query tile (2560 / 640 / 160 tokens at 320x512):
+        // tcgen05 / TMEM kernel; ragged last query / key tiles are masked (keys) and clipped by TMA (queries)
         static int use_tc = -1;                 // DCB_FLASH_TC=0 forces the mma.sync kernel (A/B testing)
         if (use_tc < 0) { const char* e = getenv("DCB_FLASH_TC"); use_tc = (e == nullptr) ? 1 : atoi(e); }
         if (use_tc) {

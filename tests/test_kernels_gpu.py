@@ -59,7 +59,7 @@ def _sdpa(q, k, v, scale):
     return torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1) @ v
 
 
-@pytest.mark.parametrize("B,H,N", [(2, 2, 200), (1, 5, 2560), (3, 1, 40), (2, 3, 640), (1, 2, 16), (2, 2, 300), (1, 1, 257),
+@pytest.mark.parametrize("B,H,N", [(2, 2, 200), (4, 20, 160), (1, 3, 130), (1, 5, 2560), (3, 1, 40), (2, 3, 640), (1, 2, 16), (2, 2, 300), (1, 1, 257),
                                    (3, 2, 256), (2, 1, 1000)])
 def test_flash_self_attention(B, H, N):
     from dynamicrafter_b200 import ops
