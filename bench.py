@@ -260,6 +260,16 @@ def _reference_available():
     return ref_host.ref_root() is not None
 
 
+def workload_name(config):
+    """config.workload, identical in both arms (the reference arm times the same step of the same workload)."""
+    from dynamicrafter_b200.configs import SAMPLER, model_params
+    sm = SAMPLER[config]
+    h, w = model_params(config)["image_size"]
+    return (f"DynamiCrafter {config} ({h * 8}x{w * 8}x16f, latent {h}x{w}), DDIM {sm['S']} {sm['timestep_spacing']} eta "
+            f"{sm['eta']}, CFG {sm['cfg']}, guidance_rescale {sm['guidance_rescale']}; 1 video per GPU; random-init weights "
+            "(1.44 B params)")
+
+
 class _StdoutToStderr:
     """The reference prints while it builds ("AE working on z of shape ..."); stdout must carry the ONE JSON line only."""
 
@@ -346,8 +356,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": n_steps,
             "warmup": warm, "steps_requested": args.steps, "ms_per_step": step_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "DynamiCrafter 512 (320x512x16f, latent 40x64), DDIM 50 uniform_trailing eta 1.0, CFG 7.5, "
-                                   "guidance_rescale 0.7; 1 video; reference default-init weights (1.44 B params); CPU"},
+            "config": {"workload": workload_name(args.config), "videos_per_gpu": 1,
+                       "parallelism": "host CPU threads (the reference has no GPU-free path other than torch CPU)",
+                       "note": "reference default-init weights; timing does not depend on the values"},
             "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -739,9 +750,7 @@ def main():
                 "vs_baseline": None,
                 "dtype": "bf16" if args.precision == "bf16" else "fp32 (bf16 hi/lo split x3 on tensor cores)",
                 "data": "synthetic",
-                "config": {"workload": f"DynamiCrafter {args.config} ({h * 8}x{w * 8}x16f, latent {h}x{w}), DDIM {sm['S']} "
-                                       f"{sm['timestep_spacing']} eta {sm['eta']}, CFG {sm['cfg']}, guidance_rescale "
-                                       f"{sm['guidance_rescale']}; 1 video per GPU; random-init weights (1.44 B params)",
+                "config": {"workload": workload_name(args.config),
                            "videos_per_gpu": B, "cuda_graph": (not args.no_graph) and (not fshard or _graph_collectives()),
                            "parallelism": (f"frame-sharded x{nf}" + (" x 2 guidance branches" if bshard else "") +
                                            f": one video, {T // nf} frames per GPU, all-to-all "
