@@ -899,6 +899,97 @@ static int launch_gn_stream_apply(const T* x, int C, int G, int S, long long sta
     return check_launch("group_norm_stream_apply");
 }
 
+// Two-source variant for the skip-concat GroupNorms of the UNet's output blocks (openaimodel3d.py:596: cat([h, hs.pop()], 1)
+// then in_layers GroupNorm): x1 [G*S, C1] and x2 [G*S, C2] are fp32 and come from two different producer GEMMs, each with
+// its own accumulator over C_i / 32-channel groups.  A group of the concatenated tensor ((C1 + C2) / 32 channels) is a
+// union of WHOLE producer groups of ONE source when C1 % cg == 0 and cg % (C_i / 32) == 0 (true for 1280+1280, 640+640,
+// 320+320; the host checks): its sums are the sums of those producer groups.  Optionally also writes the raw bf16 copy of
+// the concat (operand of the ResBlock's 1x1 skip conv).  One streaming pass, no statistics pass, no grid barrier.
+__global__ void __launch_bounds__(512)
+gn_stream_apply2_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int S, int rows_per_chunk,
+                        const unsigned long long* __restrict__ acc1, int upi1, const unsigned long long* __restrict__ acc2,
+                        int upi2, float eps, const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
+                        __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ raw) {
+    __shared__ float s_mr[kGroups * 2];
+    const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    const int C = C1 + C2;
+    const int cg = C / kGroups;
+    const int O = C >> 3;
+    const int rpp = blockDim.x / O;
+    const int my_r = tid / O, my_o = tid - my_r * O;
+    const int c0 = my_o * 8;
+    float gm[8], bt[8];
+    {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
+        gm[0] = g0.x; gm[1] = g0.y; gm[2] = g0.z; gm[3] = g0.w; gm[4] = g1.x; gm[5] = g1.y; gm[6] = g1.z; gm[7] = g1.w;
+        bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w; bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
+    }
+    pdl_launch_dependents();
+    pdl_wait();
+    if (tid < kGroups) {
+        // concat group tid = producer groups [pg0, pg0 + k) of source 1 or 2
+        const int ch0 = tid * cg;
+        const bool first = ch0 < C1;
+        const int cgs = (first ? C1 : C2) / kGroups;            // channels per producer group of that source
+        const int pg0 = (first ? ch0 : ch0 - C1) / cgs, k = cg / cgs;
+        const unsigned long long* acc = first ? acc1 : acc2;
+        const int upi = first ? upi1 : upi2;
+        long long sx = 0, sq = 0;
+        const unsigned long long* a = acc + (static_cast<size_t>(n) * upi * kGroups + pg0) * 2;
+        for (int u = 0; u < upi; ++u)
+            for (int j = 0; j < k; ++j) {
+                sx += static_cast<long long>(__ldcg(a + (static_cast<size_t>(u) * kGroups + j) * 2));
+                sq += static_cast<long long>(__ldcg(a + (static_cast<size_t>(u) * kGroups + j) * 2 + 1));
+            }
+        const double count = static_cast<double>(S) * cg;
+        const double mean = static_cast<double>(sx) * kGnFixInv / count;
+        double var = static_cast<double>(sq) * kGnFixInv / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mr[2 * tid] = static_cast<float>(mean);
+        s_mr[2 * tid + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+    __syncthreads();
+    float am[8], bm[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int g = (c0 + e) / cg;
+        am[e] = s_mr[2 * g + 1] * gm[e];
+        bm[e] = bt[e] - s_mr[2 * g] * am[e];
+    }
+    const int r0 = chunk * rows_per_chunk;
+    const int nrows = min(S, r0 + rows_per_chunk) - r0;
+    constexpr int U = kStreamU;
+    const size_t row0 = static_cast<size_t>(n) * S + r0 + my_r;
+    const bool from1 = c0 < C1;
+    const int Cs = from1 ? C1 : C2;
+    const float* src = (from1 ? x1 + c0 : x2 + (c0 - C1)) + row0 * Cs;
+    const size_t sstep = static_cast<size_t>(rpp) * Cs, dstep = static_cast<size_t>(rpp) * C;
+    __nv_bfloat16* dst = y + row0 * C + c0;
+    __nv_bfloat16* rdst = raw != nullptr ? raw + row0 * C + c0 : nullptr;
+    for (int r = my_r; r < nrows; r += rpp * U) {
+        float v[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (r + u * rpp < nrows) ld8(src + u * sstep, v[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (r + u * rpp < nrows) {
+                if (rdst != nullptr) store8(rdst + u * dstep, v[u]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float t = fmaf(v[u][e], am[e], bm[e]);
+                    v[u][e] = do_silu ? silu_fast(t) : t;
+                }
+                store8(dst + u * dstep, v[u]);
+            }
+        }
+        src += U * sstep;
+        dst += U * dstep;
+        if (rdst != nullptr) rdst += U * dstep;
+    }
+}
+
 template <typename T, typename TOut = __nv_bfloat16>
 static int launch_gn_fused(const T* x1, const T* x2, int C1, int C2, int G, int S, float eps, const float* gamma,
                            const float* beta, int silu_act, void* y, void* raw, void* workspace, unsigned* counters,
@@ -1003,6 +1094,40 @@ extern "C" int dcb_group_norm_stream_apply(const void* x, int x_is_bf16, int C, 
                                                      units_per_instance, eps, gamma, beta, silu_act, y_bf16, s);
     return launch_gn_stream_apply<float>(static_cast<const float*>(x), C, G, S, stat_rows, gn_acc, units_per_instance, eps, gamma,
                                          beta, silu_act, y_bf16, s);
+}
+
+extern "C" int dcb_group_norm_stream_apply2(const float* x1, const float* x2, int C1, int C2, int G, int S,
+                                            const unsigned long long* gn_acc1, int units_per_instance1,
+                                            const unsigned long long* gn_acc2, int units_per_instance2, float eps,
+                                            const float* gamma, const float* beta, int silu_act, void* y_bf16, void* raw_bf16,
+                                            void* stream) {
+    if (x1 == nullptr || x2 == nullptr || y_bf16 == nullptr || gn_acc1 == nullptr || gn_acc2 == nullptr || gamma == nullptr ||
+        beta == nullptr)
+        return set_error(DCB_ERR_INVALID, "group_norm_stream_apply2: null argument");
+    const int C = C1 + C2;
+    if (C1 < 1 || C2 < 1 || C % kGroups != 0 || (C1 & 7) || (C2 & 7) || C1 % kGroups != 0 || C2 % kGroups != 0 || G < 1 || S < 1 ||
+        C > kMaxC || G > 65535 || units_per_instance1 < 1 || units_per_instance2 < 1)
+        return set_error(DCB_ERR_INVALID, "group_norm_stream_apply2: C1=%d C2=%d G=%d S=%d", C1, C2, G, S);
+    const int cg = C / kGroups;
+    if (C1 % cg != 0 || cg % (C1 / kGroups) != 0 || cg % (C2 / kGroups) != 0)
+        return set_error(DCB_ERR_UNSUPPORTED, "group_norm_stream_apply2: the groups of the concatenation (%d channels) are not unions "
+                         "of whole producer groups (%d / %d channels)", cg, C1 / kGroups, C2 / kGroups);
+    const int O = C / 8;
+    if (O > 512) return set_error(DCB_ERR_UNSUPPORTED, "group_norm_stream_apply2: C=%d > 4096", C);
+    int rpp = 288 / O;
+    if (rpp < 1) rpp = 1;
+    const int threads = O * rpp;
+    const int capacity = 2 * num_sms();
+    int nch = capacity / G;
+    if (nch < 1) nch = 1;
+    int rpc = (S + nch - 1) / nch;
+    if (rpc < rpp * kStreamU) rpc = rpp * kStreamU;
+    rpc = (rpc + rpp - 1) / rpp * rpp;
+    nch = (S + rpc - 1) / rpc;
+    launch_pdl(kPdlGnStream, gn_stream_apply2_kernel, dim3(nch, G), dim3(threads), 0, static_cast<cudaStream_t>(stream), x1, x2, C1, C2,
+               S, rpc, gn_acc1, units_per_instance1, gn_acc2, units_per_instance2, eps, gamma, beta, silu_act,
+               static_cast<__nv_bfloat16*>(y_bf16), static_cast<__nv_bfloat16*>(raw_bf16));
+    return check_launch("group_norm_stream_apply2");
 }
 
 extern "C" int dcb_layer_norm(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,

@@ -227,8 +227,12 @@ class ResBlock(PackedModule, TimestepBlock):
         nf, S = h.B * h.T, h.H * h.W
         g1 = self.in_layers[0]
         has_skip_conv = "ws" in p
+        # skip: fp32 rows, or the Act of the stored skip connection (then its producer's statistics serve the GroupNorm of
+        # the concatenation where the group boundaries line up)
+        skip_cs = getattr(skip, "cs", None)
+        skip = getattr(skip, "x", skip)
         res = ops.group_norm(h.x, nf, S, g1.weight, g1.bias, g1.eps, x2=skip, silu=True, want_raw=has_skip_conv,
-                             colsums=h.cs if skip is None else None)
+                             colsums=h.cs if (skip is None or skip_cs is not None) else None, colsums2=skip_cs)
         y, raw = res if has_skip_conv else (res, None)
         # each conv also emits the column sums its consumer GroupNorm needs (fused statistics, no extra pass)
         h1, cs1 = ops.conv3x3(y, nf, h.H, h.W, p["w1"], bias=p["b1"], group_bias=emb_out, rows_per_group=rows_per_emb,
@@ -588,7 +592,7 @@ class UNetModel(PackedModule):
             hs.append(h)
         h = self._run(self.middle_block, h, emb_all, pk, ctx, shard=shard)
         for module in self.output_blocks:
-            h = self._run(module, h, emb_all, pk, ctx, skip=hs.pop().x, shard=shard)
+            h = self._run(module, h, emb_all, pk, ctx, skip=hs.pop(), shard=shard)
         g = self.out[0]
         y = ops.group_norm(h.x, b * t, hh * ww, g.weight, g.bias, g.eps, silu=True, colsums=h.cs)
         o = ops.conv3x3(y, b * t, hh, ww, pk["w_out"], bias=pk["b_out"])

@@ -505,10 +505,32 @@ def _group_norm_sharded(x1, G, S, gamma, beta, eps, silu, shard):
     return y
 
 
-def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False, want_norm=True, colsums=None):
+def _concat_groups_align(C1, C2):
+    """Can the 32 groups of cat([x1, x2]) be assembled from whole producer groups (C_i / 32 channels) of one source each?"""
+    if C1 % 32 or C2 % 32:
+        return False
+    cg = (C1 + C2) // 32
+    return C1 % cg == 0 and cg % (C1 // 32) == 0 and cg % (C2 // 32) == 0
+
+
+def group_norm(x1, G, S, gamma, beta, eps, *, x2=None, silu=True, want_raw=False, want_norm=True, colsums=None,
+               colsums2=None):
     """x1: fp32 [G*S, C1] (+ x2 [G*S, C2] concatenated on channels) -> bf16 normalised operand
-    (and/or bf16 raw copy of the concat)."""
+    (and/or bf16 raw copy of the concat).  colsums / colsums2: producer-fused statistics of x1 / x2."""
     require_cuda(x1, x2, gamma, beta)
+    if (x2 is not None and colsums is not None and colsums2 is not None and _SHARDED_GN[0] is None and not fp32_mode()
+            and want_norm and x1.dtype == F32 and x2.dtype == F32 and x1.is_contiguous() and x2.is_contiguous()
+            and x1.shape[1] % 8 == 0 and x2.shape[1] % 8 == 0 and colsums.fits(S, x1.shape[1]) and colsums2.fits(S, x2.shape[1])
+            and _concat_groups_align(x1.shape[1], x2.shape[1]) and x1.shape[1] + x2.shape[1] <= 4096):
+        C1, C2, dev = x1.shape[1], x2.shape[1], x1.device
+        y = torch.empty((G * S, C1 + C2), dtype=BF16, device=dev)
+        raw = torch.empty((G * S, C1 + C2), dtype=BF16, device=dev) if want_raw else None
+        check(_lib.lib().dcb_group_norm_stream_apply2(ptr(x1), ptr(x2), _c_i(C1), _c_i(C2), _c_i(G), _c_i(S), ptr(colsums.acc),
+                                                      _c_i(S // colsums.unit_rows), ptr(colsums2.acc),
+                                                      _c_i(S // colsums2.unit_rows), _c_f(eps), ptr(gamma), ptr(beta),
+                                                      _c_i(1 if silu else 0), ptr(y), ptr(raw), _stream()),
+              "dcb_group_norm_stream_apply2")
+        return (y, raw) if want_raw else y
     if _SHARDED_GN[0] is not None:
         assert x2 is None and not want_raw and want_norm
         if colsums is not None and not fp32_mode() and x1.shape[1] % 8 == 0 and x1.is_contiguous() and colsums.fits(S, x1.shape[1]):

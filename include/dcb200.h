@@ -148,6 +148,16 @@ int dcb_group_norm_stats_from_acc(const unsigned long long* gn_acc, int units_pe
 int dcb_group_norm_stream_apply(const void* x, int x_is_bf16, int C, int G, int S, long long stat_rows,
                                 const unsigned long long* gn_acc, int units_per_instance, float eps, const float* gamma,
                                 const float* beta, int silu_act, void* y_bf16, void* stream);
+/* Two-source variant for the GroupNorm of a channel concatenation cat([x1, x2], 1) (openaimodel3d.py:596-597: the skip
+ * connections of the UNet's output blocks): x1 [G*S, C1], x2 [G*S, C2] fp32, each with the accumulator its own producer
+ * GEMM filled.  Requires the concatenation's groups ((C1 + C2) / 32 channels) to be unions of whole producer groups of one
+ * source (C1 % cg == 0, cg % (C_i / 32) == 0), else DCB_ERR_UNSUPPORTED.  raw_bf16 (may be NULL): bf16 copy of the
+ * concatenation (operand of the ResBlock's 1x1 skip conv, openaimodel3d.py:186-189). */
+int dcb_group_norm_stream_apply2(const float* x1, const float* x2, int C1, int C2, int G, int S,
+                                 const unsigned long long* gn_acc1, int units_per_instance1,
+                                 const unsigned long long* gn_acc2, int units_per_instance2, float eps,
+                                 const float* gamma, const float* beta, int silu_act, void* y_bf16, void* raw_bf16,
+                                 void* stream);
 /* Same statistics / apply for a bf16 source (block-internal activations the producer GEMM wrote as bf16):
  * single source, C % 8 == 0. */
 int dcb_group_norm_stats_bf16(const void* x, int C, int G, int S, float eps, float* stats, void* workspace,

@@ -270,3 +270,31 @@ def test_block_transpose(Z, A, B, inner):
     res = torch.randn(Z, B, A, inner, device="cuda")
     out = ops.block_transpose(src, Z, A, B, residual=res)
     assert torch.equal(out, res + src.permute(0, 2, 1, 3).float())
+
+
+@pytest.mark.parametrize("nf,H,W,C1,C2", [(4, 10, 16, 128, 128), (2, 40, 64, 320, 320), (3, 4, 8, 64, 64)])
+def test_group_norm_concat_from_two_producers(nf, H, W, C1, C2):
+    """Skip-concat GroupNorm (openaimodel3d.py:596-597) served by the fused statistics of BOTH producers (one streaming pass)
+    vs the self-contained cooperative kernel on the same tensors; also the raw bf16 copy of the concatenation."""
+    from dynamicrafter_b200 import ops
+    torch.manual_seed(3)
+    dev = "cuda"
+    S = H * W
+    outs = []
+    for C in (C1, C2):
+        a = torch.randn(nf * S, 64, device=dev).to(torch.bfloat16)
+        w = (torch.randn(C, 9 * 64, device=dev) * (9 * 64) ** -0.5).to(torch.bfloat16)
+        x, cs = ops.conv3x3(a, nf, H, W, w, bias=torch.randn(C, device=dev), stats=True)
+        assert cs is not None
+        outs.append((x, cs))
+    (x1, cs1), (x2, cs2) = outs
+    gamma, beta = torch.randn(C1 + C2, device=dev) * 0.2 + 1.0, torch.randn(C1 + C2, device=dev) * 0.2
+    y_ref, raw_ref = ops.group_norm(x1, nf, S, gamma, beta, 1e-5, x2=x2, silu=True, want_raw=True)
+    y, raw = ops.group_norm(x1, nf, S, gamma, beta, 1e-5, x2=x2, silu=True, want_raw=True, colsums=cs1, colsums2=cs2)
+    torch.cuda.synchronize()
+    assert torch.equal(raw, raw_ref)
+    err = (y.float() - y_ref.float()).abs().max().item()
+    assert err < 2e-2 * (1 + y_ref.float().abs().max().item()), err          # bf16 outputs of two statistics paths
+    ref = F.group_norm(torch.cat([x1, x2], 1).reshape(nf, S, C1 + C2).permute(0, 2, 1), 32, gamma, beta, 1e-5)
+    ref = F.silu(ref).permute(0, 2, 1).reshape(nf * S, C1 + C2)
+    assert (y.float() - ref).abs().max().item() < 3e-2 * (1 + ref.abs().max().item())
