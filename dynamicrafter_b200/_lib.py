@@ -86,7 +86,7 @@ EXPORTS = [
     "dcb_timestep_embedding", "dcb_small_linear", "dcb_ddim_update", "dcb_ddim_update_multicond", "dcb_video_to_uint8",
     "dcb_split_bf16x3", "dcb_geglu_f32", "dcb_attention_f32", "dcb_group_norm_fused_f32out", "dcb_layer_norm_f32out",
     "dcb_nchw_to_rows_f32out", "dcb_upsample2x_f32out", "dcb_space_to_depth_f32out",
-    "dcb_q_sample", "dcb_vae_attention", "dcb_group_norm_stream_apply", "dcb_block_transpose", "dcb_group_norm_stream_apply2",
+    "dcb_q_sample", "dcb_vae_attention", "dcb_group_norm_stream_apply", "dcb_block_transpose", "dcb_group_norm_stream_apply2", "dcb_sds_grad",
 ]
 
 

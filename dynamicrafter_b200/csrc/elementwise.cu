@@ -292,6 +292,86 @@ ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ e_c, c
     *reinterpret_cast<float4*>(pred_x0 + i4) = make_float4(x0[0], x0[1], x0[2], x0[3]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// SDS guidance (guidance_pipeline.py:326-424): the second consumer of apply_model.  From the two predictions at the noisy
+// latents:  pred = u + s (c - u)  [+ guidance rescale, :326-345]  ->  x0 = (noisy - sqrt(1 - a_t) pred) / sqrt(a_t) (:392)
+// ->  diff = latents - x0  ->  grad = w diff with w = 1 - a_t ("t"), 1 ("uniform") or 1 / clamp(mean |diff|, 1e-4)
+// ("ada") (:395-408)  ->  nan_to_num  ->  target = latents - grad, loss = 0.5 mean((latents - target)^2) / B (:417-419).
+// Every step an explicitly rounded fp32 op in the reference's order.  Per-sample coefficients live on the device
+// (timesteps differ per sample).  Two launches: differences (+ per-sample mean |diff| for "ada"), then the gradient and
+// the per-sample sums of squares of the loss.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sds_diff_kernel(const float* __restrict__ latents, const float* __restrict__ noisy, const float* __restrict__ e_c,
+                const float* __restrict__ e_u, const float* __restrict__ stds, const float* __restrict__ sqrt_a,
+                const float* __restrict__ sqrt_1ma, long long per_sample, long long total, float cfg_scale, int use_cfg,
+                float guidance_rescale, float* __restrict__ diff) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= total) return;
+    const int b = static_cast<int>(i / per_sample);
+    float mo = e_c[i];
+    if (use_cfg) {
+        const float u = e_u[i];
+        mo = __fadd_rn(u, __fmul_rn(cfg_scale, __fsub_rn(mo, u)));
+        if (guidance_rescale > 0.f) {
+            const float resc = __fmul_rn(mo, __fdiv_rn(stds[2 * b], stds[2 * b + 1]));
+            mo = __fadd_rn(__fmul_rn(guidance_rescale, resc), __fmul_rn(__fsub_rn(1.0f, guidance_rescale), mo));
+        }
+    }
+    const float x0 = __fdiv_rn(__fsub_rn(noisy[i], __fmul_rn(sqrt_1ma[b], mo)), sqrt_a[b]);
+    diff[i] = __fsub_rn(latents[i], x0);
+}
+
+// one block per sample: mean |diff| (double accumulation) -> 1 / clamp(mean, 1e-4) is applied by the caller as a divisor
+__global__ void __launch_bounds__(1024)
+sds_mean_abs_kernel(const float* __restrict__ diff, long long per_sample, float* __restrict__ mean_abs) {
+    __shared__ double red[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* p = diff + b * per_sample;
+    double a = 0.0;
+    for (long long i = tid; i < per_sample; i += blockDim.x) a += fabs(static_cast<double>(p[i]));
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) red[warp] = a;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+        mean_abs[b] = static_cast<float>(t / per_sample);
+    }
+}
+
+// grad = weight(diff), nan_to_num, loss partial: one block per (sample, slice); sumsq[b] += sum (latents - (latents - grad))^2
+__global__ void __launch_bounds__(256)
+sds_grad_kernel(const float* __restrict__ latents, const float* __restrict__ diff, const float* __restrict__ w_t,
+                const float* __restrict__ mean_abs, int weight_type, long long per_sample, long long total,
+                float* __restrict__ grad, double* __restrict__ sumsq) {
+    __shared__ double red[8];
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    double sq = 0.0;
+    int b = 0;
+    if (i < total) {
+        b = static_cast<int>(i / per_sample);
+        float g = diff[i];
+        if (weight_type == 0) g = __fmul_rn(w_t[b], g);
+        else if (weight_type == 1) g = __fdiv_rn(g, fmaxf(mean_abs[b], 1e-4f));
+        if (g != g) g = 0.f;                                               // torch.nan_to_num defaults
+        else if (isinf(g)) g = g > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+        grad[i] = g;
+        const float l = latents[i];
+        const float d = __fsub_rn(l, __fsub_rn(l, g));
+        sq = static_cast<double>(d) * static_cast<double>(d);
+    }
+    // a block never straddles two samples when per_sample % 256 == 0 (checked by the host); fixed-order reduction
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        sumsq[blockIdx.x] = t;                                             // per-block partial, summed by the host in order
+    }
+}
+
 // y = gelu(x) (exact erf, nn.GELU default; resampler.py:32), fp32 in -> bf16 operand of the next GEMM.
 __global__ void __launch_bounds__(256)
 gelu_bf16_kernel(const float* __restrict__ src, long long n8, __nv_bfloat16* __restrict__ dst) {
@@ -394,6 +474,26 @@ extern "C" int dcb_cast_bf16(const float* src, long long n, void* dst_bf16, void
     cast_bf16_kernel<<<blocks_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         src, n / 8, static_cast<__nv_bfloat16*>(dst_bf16));
     return check_launch("cast_bf16");
+}
+
+extern "C" int dcb_sds_grad(const float* latents, const float* noisy, const float* e_cond, const float* e_uncond, int B,
+                            long long per_sample, const float* sqrt_a, const float* sqrt_1ma, const float* w_t,
+                            float cfg_scale, float guidance_rescale, int weight_type, float* stds_ws, float* mean_abs_ws,
+                            float* diff_ws, float* grad, double* block_sumsq, void* stream) {
+    if (!latents || !noisy || !e_cond || !sqrt_a || !sqrt_1ma || !w_t || !stds_ws || !mean_abs_ws || !diff_ws || !grad ||
+        !block_sumsq || B < 1 || per_sample < 256 || (per_sample & 255) || weight_type < 0 || weight_type > 2)
+        return set_error(DCB_ERR_INVALID, "sds_grad: bad argument (per_sample must be a multiple of 256)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int use_cfg = e_uncond != nullptr ? 1 : 0;
+    if (use_cfg && guidance_rescale > 0.f)
+        cfg_std_kernel<<<B, 1024, 0, s>>>(e_cond, e_uncond, nullptr, per_sample, cfg_scale, 0.f, stds_ws);
+    const long long total = static_cast<long long>(B) * per_sample;
+    sds_diff_kernel<<<blocks_for(total, 256), 256, 0, s>>>(latents, noisy, e_cond, e_uncond, stds_ws, sqrt_a, sqrt_1ma, per_sample,
+                                                          total, cfg_scale, use_cfg, guidance_rescale, diff_ws);
+    if (weight_type == 1) sds_mean_abs_kernel<<<B, 1024, 0, s>>>(diff_ws, per_sample, mean_abs_ws);
+    sds_grad_kernel<<<blocks_for(total, 256), 256, 0, s>>>(latents, diff_ws, w_t, mean_abs_ws, weight_type, per_sample, total, grad,
+                                                          block_sumsq);
+    return check_launch("sds_grad");
 }
 
 extern "C" int dcb_block_transpose(const void* src, void* dst, int Z, int A, int B, long long inner_bytes,

@@ -861,6 +861,27 @@ def ddim_update(x, e_cond, e_uncond, noise, coeffs, e_uncond_img=None, cfg_img=N
     return x_prev, pred
 
 
+def sds_grad(latents, noisy, e_cond, e_uncond, sqrt_a, sqrt_1ma, w_t, cfg_scale, guidance_rescale, weight_type):
+    """SDS gradient + loss value (dcb_sds_grad).  fp32 [B, ...] tensors; sqrt_a / sqrt_1ma / w_t: fp32 [B].
+    Returns (grad like latents, loss as a 0-dim fp64 tensor = 0.5 * mean((latents - (latents - grad))^2) / B)."""
+    require_cuda(latents, noisy, e_cond, e_uncond)
+    B = latents.shape[0]
+    per = latents.numel() // B
+    dev = latents.device
+    f = lambda v: v.to(device=dev, dtype=F32).reshape(B).contiguous()
+    sa, s1, wt = f(sqrt_a), f(sqrt_1ma), f(w_t)
+    grad = torch.empty_like(latents)
+    stds = torch.empty(2 * B, dtype=F32, device=dev)
+    mabs = torch.empty(B, dtype=F32, device=dev)
+    diff = torch.empty_like(latents)
+    part = torch.empty(B * per // 256, dtype=torch.float64, device=dev)
+    check(_lib.lib().dcb_sds_grad(ptr(latents), ptr(noisy), ptr(e_cond), ptr(e_uncond), _c_i(B), _c_ll(per), ptr(sa), ptr(s1),
+                                  ptr(wt), _c_f(cfg_scale), _c_f(guidance_rescale), _c_i(weight_type), ptr(stds), ptr(mabs),
+                                  ptr(diff), ptr(grad), ptr(part), _stream()), "dcb_sds_grad")
+    loss = 0.5 * part.sum() / (B * per) / B
+    return grad, loss
+
+
 def q_sample(x0, noise, a, c):
     """out[b] = a[b] * x0[b] + c[b] * noise[b]; a, c: fp32 [B] (forward diffusion of clean latents)."""
     require_cuda(x0, noise)                 # a, c: tiny per-sample coefficient vectors, host or device

@@ -230,6 +230,19 @@ int dcb_rows_to_nchw(const float* src, int ld, int B, int C, int T, int HW, floa
 int dcb_upsample2x(const float* src, int nf, int H, int W, int C, void* dst_bf16, void* stream);
 int dcb_space_to_depth(const float* src, int nf, int H, int W, int C, void* dst_bf16, void* stream);
 int dcb_cast_bf16(const float* src, long long n, void* dst_bf16, void* stream);
+/* SDS guidance gradient (guidance_pipeline.py:326-424), the second consumer of apply_model: from the cond / uncond
+ * predictions at noisy = sqrt(a_t) latents + sqrt(1 - a_t) noise (dcb_q_sample):
+ *   pred = e_u + s (e_c - e_u), optionally guidance-rescaled (:326-345; guidance_rescale = 0.7 for the 512 / 1024 models);
+ *   x0 = (noisy - sqrt_1ma[b] pred) / sqrt_a[b] (:392);  diff = latents - x0;
+ *   grad = w_t[b] diff (weight_type 0, "t": w = 1 - a_t) | diff / clamp(mean |diff|, 1e-4) (1, "ada") | diff (2, "uniform");
+ *   nan_to_num (:410); block_sumsq[k] = partial sums of (latents - (latents - grad))^2 over 256-element blocks, from which
+ *   loss = 0.5 * sum / (B * per_sample) / B (:417-419).
+ * fp32 contiguous [B, per_sample] tensors, per_sample % 256 == 0; e_uncond NULL = no guidance.  Workspaces: stds_ws [2B],
+ * mean_abs_ws [B], diff_ws [B * per_sample] floats; block_sumsq [B * per_sample / 256] doubles. */
+int dcb_sds_grad(const float* latents, const float* noisy, const float* e_cond, const float* e_uncond, int B,
+                 long long per_sample, const float* sqrt_a, const float* sqrt_1ma, const float* w_t, float cfg_scale,
+                 float guidance_rescale, int weight_type, float* stds_ws, float* mean_abs_ws, float* diff_ws, float* grad,
+                 double* block_sumsq, void* stream);
 /* Batched block transpose src [Z, A, B, inner_bytes] -> dst [Z, B, A, inner_bytes] (16-byte multiples): the frame <-> pixel
  * re-ordering on either side of the all-to-all of the frame-sharded mode (parallel.py).  With
  * residual_f32 != NULL the source holds bf16 values and out_f32[dst order] = residual_f32[dst order] + src (dst unused):

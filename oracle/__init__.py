@@ -16,6 +16,8 @@ weights read straight out of a ``state_dict``) of the reference algorithm:
 * ``vae_oracle.encode``             <- lvdm/models/autoencoder.py:97-102, ae_modules.py:438-463
 * ``resampler_oracle.resampler_forward`` <- lvdm/modules/encoders/resampler.py:48-145
 * ``output_oracle.video_to_uint8``  <- scripts/evaluation/inference.py:153-159
+* ``sds_oracle.sds_target`` (+ ``sample_timestep``, ``add_noise``, ``apply_guidance_rescale``)
+                                    <- guidance_pipeline.py:273-424 (SDS guidance core)
 
 Parity pin: the reference ships no tests or golden vectors, so
 the oracle is pinned against outputs of the reference itself, imported in the

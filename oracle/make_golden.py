@@ -348,6 +348,63 @@ def golden_resampler():
     print("resampler_tiny y std", float(y.std()), tuple(y.shape))
 
 
+def golden_sds():
+    """SDS guidance core: the unmodified DynamiCrafterGuidancePipeline._sds_loss / _add_noise /
+    _sample_timestep (guidance_pipeline.py:273-424) on a deterministic mock denoiser.  The module imports omegaconf,
+    matplotlib and (through scripts.evaluation.funcs) decord at top level: absent here -> empty stub modules; the object
+    is created without __init__ (which would download a checkpoint) and given exactly the attributes the methods read."""
+    for name in ("omegaconf", "matplotlib", "matplotlib.pyplot", "decord"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["omegaconf"].OmegaConf = object
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["decord"].VideoReader = object
+    sys.modules["decord"].cpu = lambda *a, **k: None
+    import torch.nn.functional as F
+    import guidance_pipeline as gp
+    out = {}
+    shape = (2, 4, 16, 8, 8)
+    for tag, yml, res in (("c2", "inference_512_v1.0.yaml", (320, 512)), ("c1", "inference_256_v1.0.yaml", (256, 256))):
+        model, _ = build_lvd(TINY_UNET_256 if "256" in yml else TINY_UNET, TINY_VAE, yml, 21)
+        model.apply_model = lambda x, t, c, **kw: torch.tanh(0.3 * x + c)
+        p = object.__new__(gp.DynamiCrafterGuidancePipeline)
+        p.device, p.resolution, p.model, p.debug_enabled = torch.device("cpu"), res, model, False
+        torch.manual_seed(5)
+        ts = [p._sample_timestep(2) for _ in range(3)]
+        out[f"{tag}_timesteps_seed5"] = torch.stack(ts)
+        for wt in ("t", "ada", "uniform"):
+            latents = synth_input("sds_latents_" + wt, shape, 71).requires_grad_(True)
+            t_fixed = torch.tensor([439, 79] if tag == "c2" else [501, 101], dtype=torch.long)
+            p._sample_timestep = lambda b, lo=0.02, hi=0.98, _t=t_fixed: _t
+            rec = {}
+            real_add, real_mse = p._add_noise, F.mse_loss
+
+            def add_noise(x, n, t, _r=rec, _f=real_add):
+                _r["noise"], _r["t"] = n.clone(), t.clone()
+                return _f(x, n, t)
+
+            def mse(a, b, reduction="mean", _r=rec, _f=real_mse):
+                _r["target"] = b.clone()
+                return _f(a, b, reduction=reduction)
+
+            p._add_noise = add_noise
+            F.mse_loss = mse
+            try:
+                torch.manual_seed(9)
+                loss = p._sds_loss(latents, {"cond": torch.tensor([0.1]), "uc": torch.tensor([-0.1]), "fs": None},
+                                   cfg_scale=7.5, weight_type=wt)
+            finally:
+                F.mse_loss = real_mse
+                del p._add_noise
+            loss.backward()
+            out[f"{tag}_{wt}"] = dict(noise=rec["noise"], t=rec["t"], target=rec["target"], loss=loss.detach().clone(),
+                                      dloss=latents.grad.clone())
+            print("sds", tag, wt, float(loss), float(rec["target"].std()))
+        out[f"{tag}_alphas_cumprod"] = model.alphas_cumprod.clone()
+        out[f"{tag}_resolution"] = res
+    torch.save(out, os.path.join(OUT, "sds.pt"))
+
+
 def golden_keys():
     """state_dict key -> shape of the full-size 512 / 256 models (drop-in contract)."""
     from lvdm.modules.networks.openaimodel3d import UNetModel
