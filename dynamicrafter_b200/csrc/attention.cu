@@ -571,6 +571,12 @@ extern "C" int dcb_flash_attention(const dcb_attention_args* a, void* stream) {
         // tcgen05 / TMEM kernel; ragged last query / key tiles are masked (keys) and clipped by TMA (queries)
         static int use_tc = -1;                 // DCB_FLASH_TC=0 forces the mma.sync kernel (A/B testing)
         if (use_tc < 0) { const char* e = getenv("DCB_FLASH_TC"); use_tc = (e == nullptr) ? 1 : atoi(e); }
+        static int use_pp = -1;                 // DCB_FLASH_PP=1: ping-pong kernel (flash_pp.cu), two query tiles per CTA
+        if (use_pp < 0) { const char* e = getenv("DCB_FLASH_PP"); use_pp = (e == nullptr) ? 0 : atoi(e); }
+        if (use_tc && use_pp) {
+            const int rc = flash_pp_launch(a, static_cast<cudaStream_t>(stream));
+            if (rc != DCB_ERR_UNSUPPORTED) return rc;
+        }
         if (use_tc) {
             const int rc = flash_tc_launch(a, static_cast<cudaStream_t>(stream));
             if (rc != DCB_ERR_UNSUPPORTED) return rc;

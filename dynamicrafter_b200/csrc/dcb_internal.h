@@ -14,6 +14,7 @@ bool pdl_enabled(int cls);                        // programmatic dependent laun
 constexpr int kPdlGemm = 1, kPdlLayerNorm = 2, kPdlGroupNorm = 4, kPdlAttention = 8, kPdlGnStream = 16;
 // tcgen05 flash attention (flash_tc.cu); DCB_ERR_UNSUPPORTED if the arguments do not fit that kernel
 int flash_tc_launch(const dcb_attention_args* a, cudaStream_t stream);
+int flash_pp_launch(const dcb_attention_args* a, cudaStream_t stream);   // ping-pong variant (flash_pp.cu)
 // tcgen05 text + image cross-attention and temporal attention (attn_tc.cu); DCB_ERR_UNSUPPORTED if the arguments do not fit
 int cross_tc_launch(const dcb_attention_args* a, cudaStream_t stream);
 int temporal_tc_launch(const void* q, const void* k, const void* v, void* o, long long ldq, long long ldk, long long ldv,
