@@ -1,15 +1,17 @@
 // tcgen05 / TMEM / TMA flash attention, ping-pong variant, for the spatial self-attention of the UNet
 // (attention.py:101-125, head_dim 64).  EXPERIMENTAL (DCB_FLASH_PP=1; flash_tc.cu stays the default): parity green on all
-// flash tests (2560 / 640 / 160 / 9216 / 2304 keys, ragged tiles), but 505 TFLOP/s at 2560 keys and 535 at 9216 against
-// flash_tc's 607 / 661.  In-kernel timeline (tools/trace_flash_pp.py, gpurun r03e / r03f): a 64-key step of both sets
-// takes ~2100 clk; a softmax warp spends ~960 clk on its 64 exponentials (the MUFU pipe alone would need 512), ~300 clk
-// waiting for S and ~500 clk between the TMEM read and the rescale decision -- with 2 softmax warps per scheduler (8 per
-// SM, flash_tc: 16) the pipes are not kept busy.  Next: two threads per row (16 softmax warps) on this structure.
+// flash tests (2560 / 640 / 160 / 9216 / 2304 keys, ragged tiles), but 520 TFLOP/s at 2560 keys and 562 at 9216 against
+// flash_tc's 610 / 664.  In-kernel timeline (tools/trace_flash_pp.py, profiles/r02_flash_pp_timeline.txt, taken with one
+// thread per row): a 64-key step of both sets takes ~2100 clk; a softmax warp spends ~960 clk on its exponentials, ~300
+// clk waiting for S and ~500 clk between the TMEM read and the rescale decision.  Going from one to two threads per
+// query row (8 -> 16 softmax warps) moved 505 -> 520 TFLOP/s only, so the warps are not what is missing; the step time
+// is the same in both variants, which points at the issuing warp / barrier round trips per 64-key step.  Next: 128-key
+// steps for the MMA warp (two S sub-tiles per commit) and a timeline of the MMA warp itself.
 // Design:
 //
 //   * ONE CTA per SM works on TWO 128-query tiles ("sets" A and B) of one (batch, head) and walks over the key tiles
 //     once for both: every K_j / V_j tile is fetched once per 256 queries (half the L2 traffic of flash_tc);
-//   * two softmax groups (4 warps each, ONE thread per query row) ping-pong: group A exponentiates tile j of set A while
+//   * two softmax groups (8 warps each, two threads per query row) ping-pong: group A exponentiates tile j of set A while
 //     the tensor core computes S_j of set B and P V of the previous step -- the MUFU-bound exponential phase of one group
 //     runs under the TMEM round trips, row maxima and MMA waits of the other;
 //   * keys are processed in 64-key sub-tiles with S double buffered per set (the next scores are in TMEM before the
@@ -20,7 +22,7 @@
 //
 //   warp 0      TMA producer: Q_A, Q_B once, then {K_j, V_j} into a 3-stage ring (SWIZZLE_128B)
 //   warp 1      TMEM owner + MMA issuer, order  S_0^A S_0^B S_1^A S_1^B | P V_t^A, S_{t+2}^A | P V_t^B, S_{t+2}^B | ...
-//   warps 2..5  softmax group A, warps 6..9 group B
+//   warps 2..9  softmax of set A (two threads per query row), warps 10..17 set B
 // TMEM (512 columns): S_A 0..63 | 64..127, O_A 128..191, S_B 256..319 | 320..383, O_B 384..447.
 #include "dcb_internal.h"
 #include "ptx.cuh"
@@ -28,7 +30,7 @@
 namespace dcb {
 
 constexpr int kPTile = 128 * 128;              // 128 rows x 64 bf16 (SWIZZLE_128B)
-constexpr int kPThreads = 320;
+constexpr int kPThreads = 576;                 // TMA warp, MMA warp, 2 sets x 2 halves x 4 softmax warps
 constexpr int kPKV = 3;                        // {K, V} ring depth
 constexpr int kPSmem = 2 * kPTile + kPKV * 2 * kPTile + 2 * 2 * kPTile + 256;     // Q x2, {K,V} ring, P x2 (2 halves each)
 
@@ -129,7 +131,7 @@ flash_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
         mbar_init(q_full, 1);
         for (int i = 0; i < kPKV; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); mbar_init(&o_full[i], 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -211,44 +213,52 @@ flash_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
         }
     } else {
-        // ------------------------------------------------------------------ softmax groups: one thread per query row
+        // ------------------------------------------------------------------ softmax groups: TWO threads per query row
+        // (warps 2..5 / 6..9 = set A halves 0 / 1, warps 10..13 / 14..17 = set B): both threads find the row max of the 64
+        // scores, each exponentiates ITS 32 keys and owns 32 of the 64 O columns at the rescale / in the output.  Four
+        // softmax warps per scheduler instead of two: the softmax is latency bound, not throughput bound.
         const int q = warp & 3;                         // TMEM lane quarter
-        const int g = (warp - 2) >> 2;                  // group = set
+        const int g = (warp - 2) >> 3;                  // set
+        const int hf = ((warp - 2) >> 2) & 1;           // which 32 keys / which 32 output columns are mine
         const int r = q * 32 + lane;
         if (g < nsets) {
             const uint32_t t_set = tmem_base + g * 256 + (static_cast<uint32_t>(q * 32) << 16);
-            const uint32_t t_o = t_set + 128;
+            const uint32_t t_o = t_set + 128 + hf * 32;
             const float sl2 = p.scale_log2;
-            float m_run = -INFINITY, l_run = 0.f;
+            float m_run = -INFINITY, l_run = 0.f;       // l_run: sum over MY keys only
             for (int t = 0; t < T2; ++t) {
                 const int b = t & 1;
                 const int kmax = p.nk - t * 64;             // valid keys in this sub-tile (>= 64 unless last)
-                if (q == 2 && lane == 0) PTR(1 + g, 0, t);
+                if (q == 2 && hf == 0 && lane == 0) PTR(1 + g, 0, t);
                 mbar_wait(&s_full[g * 2 + b], (t >> 1) & 1);
                 tc_fence_after();
-                if (q == 2 && lane == 0) PTR(1 + g, 1, t);
-                uint32_t v[64];
-                {
-                    uint32_t a0[32], a1[32];
-                    tmem_ld32(t_set + b * 64, a0);
-                    tmem_ld32(t_set + b * 64 + 32, a1);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) { v[k] = a0[k]; v[32 + k] = a1[k]; }
-                }
-                if (q == 2 && lane == 0) PTR(1 + g, 2, t);
+                if (q == 2 && hf == 0 && lane == 0) PTR(1 + g, 1, t);
+                uint32_t v[32];                              // my half of the scores
                 float mx = -INFINITY;
-                if (kmax >= 64) {
+                {
+                    uint32_t w[32];                          // the other half (for the row max only)
+                    tmem_ld32(t_set + b * 64 + hf * 32, v);
+                    tmem_ld32(t_set + b * 64 + (hf ^ 1) * 32, w);
+                    tmem_ld_wait();
+                    if (q == 2 && hf == 0 && lane == 0) PTR(1 + g, 2, t);
+                    if (kmax >= 64) {
 #pragma unroll
-                    for (int k = 0; k < 64; k += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[k]), __uint_as_float(v[k + 1])));
-                } else {
+                        for (int k = 0; k < 32; k += 2) {
+                            mx = fmaxf(mx, fmaxf(__uint_as_float(v[k]), __uint_as_float(v[k + 1])));
+                            mx = fmaxf(mx, fmaxf(__uint_as_float(w[k]), __uint_as_float(w[k + 1])));
+                        }
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < 64; ++k)
-                        if (k < kmax) mx = fmaxf(mx, __uint_as_float(v[k]));
+                        for (int k = 0; k < 32; ++k) {
+                            if (hf * 32 + k < kmax) mx = fmaxf(mx, __uint_as_float(v[k]));
+                            if ((hf ^ 1) * 32 + k < kmax) mx = fmaxf(mx, __uint_as_float(w[k]));
+                        }
+                    }
                 }
                 // P buffer b was read by P V_{t-2}: that MMA must have retired before the buffer is rewritten
                 if (t >= 2) mbar_wait(&o_full[g * 2 + b], ((t >> 1) - 1) & 1);
-                // lazy rescale: keep the stale reference until the true max is more than 2^8 above it
+                // lazy rescale: keep the stale reference until the true max is more than 2^8 above it (both threads of a
+                // row see the same maximum and take the same decision)
                 const bool upd = (mx - m_run) * sl2 > 8.0f;                    // first tile: m_run = -inf -> true
                 if (__any_sync(0xffffffffu, upd)) {
                     const float m_new = upd ? mx : m_run;
@@ -259,53 +269,53 @@ flash_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         mbar_wait(&o_full[g * 2 + (b ^ 1)], ((t - 1) >> 1) & 1);
                         tc_fence_after();
                         l_run *= alpha;
+                        uint32_t o[32];
+                        tmem_ld32(t_o, o);
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            uint32_t o[32];
-                            tmem_ld32(t_o + c * 32, o);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                            pp_tmem_st32(t_o + c * 32, o);
-                        }
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        pp_tmem_st32(t_o, o);
                         pp_tmem_st_wait();
                     }
                 }
-                if (q == 2 && lane == 0) PTR(1 + g, 3, t);
+                if (q == 2 && hf == 0 && lane == 0) PTR(1 + g, 3, t);
                 const float msc = m_run * sl2;
                 float rs = 0.f;
                 uint8_t* const prow = sP + (g * 2 + b) * kPTile + r * 128;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {               // 8 keys = one 16-byte chunk of the bf16 row
+                for (int c = 0; c < 4; ++c) {               // 8 keys = one 16-byte chunk of the bf16 row
                     float e[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         e[i] = pp_ex2(fmaf(__uint_as_float(v[c * 8 + i]), sl2, -msc));
-                        if (kmax < 64 && c * 8 + i >= kmax) e[i] = 0.f;
+                        if (kmax < 64 && hf * 32 + c * 8 + i >= kmax) e[i] = 0.f;
                     }
                     rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
                     uint4 pk;
                     pk.x = pp_pack2(e[0], e[1]); pk.y = pp_pack2(e[2], e[3]);
                     pk.z = pp_pack2(e[4], e[5]); pk.w = pp_pack2(e[6], e[7]);
-                    *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = pk;
+                    *reinterpret_cast<uint4*>(prow + (((hf * 4 + c) ^ (r & 7)) << 4)) = pk;
                 }
                 l_run += rs;
                 fence_proxy_async();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[g * 2 + b]);
-                if (q == 2 && lane == 0) PTR(1 + g, 4, t);
+                if (q == 2 && hf == 0 && lane == 0) PTR(1 + g, 4, t);
             }
-            // ---- O / l -> bf16 -> staging (this set's Q tile: every S MMA has retired) -> TMA store
+            // ---- combine the two partial row sums (through the P buffers: all P V MMAs have retired), O / l -> bf16 ->
+            // staging (this set's Q tile: every S MMA has retired) -> TMA store
             if (T2 >= 2) mbar_wait(&o_full[g * 2 + ((T2 - 2) & 1)], ((T2 - 2) >> 1) & 1);
             mbar_wait(&o_full[g * 2 + ((T2 - 1) & 1)], ((T2 - 1) >> 1) & 1);
             tc_fence_after();
-            const float inv = 1.f / l_run;
+            float* s_l = reinterpret_cast<float*>(sP + g * 2 * kPTile);          // [2 halves][128 rows]
+            s_l[hf * 128 + r] = l_run;
+            named_bar_sync(1 + g, 256);
+            const float inv = 1.f / (s_l[r] + s_l[128 + r]);
             uint8_t* orow = sQ + g * kPTile + r * 128;
-#pragma unroll
-            for (int c2 = 0; c2 < 2; ++c2) {
+            {
                 uint32_t o[32];
-                tmem_ld32(t_o + c2 * 32, o);
+                tmem_ld32(t_o, o);
                 tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -314,12 +324,12 @@ flash_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     pk.y = pp_pack2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
                     pk.z = pp_pack2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
                     pk.w = pp_pack2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + (((c2 * 4 + c) ^ (r & 7)) << 4)) = pk;
+                    *reinterpret_cast<uint4*>(orow + (((hf * 4 + c) ^ (r & 7)) << 4)) = pk;
                 }
             }
             fence_proxy_async();
-            named_bar_sync(1 + g, 128);
-            if (q == 0 && lane == 0) {
+            named_bar_sync(1 + g, 256);
+            if (q == 0 && hf == 0 && lane == 0) {
                 pp_st3(&tmO, sQ + g * kPTile, head * 64, q0 + g * 128, batch);
                 tma_store_commit();
                 tma_store_wait_all<0>();
@@ -327,7 +337,7 @@ flash_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
     }
     if (warp == 1 && lane == 0) PTR_DONE(0);
-    if ((warp == 2 || warp == 6) && lane == 0) PTR_DONE(1 + ((warp - 2) >> 2));
+    if ((warp == 2 || warp == 10) && lane == 0) PTR_DONE(1 + ((warp - 2) >> 3));
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<512>(tmem_base);
