@@ -711,6 +711,9 @@ def main():
             torch.cuda.empty_cache()
         except Exception as exc:
             replay_ms = {"error": f"{type(exc).__name__}: {exc}"}
+        # the replayed GEMMs added into the step's (already consumed) statistics accumulators: clear them again
+        ops.zero_stats_arena(dev)
+        torch.cuda.synchronize()
         host.unet.use_cuda_graph = not args.no_graph
     gemm_replay = replay_ms.get("tcgen05_gemm_conv") if isinstance(replay_ms.get("tcgen05_gemm_conv"), float) else None
     achieved = gemm_flops / (gemm_replay * 1e-3) / 1e12 if gemm_replay else achieved_ev

@@ -119,6 +119,14 @@ class stats_scope:
             ar.off, ar.active = 0, False
 
 
+def zero_stats_arena(dev):
+    """Re-zero the whole accumulator arena of a device.  Only needed by tools that re-issue statistics-emitting GEMMs
+    OUTSIDE a stats_scope (bench.py's class replay): those launches add into accumulators nobody clears afterwards."""
+    ar = _ARENAS.get(dev.index)
+    if ar is not None and ar.buf is not None:
+        ar.buf.zero_()
+
+
 def _alloc_acc(units, dev):
     return _alloc_i64(units * 64, dev).view(units, 32, 2)
 

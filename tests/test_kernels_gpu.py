@@ -91,7 +91,8 @@ def test_flash_dual_cross_attention(B, T, H, N, NT, NI):
     assert _rel(out, ref.permute(0, 2, 1, 3).reshape(nb * N, inner)) < 1e-2
 
 
-@pytest.mark.parametrize("B,L,HW,H", [(2, 16, 40, 5), (1, 16, 7, 8), (1, 4, 33, 2)])
+@pytest.mark.parametrize("B,L,HW,H", [(2, 16, 40, 5), (1, 16, 7, 8), (1, 4, 33, 2), (2, 16, 2, 2), (2, 16, 8, 1), (2, 16, 1, 2),
+                                      (2, 16, 4, 2)])
 def test_temporal_attention(B, L, HW, H):
     from dynamicrafter_b200 import ops
     inner = H * 64
