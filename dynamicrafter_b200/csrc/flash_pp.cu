@@ -1,17 +1,22 @@
 // tcgen05 / TMEM / TMA flash attention, ping-pong variant, for the spatial self-attention of the UNet
 // (attention.py:101-125, head_dim 64).  EXPERIMENTAL (DCB_FLASH_PP=1; flash_tc.cu stays the default): parity green on all
-// flash tests (2560 / 640 / 160 / 9216 / 2304 keys, ragged tiles), but 520 TFLOP/s at 2560 keys and 562 at 9216 against
-// flash_tc's 610 / 664.  In-kernel timeline (tools/trace_flash_pp.py, profiles/r02_flash_pp_timeline.txt, taken with one
-// thread per row): a 64-key step of both sets takes ~2100 clk; a softmax warp spends ~960 clk on its exponentials, ~300
-// clk waiting for S and ~500 clk between the TMEM read and the rescale decision.  Going from one to two threads per
-// query row (8 -> 16 softmax warps) moved 505 -> 520 TFLOP/s only, so the warps are not what is missing; the step time
-// is the same in both variants, which points at the issuing warp / barrier round trips per 64-key step.  Next: 128-key
-// steps for the MMA warp (two S sub-tiles per commit) and a timeline of the MMA warp itself.
+// flash tests (2560 / 640 / 160 / 9216 / 2304 keys, ragged tiles), 536 TFLOP/s at 2560 keys and 588 at 9216 against
+// flash_tc's 600 / 665.  What the variants measured (tools/trace_flash_pp.py, profiles/r02_flash_pp_timeline.txt,
+// profiles/r02_summary.md):
+//   * one MMA-issuing warp for both sets paces the CTA: a 128 x 64 x 16 tcgen05.mma takes ~90 clk to issue (32 to
+//     execute), 16 per 64-key step -> ~2100 clk; one issuer per set halves that chain (kept); separate S / P V issuers
+//     per set do not help further;
+//   * a 64-key step of both sets then still takes ~2000 clk with one OR two threads per query row (8 or 16 softmax
+//     warps; one read of every score or two), with the two groups started together or 400..1400 clk apart: the exponential
+//     phases (MUFU: 1024 clk per step), the TMEM reads (64 KB per step at ~64 B/clk) and the shared-memory traffic of the
+//     small MMAs (6 KB per 32-clk instruction) are each about half of that, none alone explains it.
+// Next: per-pipe utilisation from an ncu --set full capture of this kernel, and P kept in TMEM (tcgen05.mma with A from
+// TMEM) to take the P stores and half of the operand reads off shared memory.
 // Design:
 //
 //   * ONE CTA per SM works on TWO 128-query tiles ("sets" A and B) of one (batch, head) and walks over the key tiles
 //     once for both: every K_j / V_j tile is fetched once per 256 queries (half the L2 traffic of flash_tc);
-//   * two softmax groups (8 warps each, two threads per query row) ping-pong: group A exponentiates tile j of set A while
+//   * two softmax groups (4 warps each, ONE thread per query row) ping-pong: group A exponentiates tile j of set A while
 //     the tensor core computes S_j of set B and P V of the previous step -- the MUFU-bound exponential phase of one group
 //     runs under the TMEM round trips, row maxima and MMA waits of the other;
 //   * keys are processed in 64-key sub-tiles with S double buffered per set (the next scores are in TMEM before the
@@ -22,7 +27,7 @@
 //
 //   warp 0      TMA producer: Q_A, Q_B once, then {K_j, V_j} into a 3-stage ring (SWIZZLE_128B)
 //   warp 1      TMEM owner + MMA issuer, order  S_0^A S_0^B S_1^A S_1^B | P V_t^A, S_{t+2}^A | P V_t^B, S_{t+2}^B | ...
-//   warps 2..9  softmax of set A (two threads per query row), warps 10..17 set B
+//   warps 2..5  softmax group A, warps 6..9 group B (one thread per query row); warp 10: MMA issuer of set B
 // TMEM (512 columns): S_A 0..63 | 64..127, O_A 128..191, S_B 256..319 | 320..383, O_B 384..447.
 #include "dcb_internal.h"
 #include "ptx.cuh"
@@ -30,7 +35,7 @@
 namespace dcb {
 
 constexpr int kPTile = 128 * 128;              // 128 rows x 64 bf16 (SWIZZLE_128B)
-constexpr int kPThreads = 576;                 // TMA warp, MMA warp, 2 sets x 2 halves x 4 softmax warps
+constexpr int kPThreads = 352;                 // TMA warp, MMA issuer A, 4 + 4 softmax warps, MMA issuer B
 constexpr int kPKV = 3;                        // {K, V} ring depth
 constexpr int kPSmem = 2 * kPTile + kPKV * 2 * kPTile + 2 * 2 * kPTile + 256;     // Q x2, {K,V} ring, P x2 (2 halves each)
 
@@ -59,6 +64,7 @@ struct PpTrace {
 struct FlashPpParams {
     int nq, nk, ntiles;                        // queries = keys per (batch, head); 64-key sub-tiles
     float scale_log2;
+    int stagger_clk;                           // start delay of softmax group B (DCB_FLASH_PP_STAGGER, clocks)
 };
 
 __device__ __forceinline__ uint64_t pp_desc_mn(uint32_t smem_addr) {         // MN-major B operand (V), 8-row groups 1024 B apart
@@ -130,8 +136,8 @@ flash_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
         mbar_init(q_full, 1);
-        for (int i = 0; i < kPKV; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); mbar_init(&o_full[i], 1); }
+        for (int i = 0; i < kPKV; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], nsets); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -160,19 +166,21 @@ flash_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             __syncwarp();
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else if (warp == 1 || warp == 10) {
+        // ------------------------------------------------------------------ MMA issuers: warp 1 for set A, warp 10 for set B.
+        // A tcgen05.mma of this size (128 x 64 x 16) takes ~90 clk to ISSUE and 32 clk to execute, so the issue rate of a
+        // warp paces its set (measured: one issuer for both sets ~2100 clk per 64-key step, one per set ~1150; splitting
+        // S and P V over two more warps did not help).  tcgen05.commit tracks the MMAs of its own thread.
+        const int g = warp == 1 ? 0 : 1;
         constexpr uint32_t kIdescS = make_idesc_bf16(128, 64);
         constexpr uint32_t kIdescPV = make_idesc_bf16(128, 64) | (1u << 16);       // B (= V) is MN-major
-        // The issuing warp shares its scheduler with two softmax warps, so its instruction count is what paces the whole
-        // CTA (measured: ~1000 clk per set and step with descriptors rebuilt per MMA): every descriptor is a constant base
-        // plus a small offset in its address field (>> 4 units; all tiles lie below 256 KB).
+        // every descriptor is a constant base plus a small offset in its address field (>> 4 units; all tiles lie below 256 KB)
         const uint64_t dQ0 = make_sw128_kmajor_desc(smem_u32(sQ));                 // + g * (kPTile >> 4)
         const uint64_t dK0 = make_sw128_kmajor_desc(smem_u32(sKV));                // + st * (2 kPTile >> 4) + b * (8192 >> 4)
         const uint64_t dV0 = pp_desc_mn(smem_u32(sKV + kPTile));                   // + st * (2 kPTile >> 4) + (4 b + kk) * (2048 >> 4)
         const uint64_t dP0 = make_sw128_kmajor_desc(smem_u32(sP));                 // + (2 g + b) * (kPTile >> 4) + 2 kk
         // S_t of set g: Q_g K_t^T (64 keys) -> TMEM columns g * 256 + (t & 1) * 64 .. + 63
-        auto issue_S = [&](int t, int g) {
+        auto issue_S = [&](int t) {
             const int j = t >> 1, st = j % kPKV, b = t & 1;
             mbar_wait(&kv_full[st], (j / kPKV) & 1);
             tc_fence_after();
@@ -188,15 +196,14 @@ flash_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             __syncwarp();
         };
-        mbar_wait(q_full, 0);
-        for (int t = 0; t < 2 && t < T2; ++t)
-            for (int g = 0; g < nsets; ++g) issue_S(t, g);
-        for (int t = 0; t < T2; ++t) {
-            const int j = t >> 1, st = j % kPKV, b = t & 1;
-            for (int g = 0; g < nsets; ++g) {
+        if (g < nsets) {
+            mbar_wait(q_full, 0);
+            for (int t = 0; t < 2 && t < T2; ++t) issue_S(t);
+            for (int t = 0; t < T2; ++t) {
+                const int j = t >> 1, st = j % kPKV, b = t & 1;
                 mbar_wait(&p_full[g * 2 + b], (t >> 1) & 1);      // P_t^g written, S_t^g read, O_g rescaled if needed
                 tc_fence_after();
-                if (lane == 0) PTR(0, 5 + g, t);
+                if (lane == 0 && g == 0) PTR(0, 5 + g, t);
                 if (elect_one()) {
                     const uint64_t ad = dP0 + static_cast<uint64_t>((g * 2 + b) * (kPTile >> 4));
                     const uint64_t bd = dV0 + static_cast<uint64_t>(st * (2 * kPTile >> 4) + b * 4 * (2048 >> 4));
@@ -206,59 +213,66 @@ flash_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     umma_bf16_ss(d, ad + 4, bd + 2 * (2048 >> 4), kIdescPV, 1u);
                     umma_bf16_ss(d, ad + 6, bd + 3 * (2048 >> 4), kIdescPV, 1u);
                     umma_commit(&o_full[g * 2 + b]);
-                    if (g == nsets - 1 && (b == 1 || t == T2 - 1)) umma_commit(&kv_empty[st]);   // stage consumed by both sets
+                    if (b == 1 || t == T2 - 1) umma_commit(&kv_empty[st]);        // this set is done with the stage (count = sets)
                 }
                 __syncwarp();
-                if (t + 2 < T2) issue_S(t + 2, g);               // into the S buffer the softmax group has just drained
+                if (t + 2 < T2) issue_S(t + 2);                  // into the S buffer the softmax group has just drained
             }
         }
     } else {
-        // ------------------------------------------------------------------ softmax groups: TWO threads per query row
-        // (warps 2..5 / 6..9 = set A halves 0 / 1, warps 10..13 / 14..17 = set B): both threads find the row max of the 64
-        // scores, each exponentiates ITS 32 keys and owns 32 of the 64 O columns at the rescale / in the output.  Four
-        // softmax warps per scheduler instead of two: the softmax is latency bound, not throughput bound.
+        // ------------------------------------------------------------------ softmax groups: ONE thread per query row.  Every score is read from TMEM exactly
+        // once (TMEM reads run at ~64 B/clk per SM: 1024 clk for the two 128 x 64 fp32 tiles of a step, the same as the MUFU
+        // time of their exponentials -- reading scores twice, or O back every tile as flash_tc does, is what bounds that kernel)
         const int q = warp & 3;                         // TMEM lane quarter
-        const int g = (warp - 2) >> 3;                  // set
-        const int hf = ((warp - 2) >> 2) & 1;           // which 32 keys / which 32 output columns are mine
+        const int g = (warp - 2) >> 2;                  // group = set
         const int r = q * 32 + lane;
         if (g < nsets) {
             const uint32_t t_set = tmem_base + g * 256 + (static_cast<uint32_t>(q * 32) << 16);
-            const uint32_t t_o = t_set + 128 + hf * 32;
+            const uint32_t t_o = t_set + 128;
             const float sl2 = p.scale_log2;
-            float m_run = -INFINITY, l_run = 0.f;       // l_run: sum over MY keys only
+            float m_run = -INFINITY, l_run = 0.f;
+            if (g == 1 && p.stagger_clk > 0) {
+                // ping-pong needs the two groups in ANTI-phase (one exponentiating while the other reads TMEM / waits):
+                // identical groups started together stay in lockstep, so group B starts half a step late
+                const long long t0 = clock64();
+                while (clock64() - t0 < p.stagger_clk) __nanosleep(32);
+            }
             for (int t = 0; t < T2; ++t) {
                 const int b = t & 1;
                 const int kmax = p.nk - t * 64;             // valid keys in this sub-tile (>= 64 unless last)
-                if (q == 2 && hf == 0 && lane == 0) PTR(1 + g, 0, t);
+                if (q == 2 && lane == 0) PTR(1 + g, 0, t);
                 mbar_wait(&s_full[g * 2 + b], (t >> 1) & 1);
                 tc_fence_after();
-                if (q == 2 && hf == 0 && lane == 0) PTR(1 + g, 1, t);
-                uint32_t v[32];                              // my half of the scores
-                float mx = -INFINITY;
+                if (q == 2 && lane == 0) PTR(1 + g, 1, t);
+                uint32_t v[64];
                 {
-                    uint32_t w[32];                          // the other half (for the row max only)
-                    tmem_ld32(t_set + b * 64 + hf * 32, v);
-                    tmem_ld32(t_set + b * 64 + (hf ^ 1) * 32, w);
+                    uint32_t a0[32], a1[32];
+                    tmem_ld32(t_set + b * 64, a0);
+                    tmem_ld32(t_set + b * 64 + 32, a1);
                     tmem_ld_wait();
-                    if (q == 2 && hf == 0 && lane == 0) PTR(1 + g, 2, t);
-                    if (kmax >= 64) {
 #pragma unroll
-                        for (int k = 0; k < 32; k += 2) {
-                            mx = fmaxf(mx, fmaxf(__uint_as_float(v[k]), __uint_as_float(v[k + 1])));
-                            mx = fmaxf(mx, fmaxf(__uint_as_float(w[k]), __uint_as_float(w[k + 1])));
-                        }
-                    } else {
+                    for (int k = 0; k < 32; ++k) { v[k] = a0[k]; v[32 + k] = a1[k]; }
+                }
+                if (q == 2 && lane == 0) PTR(1 + g, 2, t);
+                float mx = -INFINITY;
+                if (kmax >= 64) {
+                    // four independent chains (a single dependent chain of 32 max3 ops costs ~200 clk of pure latency)
+                    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) {
-                            if (hf * 32 + k < kmax) mx = fmaxf(mx, __uint_as_float(v[k]));
-                            if ((hf ^ 1) * 32 + k < kmax) mx = fmaxf(mx, __uint_as_float(w[k]));
-                        }
+                    for (int k = 0; k < 64; k += 8) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            m4[u] = fmaxf(m4[u], fmaxf(__uint_as_float(v[k + 2 * u]), __uint_as_float(v[k + 2 * u + 1])));
                     }
+                    mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 64; ++k)
+                        if (k < kmax) mx = fmaxf(mx, __uint_as_float(v[k]));
                 }
                 // P buffer b was read by P V_{t-2}: that MMA must have retired before the buffer is rewritten
                 if (t >= 2) mbar_wait(&o_full[g * 2 + b], ((t >> 1) - 1) & 1);
-                // lazy rescale: keep the stale reference until the true max is more than 2^8 above it (both threads of a
-                // row see the same maximum and take the same decision)
+                // lazy rescale: keep the stale reference until the true max is more than 2^8 above it
                 const bool upd = (mx - m_run) * sl2 > 8.0f;                    // first tile: m_run = -inf -> true
                 if (__any_sync(0xffffffffu, upd)) {
                     const float m_new = upd ? mx : m_run;
@@ -269,53 +283,53 @@ flash_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         mbar_wait(&o_full[g * 2 + (b ^ 1)], ((t - 1) >> 1) & 1);
                         tc_fence_after();
                         l_run *= alpha;
-                        uint32_t o[32];
-                        tmem_ld32(t_o, o);
-                        tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        pp_tmem_st32(t_o, o);
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t o[32];
+                            tmem_ld32(t_o + c * 32, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            pp_tmem_st32(t_o + c * 32, o);
+                        }
                         pp_tmem_st_wait();
                     }
                 }
-                if (q == 2 && hf == 0 && lane == 0) PTR(1 + g, 3, t);
+                if (q == 2 && lane == 0) PTR(1 + g, 3, t);
                 const float msc = m_run * sl2;
                 float rs = 0.f;
                 uint8_t* const prow = sP + (g * 2 + b) * kPTile + r * 128;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {               // 8 keys = one 16-byte chunk of the bf16 row
+                for (int c = 0; c < 8; ++c) {               // 8 keys = one 16-byte chunk of the bf16 row
                     float e[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         e[i] = pp_ex2(fmaf(__uint_as_float(v[c * 8 + i]), sl2, -msc));
-                        if (kmax < 64 && hf * 32 + c * 8 + i >= kmax) e[i] = 0.f;
+                        if (kmax < 64 && c * 8 + i >= kmax) e[i] = 0.f;
                     }
                     rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
                     uint4 pk;
                     pk.x = pp_pack2(e[0], e[1]); pk.y = pp_pack2(e[2], e[3]);
                     pk.z = pp_pack2(e[4], e[5]); pk.w = pp_pack2(e[6], e[7]);
-                    *reinterpret_cast<uint4*>(prow + (((hf * 4 + c) ^ (r & 7)) << 4)) = pk;
+                    *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = pk;
                 }
                 l_run += rs;
                 fence_proxy_async();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[g * 2 + b]);
-                if (q == 2 && hf == 0 && lane == 0) PTR(1 + g, 4, t);
+                if (q == 2 && lane == 0) PTR(1 + g, 4, t);
             }
-            // ---- combine the two partial row sums (through the P buffers: all P V MMAs have retired), O / l -> bf16 ->
-            // staging (this set's Q tile: every S MMA has retired) -> TMA store
+            // ---- O / l -> bf16 -> staging (this set's Q tile: every S MMA has retired) -> TMA store
             if (T2 >= 2) mbar_wait(&o_full[g * 2 + ((T2 - 2) & 1)], ((T2 - 2) >> 1) & 1);
             mbar_wait(&o_full[g * 2 + ((T2 - 1) & 1)], ((T2 - 1) >> 1) & 1);
             tc_fence_after();
-            float* s_l = reinterpret_cast<float*>(sP + g * 2 * kPTile);          // [2 halves][128 rows]
-            s_l[hf * 128 + r] = l_run;
-            named_bar_sync(1 + g, 256);
-            const float inv = 1.f / (s_l[r] + s_l[128 + r]);
+            const float inv = 1.f / l_run;
             uint8_t* orow = sQ + g * kPTile + r * 128;
-            {
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
                 uint32_t o[32];
-                tmem_ld32(t_o, o);
+                tmem_ld32(t_o + c2 * 32, o);
                 tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -324,12 +338,12 @@ flash_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     pk.y = pp_pack2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
                     pk.z = pp_pack2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
                     pk.w = pp_pack2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + (((hf * 4 + c) ^ (r & 7)) << 4)) = pk;
+                    *reinterpret_cast<uint4*>(orow + (((c2 * 4 + c) ^ (r & 7)) << 4)) = pk;
                 }
             }
             fence_proxy_async();
-            named_bar_sync(1 + g, 256);
-            if (q == 0 && hf == 0 && lane == 0) {
+            named_bar_sync(1 + g, 128);
+            if (q == 0 && lane == 0) {
                 pp_st3(&tmO, sQ + g * kPTile, head * 64, q0 + g * 128, batch);
                 tma_store_commit();
                 tma_store_wait_all<0>();
@@ -337,7 +351,7 @@ flash_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
     }
     if (warp == 1 && lane == 0) PTR_DONE(0);
-    if ((warp == 2 || warp == 10) && lane == 0) PTR_DONE(1 + ((warp - 2) >> 3));
+    if ((warp == 2 || warp == 6) && lane == 0) PTR_DONE(1 + ((warp - 2) >> 2));
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<512>(tmem_base);
@@ -394,6 +408,9 @@ int flash_pp_launch(const dcb_attention_args* a, cudaStream_t stream) {
     p.nk = a->nq;
     p.ntiles = (a->nq + 63) / 64;                  // 64-key sub-tiles
     p.scale_log2 = a->softmax_scale * 1.4426950408889634f;
+    static int stagger = -1;
+    if (stagger < 0) { const char* e = getenv("DCB_FLASH_PP_STAGGER"); stagger = e ? atoi(e) : 700; }
+    p.stagger_clk = stagger;
     dim3 grid((a->nq + 255) / 256, a->heads, a->batch);
     launch_pdl(kPdlAttention, flash_pp_kernel, grid, dim3(kPThreads), kPSmem, stream, tq, tk, tv, to, p);
     return check_launch("flash_pp");

@@ -21,7 +21,8 @@ for role in range(3):
     ev += [(buf[role * 4096 + i] >> 20, role, (buf[role * 4096 + i] >> 12) & 0xff, buf[role * 4096 + i] & 0xfff) for i in range(1, n)]
 ev.sort()
 t0 = ev[0][0]
-names = {0: "start", 1: "S_ready", 2: "S_in_regs", 3: "max_done", 4: "P_done", 5: "mma_P_A", 6: "mma_P_B"}
+names = {0: "start", 1: "S_ready", 2: "S_in_regs", 3: "max_done", 4: "P_done", 5: "mma_P_A", 6: "mma_P_B",
+         7: "mma_S_begin", 8: "mma_kv_ok", 9: "mma_PV_issued", 10: "mma_S_issued"}
 print(f"{len(ev)} events, span {ev[-1][0] - t0} clk")
 for t, role, c, arg in ev[:int(os.environ.get("TRACE_LINES", "260"))]:
     print(f"{t - t0:8d} r{role} {names.get(c, c):>10s} {arg}")
