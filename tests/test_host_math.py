@@ -1,0 +1,74 @@
+"""Host-side math of the round-2 restructurings, checked on the CPU in fp32 (no kernel involved): the weight folding
+that lets the CUDA path skip a tensor or a pass must be an identity of the reference computation."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def test_upsample_fold_is_the_reference_upsample_conv():
+    """nearest-x2 + 3x3 conv (openaimodel3d.py:98-106, ae_modules.py:123-127) == four 2x2-tap phase convs of the original
+    image with the pre-summed weights of pack_conv3x3_up2 (what ops.conv3x3_up2 runs as phase GEMMs)."""
+    from dynamicrafter_b200.lvdm import _packing
+    from dynamicrafter_b200 import ops
+    torch.manual_seed(0)
+    N, C, H, W = 5, 64, 6, 7
+    x = torch.randn(2, C, H, W)
+    w = torch.randn(N, C, 3, 3) * 0.1
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, padding=1)
+    # emulate the packing in fp32 (the packer rounds to bf16 at the end: take the values before the cast)
+    sets = (((0,), (1, 2)), ((0, 1), (2,)))
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for py in range(2):
+        for px in range(2):
+            acc = 0
+            for a in range(2):
+                for b in range(2):
+                    wk = sum(w[:, :, ky, kx] for ky in sets[py][a] for kx in sets[px][b])          # [N, C]
+                    dy, dx = ops._UP2_OFFS[py][a], ops._UP2_OFFS[px][b]
+                    patch = xp[:, :, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W]                       # x[j + dy, i + dx], zero padded
+                    acc = acc + torch.einsum("bchw,nc->bnhw", patch, wk)
+            out[:, :, py::2, px::2] = acc
+    assert (out - ref).abs().max().item() < 1e-4
+    # and the packer's layout: [N, (a, b, c)] with c padded to 64
+    w4 = _packing.pack_conv3x3_up2(w)
+    assert len(w4) == 4 and w4[0].shape == (N, 4 * 64) and w4[0].dtype == torch.bfloat16
+    wk00 = w[:, :, 0, 0]                                           # phase (0,0), tap (a=0, b=0) = kernel tap (0,0) alone
+    assert torch.equal(w4[0][:, :C], wk00.to(torch.bfloat16))
+
+
+def test_layer_norm_fold_is_layernorm_then_linear():
+    """fold_layer_norm: LN(x) W^T + b == rstd * (x W'^T) - rstd * mean * rowsum(W') + b' with W' = W gamma, b' = b + W beta
+    (attention.py:242-246; what the LayerNorm-folding GEMM mode evaluates in its epilogue)."""
+    from dynamicrafter_b200.lvdm.modules.attention import _fold_ln_weights
+    torch.manual_seed(1)
+    C, N, M = 96, 40, 33
+    norm = nn.LayerNorm(C)
+    with torch.no_grad():
+        norm.weight.copy_(torch.randn(C) * 0.3 + 1.0)
+        norm.bias.copy_(torch.randn(C) * 0.3)
+    w, b = torch.randn(N, C) * C ** -0.5, torch.randn(N)
+    x = torch.randn(M, C) * 2.0 + 0.7
+    with torch.no_grad():
+        ref = F.linear(norm(x), w, b)
+        wf, bf = _fold_ln_weights(norm, w, b)
+        mean = x.mean(1, keepdim=True)
+        rstd = (x.var(1, unbiased=False, keepdim=True) + norm.eps).rsqrt()
+        got = rstd * (x @ wf.t()) - rstd * mean * wf.sum(1)[None, :] + bf
+    assert (got - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("C1,C2,ok", [(1280, 1280, True), (640, 640, True), (320, 320, True), (1280, 640, False),
+                                      (640, 320, False), (64, 64, True), (96, 32, False)])
+def test_concat_groupnorm_group_alignment(C1, C2, ok):
+    """A group of cat([x1, x2]) must be a union of whole producer groups of ONE source for the two-source apply."""
+    from dynamicrafter_b200 import ops
+    assert ops._concat_groups_align(C1, C2) == ok
+    if ok:
+        cg = (C1 + C2) // 32
+        for g in range(32):
+            lo, hi = g * cg, (g + 1) * cg
+            assert hi <= C1 or lo >= C1                                     # never straddles the two sources
+            src_cg = (C1 if hi <= C1 else C2) // 32
+            assert (lo if hi <= C1 else lo - C1) % src_cg == 0 and cg % src_cg == 0
