@@ -153,6 +153,20 @@ template <int kM>
 __global__ void __launch_bounds__(256)
 small_linear_kernel(const float* __restrict__ a, int lda, const float* __restrict__ w, const float* __restrict__ bias,
                     int M, int N, int K, int silu_in, int silu_out, int accumulate, float* __restrict__ out, int ldo) {
+    // the (activated) input rows are staged once per block in shared memory when they fit (use_smem): without it every
+    // warp re-evaluates SiLU of the same M x K inputs for its own output column (the 20 160-column emb_layers launch spent
+    // 64 us on that instead of the 16 us its 103 MB of weights need)
+    extern __shared__ float s_a[];
+    const bool use_smem = static_cast<size_t>(M) * K * sizeof(float) <= 40960;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < M * (K >> 2); i += blockDim.x) {
+            const int m = i / (K >> 2), q = i - m * (K >> 2);
+            float4 av = __ldg(reinterpret_cast<const float4*>(a + static_cast<size_t>(m) * lda) + q);
+            if (silu_in) { av.x = silu_f(av.x); av.y = silu_f(av.y); av.z = silu_f(av.z); av.w = silu_f(av.w); }
+            reinterpret_cast<float4*>(s_a)[i] = av;
+        }
+        __syncthreads();
+    }
     const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (n >= N) return;
     float acc[kM];
@@ -164,8 +178,13 @@ small_linear_kernel(const float* __restrict__ a, int lda, const float* __restric
 #pragma unroll
         for (int m = 0; m < kM; ++m) {
             if (m < M) {
-                float4 av = __ldg(reinterpret_cast<const float4*>(a + static_cast<size_t>(m) * lda) + q);
-                if (silu_in) { av.x = silu_f(av.x); av.y = silu_f(av.y); av.z = silu_f(av.z); av.w = silu_f(av.w); }
+                float4 av;
+                if (use_smem) {
+                    av = reinterpret_cast<const float4*>(s_a)[m * (K >> 2) + q];
+                } else {
+                    av = __ldg(reinterpret_cast<const float4*>(a + static_cast<size_t>(m) * lda) + q);
+                    if (silu_in) { av.x = silu_f(av.x); av.y = silu_f(av.y); av.z = silu_f(av.z); av.w = silu_f(av.w); }
+                }
                 acc[m] += (av.x * wv.x + av.y * wv.y) + (av.z * wv.z + av.w * wv.w);
             }
         }
@@ -547,7 +566,8 @@ extern "C" int dcb_small_linear(const float* a, int lda, const float* w, const f
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     for (int m0 = 0; m0 < M; m0 += 8) {
         const int m = (M - m0) < 8 ? (M - m0) : 8;
-        small_linear_kernel<8><<<blocks_for(static_cast<long long>(N) * 32, 256), 256, 0, s>>>(
+        const size_t stage = static_cast<size_t>(m) * K * sizeof(float);
+        small_linear_kernel<8><<<blocks_for(static_cast<long long>(N) * 32, 256), 256, stage <= 40960 ? stage : 0, s>>>(
             a + static_cast<size_t>(m0) * lda, lda, w, bias, m, N, K, silu_in, silu_out, accumulate,
             out + static_cast<size_t>(m0) * ldo, ldo);
     }
