@@ -251,7 +251,10 @@ class BasicTransformerBlock(PackedModule):
                 "ln3": self.ff._ln_fold(self.norm3)}
 
     def _own_version(self):
-        return sum(q._version for q in self.parameters())          # the folds read the attention / FF weights too
+        lst = self.__dict__.get("_allp")                           # the folds read the attention / FF weights too
+        if lst is None:
+            lst = self.__dict__["_allp"] = list(self.parameters())
+        return sum([q._version for q in lst])
 
     def _ln(self, norm, x):
         return ops.layer_norm(x, norm.weight, norm.bias, norm.eps)

@@ -17,7 +17,16 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 
+try:                                       # raw handle of the current stream: ~0.3 us instead of ~16 us through the
+    _raw_stream = torch._C._cuda_getCurrentRawStream          # Stream object (an eager forward asks 2300 times)
+    _cur_device = torch._C._cuda_getDevice
+except AttributeError:                     # pragma: no cover - older / newer torch without the private accessors
+    _raw_stream = _cur_device = None
+
+
 def _stream():
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(_cur_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
