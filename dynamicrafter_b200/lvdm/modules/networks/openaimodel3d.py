@@ -515,7 +515,8 @@ class UNetModel(PackedModule):
         arrives, the main graph every call."""
         self.packed()
         shard = getattr(self, "frame_shard", None)
-        key = (tuple(x.shape), tuple(context.shape), x.dtype, self.__dict__["_packed_cache"][0])
+        key = (tuple(x.shape), tuple(context.shape), x.dtype, self.__dict__["_packed_cache"][0],
+               None if shard is None else (id(shard), shard.rank, shard.world))
         cache = self.__dict__.setdefault("_graphs", {})
         ent = cache.get(key)
         if ent is None:

@@ -1,5 +1,7 @@
 """Frame-sharded 576x1024 forward: host enqueue time (Python + launch calls, no synchronisation) against the device time of
-the same forwards -- is the eager sharded mode launch bound?  torchrun --nproc-per-node N tools/shard_host_time.py"""
+the same forwards -- is the eager sharded mode launch bound?  torchrun --nproc-per-node N tools/shard_host_time.py
+BATCH=1 at N ranks is the per-rank work of the 2N-GPU frames x N x 2 guidance-branch mode.  GRAPH=1 also times the forward
+replayed as a CUDA graph that holds the NCCL kernels (leaves with os._exit: process-group teardown hangs with such graphs)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -40,4 +42,28 @@ wall = time.perf_counter() - t0
 if rank == 0:
     print(f"SHARDHOST world={world} batch={B}: host enqueue {host_s / n * 1e3:.1f} ms / forward, device {e0.elapsed_time(e1) / n:.1f} ms / forward, "
           f"wall {wall / n * 1e3:.1f} ms", flush=True)
+if os.environ.get("GRAPH", "0") == "1":
+    from dynamicrafter_b200.lvdm import _packing
+    ref = unet(x, ts, context=ctx, fs=fs).clone()
+    _packing.GRAPH_COLLECTIVES = True
+    unet.use_cuda_graph = True
+    for _ in range(2):
+        out = unet(x, ts, context=ctx, fs=fs)
+    torch.cuda.synchronize(); dist.barrier()
+    diff = (out.float() - ref.float()).abs().max().item()
+    n = 8
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(n):
+        unet(x, ts, context=ctx, fs=fs)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if rank == 0:
+        print(f"SHARDHOST world={world} batch={B} graph: device {e0.elapsed_time(e1) / n:.1f} ms / forward, wall {wall / n * 1e3:.1f} ms, "
+              f"max |graph - eager| {diff:.3e}", flush=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(0)
 dist.destroy_process_group()
