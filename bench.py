@@ -516,11 +516,23 @@ def run_strong(host, dev, rank, world, args):
     host.unet.frame_shard = FrameShard(fgroup)
     if bgroup is not None:
         smp.branch_shard = BranchShard(bgroup)
+    from dynamicrafter_b200.parallel import LINK
+    LINK.reset()
     try:
         msN = timed(smp)
     finally:
         host.unet.frame_shard = None
         host.unet.use_cuda_graph = graph
+    # bytes handed to peers per step (host-side count of the eager collectives of the 2 + 3 steps just run), whole box
+    lt = torch.tensor([LINK.bytes / 5.0, LINK.calls / 5.0], device=dev, dtype=torch.float64)
+    dist.all_reduce(lt)
+    # every temporal block moves its bf16 operand to the pixel side and its bf16 delta back:
+    # (11, 10, 10, 8) blocks at (320, 640, 1280, 1280) channels and (1, 1/4, 1/16, 1/64) of the 72x128 pixels
+    alg = sum(nb * 2 * T * h * w * 2 * c // d for nb, c, d in ((11, 320, 1), (10, 640, 4), (10, 1280, 16), (8, 1280, 64)))
+    nvlink = {"sent_to_peers_gb_per_step": round(float(lt[0]) / 1e9, 3), "collectives_per_rank_per_step": round(float(lt[1]) / world, 1),
+              "algorithmic_gb_per_step": round(2 * alg / 1e9, 3),
+              "note": "both guidance branches; algorithmic = SURVEY 8(e): whole bf16 tensors of the 39 temporal blocks, there "
+                      "and back (3.6 GB per branch); sent = off-rank blocks only ((N-1)/N of it) + statistics + gathers"}
 
     def graph_fn():
         """The same sharded step with each rank's forward replayed as ONE CUDA graph that holds its NCCL kernels.  Run last
@@ -538,7 +550,7 @@ def run_strong(host, dev, rank, world, args):
             "mode": f"frames sharded x{nf}" + (" x 2 guidance branches" if bgroup is not None else ""),
             "ms_per_step_1gpu": round(ms1, 2), "ms_per_step": round(msN, 2), "speedup": round(ms1 / msN, 3),
             "n_gpus": world, "scaling": "strong", "timing": "CUDA events, max over ranks, 2 warm-up + 3 timed steps",
-            "_graph_fn": graph_fn}
+            "nvlink": nvlink, "_graph_fn": graph_fn}
 
 
 def _finish_with_graph_strong(line, strong, graph_fn, rank, limit_s=150.0):

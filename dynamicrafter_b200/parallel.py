@@ -9,6 +9,37 @@ import torch
 import torch.distributed as dist
 
 
+class LinkTraffic:
+    """Bytes this rank hands to its peers (what crosses NVLink), counted on the host from the tensors given to each
+    collective of this module: all-to-all = the off-diagonal blocks, all-gather = one copy per peer, all-reduce = the
+    ring figure 2 (N-1)/N.  `bench.py` reports it per forward next to the algorithmic figure of SURVEY.md 8(e).  Counts
+    calls as they are ENQUEUED (a replayed CUDA graph does not pass through here)."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.bytes, self.calls = 0, 0
+
+    def add(self, tensor_bytes, world, kind):
+        if world <= 1:
+            return
+        if kind == "all_to_all":
+            self.bytes += tensor_bytes * (world - 1) // world
+        elif kind == "all_gather":
+            self.bytes += tensor_bytes * (world - 1)
+        else:
+            self.bytes += 2 * tensor_bytes * (world - 1) // world
+        self.calls += 1
+
+
+LINK = LinkTraffic()
+
+
+def _nbytes(t):
+    return t.numel() * t.element_size()
+
+
 def shard_range(n_items, rank, world):
     """Contiguous, balanced split of `n_items` work units (videos) over `world` ranks -> (start, stop)."""
     base, extra = divmod(n_items, world)
@@ -69,6 +100,7 @@ def frames_to_pixels(x, B, T_loc, HW, shard):
     send = x.reshape(B, T_loc, N, HW // N, C).permute(2, 0, 1, 3, 4).contiguous()        # [dst, b, t_loc, p, c]
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=shard.group)                                 # [src, b, t_loc, p, c]
+    LINK.add(_nbytes(send), N, "all_to_all")
     return recv.permute(1, 0, 2, 3, 4).reshape(B * N * T_loc * (HW // N), C)              # (b, (src t_loc), p_loc)
 
 
@@ -79,6 +111,7 @@ def pixels_to_frames(x, B, T, HW_loc, shard):
     send = x.reshape(B, N, T_loc, HW_loc, C).permute(1, 0, 2, 3, 4).contiguous()          # [dst, b, t_loc, p_loc, c]
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=shard.group)                                 # [src = pixel block, ...]
+    LINK.add(_nbytes(send), N, "all_to_all")
     return recv.permute(1, 2, 0, 3, 4).reshape(B * T_loc * N * HW_loc, C)                 # (b, t_loc, (src p_loc))
 
 
@@ -101,6 +134,7 @@ def frames_to_pixels_v2(y, B, T_loc, HW, shard):
     sv, rv = send.view(-1), recv.view(-1)
     for b in range(B):
         dist.all_to_all_single(rv[b * per:(b + 1) * per], sv[b * per:(b + 1) * per], group=shard.group)
+        LINK.add(per * send.element_size(), N, "all_to_all")
     return recv.view(B * N * T_loc * (HW // N), C)                   # [b][src][t_loc][p_loc] = rows (b, t, p_loc)
 
 
@@ -116,6 +150,7 @@ def pixels_to_frames_add(delta, x, B, T, HW_loc, shard):
     sv, rv = delta.view(-1), recv.view(-1)
     for b in range(B):
         dist.all_to_all_single(rv[b * per:(b + 1) * per], sv[b * per:(b + 1) * per], group=shard.group)
+        LINK.add(per * delta.element_size(), N, "all_to_all")
     if delta.dtype == torch.bfloat16:
         return ops.block_transpose(recv, B, N, T_loc, residual=x)    # [b][src][t_loc][..] -> [b][t_loc][src][..] + x
     return x + ops.block_transpose(recv, B, N, T_loc).view_as(x)      # fp32 parity mode
@@ -125,12 +160,14 @@ def all_gather_frames(local, shard):
     """local: [B, C, T_loc, H, W] (this rank's frames) -> [B, C, T, H, W] on every rank."""
     bufs = [torch.empty_like(local) for _ in range(shard.world)]
     dist.all_gather(bufs, local.contiguous(), group=shard.group)
+    LINK.add(_nbytes(local), shard.world, "all_gather")
     return torch.cat(bufs, dim=2)
 
 
 def all_reduce_sums(sums, shard):
     """In-place SUM of the GroupNorm partial (sum, sum of squares) over the ranks holding the instance."""
     dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=shard.group)
+    LINK.add(_nbytes(sums), shard.world, "all_reduce")
     return sums
 
 
@@ -152,4 +189,5 @@ class BranchShard:
         """mine: this rank's branch output -> list of all branch outputs in branch order."""
         outs = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(outs, mine.contiguous(), group=self.group)
+        LINK.add(_nbytes(mine), self.world, "all_gather")
         return outs

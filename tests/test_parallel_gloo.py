@@ -69,6 +69,11 @@ def _transpose_worker(rank, world, port, out):
     ok = ok and torch.equal(back, mine)
     nchw = full[:, t0:t1].permute(0, 3, 1, 2).reshape(B, C, t1 - t0, 2, 3).contiguous()
     ok = ok and torch.equal(all_gather_frames(nchw, shard), full.permute(0, 3, 1, 2).reshape(B, C, T, 2, 3))
+    # host-side count of what was handed to the peer: two all-to-alls (half of each tensor) + one all-gather (all of it)
+    from dynamicrafter_b200.parallel import LINK
+    ok = ok and LINK.calls == 3 and LINK.bytes == 2 * (mine.numel() * 4 // 2) + nchw.numel() * 4
+    LINK.reset()
+    ok = ok and LINK.bytes == 0 and LINK.calls == 0
     t = torch.tensor([1.0 if ok else 0.0])
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
