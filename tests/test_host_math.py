@@ -72,3 +72,46 @@ def test_concat_groupnorm_group_alignment(C1, C2, ok):
             assert hi <= C1 or lo >= C1                                     # never straddles the two sources
             src_cg = (C1 if hi <= C1 else C2) // 32
             assert (lo if hi <= C1 else lo - C1) % src_cg == 0 and cg % src_cg == 0
+
+
+@pytest.mark.filterwarnings("ignore")                  # 0 / 0 in the sigma formula at alpha_prev = alpha (S = 1000 ...)
+@pytest.mark.parametrize("method", ["uniform", "uniform_trailing", "quad"])
+def test_ddim_schedule_is_the_reference_schedule(method):
+    """Host math of S2 (make_schedule): timesteps and the sigma / alpha tables, every discretisation the reference offers
+    (utils_diffusion.py:56-92; its configs only use two of them), both parameterisations' beta tables, eta 0 and 1 --
+    bit-exact against the unmodified reference functions (oracle/_ref) and against the oracle's restatement."""
+    import numpy as np
+    from dynamicrafter_b200.lvdm.models.samplers.ddim import DDIMSampler, make_ddim_timesteps
+    from oracle.ddim_oracle import DiffusionTables, ddim_tables
+    ref_host = pytest.importorskip("oracle.ref_host")
+    ref = None
+    if ref_host.ref_root() is not None:
+        ref_host.install_shims()
+        import lvdm.models.utils_diffusion as ref
+    for zero_snr in (False, True):
+        tab = DiffusionTables(rescale_betas_zero_snr=zero_snr, parameterization="v" if zero_snr else "eps",
+                              use_dynamic_rescale=zero_snr)
+        for S in (1, 2, 10, 25, 50, 200, 1000):
+            for eta in (0.0, 1.0):
+                smp = DDIMSampler(tab)
+                if method == "uniform" and S == 1000:        # steps 1..1000 index a 1000-entry table: the reference's
+                    with pytest.raises(IndexError):           # own behaviour (utils_diffusion.py:59-61,82)
+                        smp.make_schedule(S, ddim_discretize=method, ddim_eta=eta, verbose=False)
+                    if ref is not None:
+                        with pytest.raises(IndexError):
+                            ref.make_ddim_sampling_parameters(tab.alphas_cumprod.cpu(), ref.make_ddim_timesteps(
+                                method, S, tab.num_timesteps, verbose=False), eta, verbose=False)
+                    continue
+                smp.make_schedule(S, ddim_discretize=method, ddim_eta=eta, verbose=False)
+                want = ddim_tables(tab, S, method, eta)
+                assert np.array_equal(smp.ddim_timesteps, want["timesteps"])
+                assert np.array_equal(np.asarray(smp.ddim_sigmas), np.asarray(want["sigmas"]), equal_nan=True)
+                assert np.array_equal(np.asarray(smp.ddim_alphas), np.asarray(want["alphas"]))
+                assert np.array_equal(np.asarray(smp.ddim_alphas_prev), np.asarray(want["alphas_prev"]))
+                if ref is not None:
+                    ts = ref.make_ddim_timesteps(method, S, tab.num_timesteps, verbose=False)
+                    assert np.array_equal(make_ddim_timesteps(method, S, tab.num_timesteps), ts)
+                    sig, al, alp = ref.make_ddim_sampling_parameters(tab.alphas_cumprod.cpu(), ts, eta, verbose=False)
+                    assert np.array_equal(np.asarray(smp.ddim_sigmas), np.asarray(sig), equal_nan=True)
+                    assert np.array_equal(np.asarray(smp.ddim_alphas), np.asarray(al))
+                    assert np.array_equal(np.asarray(smp.ddim_alphas_prev), np.asarray(alp))
