@@ -115,3 +115,59 @@ def test_ddim_schedule_is_the_reference_schedule(method):
                     assert np.array_equal(np.asarray(smp.ddim_sigmas), np.asarray(sig), equal_nan=True)
                     assert np.array_equal(np.asarray(smp.ddim_alphas), np.asarray(al))
                     assert np.array_equal(np.asarray(smp.ddim_alphas_prev), np.asarray(alp))
+
+
+def _ref_host_or_skip():
+    ref_host = pytest.importorskip("oracle.ref_host")
+    if ref_host.ref_root() is None:
+        pytest.skip("reference sources not staged (oracle/build_ref.py)")
+    return ref_host
+
+
+@pytest.mark.parametrize("name", ["256", "512", "1024"])
+def test_config_tables_are_the_reference_yaml(name):
+    """configs.MODEL_PARAMS restates configs/inference_{256,512,1024}_v1.0.yaml: every hyper-parameter it carries equals
+    the YAML's value (UNet kwargs, VAE ddconfig, schedule, parameterisation, rescale switches)."""
+    ref_host = _ref_host_or_skip()
+    from dynamicrafter_b200.configs import MODEL_PARAMS
+    mp = ref_host.load_config(f"inference_{name}_v1.0.yaml").model.params
+    ours = MODEL_PARAMS[name]
+    for k, v in ours.items():
+        if k in ("unet_config", "first_stage_config"):
+            continue
+        if k == "parameterization" and k not in mp:  # the 256 YAML leaves the DDPM default (ddpm3d.py:58)
+            assert v == "eps"
+            continue
+        assert k in mp and (list(mp[k]) == list(v) if isinstance(v, list) else mp[k] == v), k
+    for k, v in ours["unet_config"]["params"].items():
+        if k == "use_checkpoint":                    # YAML: True (training); scripts/evaluation/inference.py:322 sets False
+            assert v is False
+            continue
+        assert mp.unet_config.params[k] == v, k
+    assert set(mp.unet_config.params) == set(ours["unet_config"]["params"])
+    vae = ours["first_stage_config"]["params"]
+    assert mp.first_stage_config.params.embed_dim == vae["embed_dim"]
+    assert dict(mp.first_stage_config.params.ddconfig) == vae["ddconfig"]
+
+
+@pytest.mark.parametrize("name", ["256", "512", "1024"])
+def test_diffusion_tables_are_the_reference_tables(name):
+    """DiffusionHost's schedule buffers (betas, alphas_cumprod, the v-parameterisation tables, the dynamic-rescale array)
+    equal those the reference's LatentVisualDiffusion registers (ddpm3d.py:135-189,520-527), bit for bit in fp32."""
+    ref_host = _ref_host_or_skip()
+    from oracle.make_golden import TINY_UNET, TINY_VAE
+    from dynamicrafter_b200.configs import model_params
+    from dynamicrafter_b200.host import DiffusionHost
+    ref, _ = ref_host.build_lvd(f"inference_{name}_v1.0.yaml", unet_params=TINY_UNET, vae_ddconfig=TINY_VAE)
+    mp = model_params(name)
+    mp["unet_config"]["params"] = dict(TINY_UNET)
+    mp.pop("first_stage_config")
+    ours = DiffusionHost.from_model_params(mp)
+    assert ours.num_timesteps == ref.num_timesteps and ours.parameterization == ref.parameterization
+    assert bool(ours.use_dynamic_rescale) == bool(ref.use_dynamic_rescale)
+    names = ["betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod"]
+    if ref.use_dynamic_rescale:
+        names.append("scale_arr")
+    for n in names:
+        a, b = getattr(ours, n), getattr(ref, n)
+        assert a.dtype == b.dtype == torch.float32 and torch.equal(a.cpu(), b.cpu()), n
