@@ -171,3 +171,28 @@ def test_diffusion_tables_are_the_reference_tables(name):
     for n in names:
         a, b = getattr(ours, n), getattr(ref, n)
         assert a.dtype == b.dtype == torch.float32 and torch.equal(a.cpu(), b.cpu()), n
+
+
+@pytest.mark.parametrize("name,h,w", [("256", 32, 32), ("512", 40, 64), ("1024", 72, 128)])
+def test_roofline_numerators_are_the_reference_flop_counts(name, h, w):
+    """bench.py's roofline divides configs.UNET_TFLOP / VAE_TFLOP by measured time.  Those constants are what torch's FLOP
+    counter sees when the UNMODIFIED reference UNetModel / Decoder run one forward at the benchmarked shape on the meta
+    device (conv + matmul, 2 FLOPs per MAC; B = 1, 16 frames) -- so the roofline's algorithmic work is the reference's."""
+    ref_host = _ref_host_or_skip()
+    ref_host.install_shims()
+    from torch.utils.flop_counter import FlopCounterMode
+    from lvdm.modules.networks.openaimodel3d import UNetModel
+    from lvdm.modules.networks.ae_modules import Decoder
+    from dynamicrafter_b200.configs import model_params, UNET_TFLOP, VAE_TFLOP
+    mp = model_params(name)
+    with torch.device("meta"), torch.no_grad():
+        unet = UNetModel(**mp["unet_config"]["params"]).eval()
+        x, ctx = torch.empty(1, 8, 16, h, w), torch.empty(1, 77 + 16 * 16, 1024)
+        t = torch.empty(1, dtype=torch.long)
+        with FlopCounterMode(display=False) as fc:
+            unet(x, t, context=ctx, fs=t)
+        assert abs(fc.get_total_flops() / 1e12 - UNET_TFLOP[name]) < 1e-3
+        dec = Decoder(**mp["first_stage_config"]["params"]["ddconfig"]).eval()
+        with FlopCounterMode(display=False) as fc:
+            dec(torch.empty(16, 4, h, w))
+        assert abs(fc.get_total_flops() / 1e12 - VAE_TFLOP[name]) < 1e-3
