@@ -37,7 +37,8 @@ typedef enum {
 
 const char* dcb_last_error(void);
 int dcb_abi_version(void);
-/* 0 if the current device is compute capability 10.x, DCB_ERR_DEVICE otherwise. */
+/* 0 if the current device is compute capability 10.x, DCB_ERR_DEVICE otherwise (the reference has no counterpart: it
+ * runs wherever torch does; dcb200 has no other path and says so instead of falling back). */
 int dcb_check_device(void);
 
 /* ------------------------------------------------------------------------------------------
@@ -251,8 +252,12 @@ int dcb_block_transpose(const void* src, void* dst, int Z, int A, int B, long lo
                         const float* residual_f32, float* out_f32, void* stream);
 /* y = gelu(x), exact erf (nn.GELU of the Resampler feed-forward, resampler.py:27-34); contiguous, n % 8 == 0. */
 int dcb_gelu_bf16(const float* src, long long n, void* dst_bf16, void* stream);
+/* Sinusoidal embedding out [B, dim] = [cos(t * f_i) | sin(t * f_i)], f_i = 10000^(-i / (dim / 2))
+ * (utils_diffusion.py:8-27 timestep_embedding, called at openaimodel3d.py:550,574). */
 int dcb_timestep_embedding(const long long* t, int B, int dim, float* out, void* stream);
-/* out[m,n] (+)= silu_out?( sum_k silu_in?(a[m,k]) * w[n,k] + bias[n] ); fp32, tiny M. */
+/* out[m,n] (+)= silu_out?( sum_k silu_in?(a[m,k]) * w[n,k] + bias[n] ); fp32, tiny M.  The Linear / SiLU chains on the
+ * embedding vector: time_embed and fps_embedding (openaimodel3d.py:370-381,551,575) and the emb_layers of ALL ResBlocks
+ * (openaimodel3d.py:168-174,219) as one launch over their concatenated weights. */
 int dcb_small_linear(const float* a, int lda, const float* w, const float* bias, int M, int N, int K,
                      int silu_in, int silu_out, int accumulate, float* out, int ldo, void* stream);
 
