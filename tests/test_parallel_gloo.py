@@ -116,6 +116,11 @@ def _branch_worker(rank, world, port, out):
     x = torch.zeros(1, 4, 2, 2, 2)
     outs = smp._eval_branches(x, torch.zeros(1, dtype=torch.long), [torch.tensor([1.0]), torch.tensor([-2.0])], {})
     ok = len(outs) == 2 and float(outs[0].mean()) == 1.0 and float(outs[1].mean()) == -2.0
+    # sharded single-video modes: every rank must apply the update with rank 0's draws, whatever its own seed was
+    torch.manual_seed(100 + rank)
+    noise = smp._sync_noise(torch.randn(1, 4, 2, 2, 2))
+    torch.manual_seed(100)
+    ok = ok and torch.equal(noise, torch.randn(1, 4, 2, 2, 2))
     try:                                            # three branches on two ranks must be refused
         smp._eval_branches(x, None, [torch.tensor([1.0])] * 3, {})
         ok = False
@@ -172,3 +177,62 @@ def test_precision_switch():
     import pytest
     with pytest.raises(ValueError):
         precision.set_precision("fp16")
+
+
+def _grid_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dynamicrafter_b200.parallel import BranchShard, FrameShard
+    from dynamicrafter_b200.lvdm.models.samplers.ddim import DDIMSampler
+    # the grid bench.py builds from 4 GPUs on: rank r = guidance branch r % 2 of frame shard r // 2
+    fgroup = bgroup = None
+    for br in range(2):
+        g = dist.new_group([r for r in range(world) if r % 2 == br])
+        if rank % 2 == br:
+            fgroup = g
+    for fi in range(world // 2):
+        g = dist.new_group([2 * fi, 2 * fi + 1])
+        if rank // 2 == fi:
+            bgroup = g
+
+    class _Unet:
+        frame_shard = FrameShard(fgroup)
+
+    class _Model:
+        num_timesteps = 1000
+        unet = _Unet()
+
+    smp = DDIMSampler.__new__(DDIMSampler)
+    smp.model = _Model()
+    smp.branch_shard = BranchShard(bgroup)
+    ok = smp.branch_shard.world == 2 and smp.branch_shard.rank == rank % 2
+    ok = ok and _Unet.frame_shard.world == world // 2 and _Unet.frame_shard.rank == rank // 2
+    ok = ok and _Unet.frame_shard.frames(16) == (rank // 2 * (32 // world), (rank // 2 + 1) * (32 // world))
+    torch.manual_seed(100 + rank)
+    noise = smp._sync_noise(torch.randn(1, 4, 2, 2, 2))
+    torch.manual_seed(100)
+    ok = ok and torch.equal(noise, torch.randn(1, 4, 2, 2, 2))
+    t = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(float(t))
+    dist.destroy_process_group()
+
+
+def test_branch_x_frame_grid_world4():
+    """4 ranks as 2 guidance branches x 2 frame shards: group membership, frame ranges, and rank 0's random draws reach
+    every rank through the two sub-group broadcasts."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grid_worker, args=(r, 4, port, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) == 1.0
