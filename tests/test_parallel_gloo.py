@@ -236,3 +236,58 @@ def test_branch_x_frame_grid_world4():
         p.join(180)
         assert p.exitcode == 0
     assert q.get(timeout=10) == 1.0
+
+
+def _block_transpose_torch(src, Z, A, B, residual=None):
+    """torch statement of ops.block_transpose (the CUDA kernel itself is checked in tests/test_kernels_gpu.py)."""
+    out = src.reshape(Z, A, B, -1).permute(0, 2, 1, 3).contiguous().reshape(src.shape)
+    if residual is not None:
+        return residual + out.float().view_as(residual)
+    return out
+
+
+def _v2_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dynamicrafter_b200 import ops, parallel
+    ops.block_transpose = _block_transpose_torch            # host logic only: no GPU in this test
+    shard = parallel.FrameShard()
+    B, T, HW, C = 2, 4, 6, 8
+    full = torch.arange(B * T * HW * C, dtype=torch.float32).reshape(B, T, HW, C)
+    t0, t1 = shard.frames(T)
+    p0, p1 = rank * HW // world, (rank + 1) * HW // world
+    mine = full[:, t0:t1].reshape(-1, C).clone()                                   # rows (b, t_loc, p)
+    ok = True
+    for dt in (torch.float32, torch.bfloat16):
+        parallel.LINK.reset()
+        px = parallel.frames_to_pixels_v2(mine.to(dt), B, t1 - t0, HW, shard)      # rows (b, t, p_loc)
+        ok = ok and torch.equal(px.float(), full[:, :, p0:p1].reshape(-1, C).to(dt).float())
+        resid = torch.full_like(mine, 0.5)
+        back = parallel.pixels_to_frames_add(px, resid, B, T, HW // world, shard)  # the way back + the fp32 residual add
+        ok = ok and back.dtype == torch.float32 and torch.equal(back, mine.to(dt).float() + 0.5)
+        # one all-to-all per video each way, half of every tensor leaves the rank
+        ok = ok and parallel.LINK.calls == 2 * B and parallel.LINK.bytes == 2 * (mine.numel() * px.element_size() // 2)
+    t = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(float(t))
+    dist.destroy_process_group()
+
+
+def test_frame_pixel_transposes_v2_world2():
+    """round-2 flow of the frame-sharded mode: operand to the pixel side, delta back + residual add, one all-to-all per
+    video each way (the block transposes replaced by their torch statement)."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_v2_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) == 1.0
