@@ -553,7 +553,7 @@ def run_strong(host, dev, rank, world, args):
             "nvlink": nvlink, "_graph_fn": graph_fn}
 
 
-def _finish_with_graph_strong(line, strong, graph_fn, rank, limit_s=150.0):
+def _finish_with_graph_strong(line, strong, graph_fn, rank, limit_s=75.0):
     """Last act of an N > 1 run: measure the graph-captured sharded step, print THE line, leave with os._exit.  A watchdog
     prints the line without that number and ends the process if the attempt has not returned within `limit_s` (a hung
     collective cannot be caught as an exception), so the headline numbers never depend on this auxiliary measurement."""
